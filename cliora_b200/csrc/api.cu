@@ -1,0 +1,630 @@
+// extern "C" entry points of libcliora_b200.so (declared in include/cliora_b200.h).
+// Host-side orchestration only: level loops, buffer carving, kernel launches on the caller's stream.
+#include <string.h>
+
+#include "align_kernels.cuh"
+#include "chart_kernels.cuh"
+#include "cky_kernels.cuh"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace cliora {
+thread_local char g_last_cuda_error[256] = "";
+long long g_launch_count = 0;
+
+static int validate(const cliora_dims* d) {
+  if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
+  if (d->B < 1 || d->n < 1 || d->n > 512 || d->D < 4 || (d->D % 4) != 0 || d->R < 0 || d->R > 64)
+    return CLIORA_ERR_BAD_SHAPE;
+  return CLIORA_OK;
+}
+
+static int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+static int compute_layout(const cliora_dims& d, cliora_layout& L) {
+  CL_TRY(validate(&d));
+  const int64_t B = d.B, n = d.n, D = d.D, R = d.R, C = num_cells(d.n);
+  const int64_t PI = d.share ? 3 : 4;
+  memset(&L, 0, sizeof(L));
+  L.PI = PI;
+  L.rows_in = B * inside_rows_before(d.n, d.n);
+  L.rows_out = B * outside_rows_before(d.n, d.n - 1);
+  int64_t o = 0;
+  auto take = [&](int64_t nf) { int64_t r = o; o += align4(nf > 0 ? nf : 4); return r; };
+  L.Pin = take(B * C * PI * D);
+  L.Pout = take(B * C * 2 * D);
+  L.q_in = R > 0 ? take(B * C * D) : -1;
+  L.nrm_in = take(B * C);
+  L.nrm2_in = R > 0 ? take(B * C) : -1;
+  L.att_in = R > 0 ? take(B * C * R) : -1;
+  L.nrm_out = take(B * C);
+  L.leaf_t = take(B * n * D);
+  L.Zin = take(L.rows_in * D);
+  L.Yin = take(L.rows_in * D);
+  L.Ein = take(L.rows_in);
+  L.Prin = take(L.rows_in);
+  L.Zout = take(L.rows_out * D);
+  L.Yout = take(L.rows_out * D);
+  L.Eout = take(L.rows_out);
+  L.Prout = take(L.rows_out);
+  L.Wcat_in = take(PI * D * D);
+  L.Wcat_out = take(2 * D * D);
+  L.ws_floats = o;
+
+  const int64_t max_rows = B * n * (n - 1) > 0 ? B * n * (n - 1) : 4;
+  o = 0;
+  L.Gh_in = take(B * C * D);
+  L.Gs_in = take(B * C);
+  L.GP_in = take(B * C * PI * D);
+  L.Gh_out = take(B * C * D);
+  L.Gs_out = take(B * C);
+  L.GP_out = take(B * C * 2 * D);
+  L.GA2 = R > 0 ? take(B * C * D) : -1;
+  L.coef = R > 0 ? take(B * C * 2 * R) : -1;
+  L.GE = take(max_rows);
+  L.GZ = take(max_rows * D);
+  int64_t sk = tn_scratch_floats((int)(B * C), (int)D, (int)D);
+  int64_t t;
+  if ((t = tn_scratch_floats((int)L.rows_in, (int)D, (int)D)) > sk) sk = t;
+  if ((t = tn_scratch_floats((int)L.rows_out, (int)D, (int)D)) > sk) sk = t;
+  if ((t = tn_scratch_floats((int)(B * n), (int)D, (int)D)) > sk) sk = t;
+  if ((t = 64 * PI * D) > sk) sk = t;
+  L.splitk = take(sk);
+  L.gu = take(B * n * D);
+  L.bws_floats = o;
+  return CLIORA_OK;
+}
+
+struct Ctx {
+  cliora_dims d;
+  cliora_layout L;
+  int64_t C;
+  cudaStream_t st;
+};
+
+static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
+  CL_TRY(validate(dims));
+  c.d = *dims;
+  CL_TRY(compute_layout(c.d, c.L));
+  c.C = num_cells(dims->n);
+  c.st = (cudaStream_t)stream;
+  return CLIORA_OK;
+}
+
+// C[rows of level] = act(A[rows of level] W^T + bias): chart-level projection
+static int project_level(const Ctx& c, int level, const float* chart_h, const float* Wcat, int ncols, float* P) {
+  GemmParams p{};
+  p.A = chart_h; p.lda = c.d.D; p.amap = level_rows(c.d.n, level);
+  p.W = Wcat; p.ldw = c.d.D;
+  p.C = P; p.ldc = ncols; p.cmap = level_rows(c.d.n, level);
+  p.M = c.d.B * (c.d.n - level); p.N = ncols; p.K = c.d.D;
+  return launch_gemm(c.st, /*nt=*/true, p);
+}
+
+// Gh[rows of level] += GP[rows of level] @ Wcat
+static int cellgrad_level(const Ctx& c, int level, const float* GP, int ncols, const float* Wcat, float* Gh) {
+  GemmParams p{};
+  p.A = GP; p.lda = ncols; p.amap = level_rows(c.d.n, level);
+  p.W = Wcat; p.ldw = c.d.D;
+  p.C = Gh; p.ldc = c.d.D; p.cmap = level_rows(c.d.n, level);
+  p.M = c.d.B * (c.d.n - level); p.N = c.d.D; p.K = ncols;
+  p.accumulate = 1;
+  return launch_gemm(c.st, /*nt=*/false, p);
+}
+
+static int dense_linear(cudaStream_t st, int M, int N, int K, const float* A, const float* W, const float* bias,
+                        int act, float* Cout) {
+  GemmParams p{};
+  p.A = A; p.lda = K; p.amap = dense_rows();
+  p.W = W; p.ldw = K;
+  p.C = Cout; p.ldc = N; p.cmap = dense_rows();
+  p.bias = bias; p.act = act;
+  p.M = M; p.N = N; p.K = K;
+  return launch_gemm(st, true, p);
+}
+
+static int colsum(cudaStream_t st, const float* src, int64_t ld, int64_t rows, int cols, float* dst, int accumulate,
+                  float* scratch) {
+  int S = (int)((rows + 511) / 512);
+  if (S < 1) S = 1;
+  if (S > 64) S = 64;
+  dim3 grid(ceil_div(cols, 32), S);
+  colsum_stage1_kernel<<<grid, dim3(32, 8), 0, st>>>(src, ld, rows, cols, scratch);
+  CL_CHECK_LAUNCH("colsum_stage1_kernel");
+  colsum_stage2_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(scratch, S, cols, dst, accumulate);
+  CL_CHECK_LAUNCH("colsum_stage2_kernel");
+  return CLIORA_OK;
+}
+
+static CellArgs cell_args(const Ctx& c, int level, bool outside, float* ws, float* chart_h, float* chart_s) {
+  CellArgs a{};
+  const int n = c.d.n;
+  a.B = c.d.B; a.n = n; a.level = level; a.D = c.d.D; a.R = outside ? 0 : c.d.R; a.C = c.C;
+  a.L = n - level;
+  a.chart_h = chart_h; a.chart_s = chart_s;
+  if (!outside) {
+    a.N = level == 0 ? 1 : level;
+    a.sp = a.N; a.sk = 1;
+    if (level == 0) {
+      a.Y = ws + c.L.leaf_t; a.E = nullptr; a.Pr = nullptr;
+    } else {
+      const int64_t r0 = c.d.B * inside_rows_before(n, level);
+      a.Y = ws + c.L.Yin + r0 * c.d.D; a.E = ws + c.L.Ein + r0; a.Pr = ws + c.L.Prin + r0;
+    }
+    a.q = c.d.R > 0 ? ws + c.L.q_in : nullptr;
+    a.nrm = ws + c.L.nrm_in;
+    a.nrm2 = c.d.R > 0 ? ws + c.L.nrm2_in : nullptr;
+    a.att = c.d.R > 0 ? ws + c.L.att_in : nullptr;
+  } else {
+    a.N = n - level - 1;
+    a.sp = 1; a.sk = a.L;
+    const int64_t r0 = c.d.B * outside_rows_before(n, level);
+    a.Y = ws + c.L.Yout + r0 * c.d.D; a.E = ws + c.L.Eout + r0; a.Pr = ws + c.L.Prout + r0;
+    a.q = nullptr;
+    a.nrm = ws + c.L.nrm_out;
+  }
+  return a;
+}
+
+static SplitArgs split_args(const Ctx& c, int level, bool outside, const float* ih, const float* is_,
+                            const float* os_, float* ws, const float* b1) {
+  SplitArgs s{};
+  const int n = c.d.n;
+  s.B = c.d.B; s.n = n; s.level = level; s.D = c.d.D; s.C = c.C;
+  s.L = n - level;
+  s.N = outside ? n - level - 1 : level;
+  s.ih = ih; s.is_ = is_; s.os_ = os_;
+  s.Pin = ws + c.L.Pin; s.Pout = ws + c.L.Pout;
+  s.ldPin = (int)(c.L.PI * c.d.D);
+  s.iAl = (outside && !c.d.share) ? 3 * c.d.D : 0;
+  s.b1 = b1;
+  const int64_t r0 = outside ? c.d.B * outside_rows_before(n, level) : c.d.B * inside_rows_before(n, level);
+  s.Z = ws + (outside ? c.L.Zout : c.L.Zin) + r0 * c.d.D;
+  s.E = ws + (outside ? c.L.Eout : c.L.Ein) + r0;
+  return s;
+}
+
+template <bool VL>
+static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
+  const size_t smem = (size_t)(a.D + a.N + 2 * a.R + 64) * sizeof(float);
+  cell_aggregate_kernel<VL><<<a.B * a.L, 128, smem, c.st>>>(a);
+  CL_CHECK_LAUNCH("cell_aggregate_kernel");
+  return CLIORA_OK;
+}
+
+template <bool VL>
+static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
+  const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64) * sizeof(float);
+  cell_bwd_kernel<VL><<<g.c.B * g.c.L, 256, smem, c.st>>>(g);
+  CL_CHECK_LAUNCH("cell_bwd_kernel");
+  return CLIORA_OK;
+}
+
+// shared by both passes: cell backward, GZ GEMM, scatter for one level
+template <bool OUTSIDE, bool VL>
+static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const float* ih, const float* is_,
+                     const float* os_, float* chart_h, float* chart_s, const float* obj, const uint8_t* keep,
+                     float* ws, float* bws) {
+  const int B = c.d.B, n = c.d.n, D = c.d.D;
+  CellBwdArgs g{};
+  g.c = cell_args(c, level, OUTSIDE, ws, chart_h, chart_s);
+  g.c.obj = obj; g.c.keep = keep;
+  g.Gh = bws + (OUTSIDE ? c.L.Gh_out : c.L.Gh_in);
+  g.Gs = bws + (OUTSIDE ? c.L.Gs_out : c.L.Gs_in);
+  g.GE = bws + c.L.GE;
+  g.GA2 = VL ? bws + c.L.GA2 : nullptr;
+  g.coef = VL ? bws + c.L.coef : nullptr;
+  g.leaf_t = ws + c.L.leaf_t;
+  g.gu = bws + c.L.gu;
+  // GE is level-local here: point the kernel at a level block starting at GE[0]
+  // (cell_bwd indexes GE with the same row ids as E, relative to the level block).
+  CL_TRY(launch_cell_bwd<VL>(c, g));
+  if (g.c.E == nullptr) return CLIORA_OK;  // leaf level: no splits
+
+  const float* W2 = (OUTSIDE && !c.d.share) ? w->oW2 : w->W2;
+  const float* b1 = (OUTSIDE && !c.d.share) ? w->ob1 : w->b1;
+  SplitArgs s = split_args(c, level, OUTSIDE, ih, is_, os_, ws, b1);
+  const int64_t rows = (int64_t)B * s.L * s.N;
+  GemmParams p{};
+  p.A = g.c.Y; p.lda = D; p.amap = dense_rows();
+  p.W = W2; p.ldw = D;
+  p.C = bws + c.L.GZ; p.ldc = D; p.cmap = dense_rows();
+  p.mask = s.Z; p.ldm = D;
+  p.M = (int)rows; p.N = D; p.K = D;
+  CL_TRY(launch_gemm(c.st, /*nt=*/false, p));
+
+  ScatterArgs sc{};
+  sc.s = s;
+  sc.GZ = bws + c.L.GZ; sc.GE = bws + c.L.GE;
+  sc.Gh_in = bws + c.L.Gh_in; sc.Gs_in = bws + c.L.Gs_in; sc.GP_in = bws + c.L.GP_in;
+  sc.Gs_out = bws + c.L.Gs_out; sc.GP_out = bws + c.L.GP_out;
+  split_scatter_kernel<OUTSIDE><<<ceil_div(rows, 8), 256, 0, c.st>>>(sc);
+  CL_CHECK_LAUNCH("split_scatter_kernel");
+  (void)n;
+  return CLIORA_OK;
+}
+
+}  // namespace cliora
+
+using namespace cliora;
+
+extern "C" {
+
+const char* cliora_status_string(int s) {
+  switch (s) {
+    case CLIORA_OK: return "ok";
+    case CLIORA_ERR_BAD_SHAPE: return "bad shape (need B>=1, 1<=n<=512, D%4==0, 0<=R<=64)";
+    case CLIORA_ERR_NULL_POINTER: return "required pointer is NULL";
+    case CLIORA_ERR_CUDA: return "CUDA error";
+    case CLIORA_ERR_NO_DEVICE: return "no CUDA device";
+    case CLIORA_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+const char* cliora_last_cuda_error(void) { return g_last_cuda_error; }
+int cliora_abi_version(void) { return 1; }
+int64_t cliora_launch_count(void) { return g_launch_count; }
+
+int64_t cliora_num_cells(int n) { return num_cells(n); }
+int64_t cliora_level_offset(int n, int level) { return lvl_off(n, level); }
+
+int cliora_inside_index(int n, int level, int64_t* left, int64_t* right) {
+  if (left == nullptr || right == nullptr) return CLIORA_ERR_NULL_POINTER;
+  if (n < 1 || level < 1 || level >= n) return CLIORA_ERR_BAD_SHAPE;
+  int64_t i = 0;
+  for (int p = 0; p < n - level; ++p)
+    for (int k = 0; k < level; ++k, ++i) {
+      int l, r;
+      inside_children(n, level, p, k, l, r);
+      left[i] = l;
+      right[i] = r;
+    }
+  return CLIORA_OK;
+}
+
+int cliora_outside_index(int n, int level, int64_t* parent, int64_t* sibling) {
+  if (parent == nullptr || sibling == nullptr) return CLIORA_ERR_NULL_POINTER;
+  if (n < 1 || level < 0 || level >= n - 1) return CLIORA_ERR_BAD_SHAPE;
+  const int L = n - level, N = L - 1;
+  for (int k = 0; k < N; ++k)
+    for (int p = 0; p < L; ++p) {
+      int pa, si;
+      outside_parent_sibling(n, level, p, k, pa, si);
+      parent[(int64_t)k * L + p] = pa;
+      sibling[(int64_t)k * L + p] = si;
+    }
+  return CLIORA_OK;
+}
+
+int64_t cliora_split_row_offset(int B, int n, int level, int outside) {
+  return (int64_t)B * (outside ? outside_rows_before(n, level) : inside_rows_before(n, level));
+}
+
+int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out) {
+  if (dims == nullptr || out == nullptr) return CLIORA_ERR_NULL_POINTER;
+  return compute_layout(*dims, *out);
+}
+
+// ---------------------------------------------------------------------------------------------
+int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const float* x, const float* obj,
+                      const uint8_t* keep, float* inside_h, float* inside_s, float* ws, cliora_stream_t stream) {
+  Ctx c;
+  CL_TRY(make_ctx(dims, stream, c));
+  if (!w || !x || !inside_h || !inside_s || !ws) return CLIORA_ERR_NULL_POINTER;
+  if (c.d.R > 0 && obj == nullptr) return CLIORA_ERR_NULL_POINTER;
+  if (!c.d.share && (!w->oW1 || !w->ob1 || !w->oW2 || !w->ob2 || !w->oWb)) return CLIORA_ERR_NULL_POINTER;
+  const int B = c.d.B, n = c.d.n, D = c.d.D, PI = (int)c.L.PI;
+  const bool vl = c.d.R > 0;
+  const float* oW1 = c.d.share ? w->W1 : w->oW1;
+  const float* oWb = c.d.share ? w->Wb : w->oWb;
+  float* Wcat_in = ws + c.L.Wcat_in;
+
+  pack_weights_kernel<<<296, 256, 0, c.st>>>(D, PI, w->W1, w->Wb, oW1, oWb, Wcat_in, ws + c.L.Wcat_out);
+  CL_CHECK_LAUNCH("pack_weights_kernel");
+
+  // leaves: t = tanh(W_leaf x + b); h = finalize(t)
+  CL_TRY(dense_linear(c.st, B * n, D, D, x, w->W_leaf, w->b_leaf, 2, ws + c.L.leaf_t));
+  for (int level = 0; level < n; ++level) {
+    if (level > 0) {
+      SplitArgs s = split_args(c, level, false, inside_h, inside_s, nullptr, ws, w->b1);
+      const int64_t rows = (int64_t)B * s.L * s.N;
+      split_build_kernel<false><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+      CL_CHECK_LAUNCH("split_build_kernel<inside>");
+      const int64_t r0 = B * inside_rows_before(n, level);
+      CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, w->W2, w->b2, 1, ws + c.L.Yin + r0 * D));
+    }
+    CellArgs a = cell_args(c, level, false, ws, inside_h, inside_s);
+    a.obj = obj; a.keep = keep;
+    if (vl) CL_TRY(launch_cell_aggregate<true>(c, a));
+    else CL_TRY(launch_cell_aggregate<false>(c, a));
+    if (level < n - 1) CL_TRY(project_level(c, level, inside_h, Wcat_in, PI * D, ws + c.L.Pin));
+  }
+  return CLIORA_OK;
+}
+
+int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const float* inside_h,
+                       const float* inside_s, float* outside_h, float* outside_s, float* ws,
+                       cliora_stream_t stream) {
+  Ctx c;
+  CL_TRY(make_ctx(dims, stream, c));
+  if (!w || !inside_h || !inside_s || !outside_h || !outside_s || !ws) return CLIORA_ERR_NULL_POINTER;
+  const int B = c.d.B, n = c.d.n, D = c.d.D;
+  const float* oW2 = c.d.share ? w->W2 : w->oW2;
+  const float* ob1 = c.d.share ? w->b1 : w->ob1;
+  const float* ob2 = c.d.share ? w->b2 : w->ob2;
+  float* Wcat_out = ws + c.L.Wcat_out;
+
+  outside_root_kernel<<<B, 128, 0, c.st>>>(B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out);
+  CL_CHECK_LAUNCH("outside_root_kernel");
+  if (n > 1) CL_TRY(project_level(c, n - 1, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
+  for (int level = n - 2; level >= 0; --level) {
+    SplitArgs s = split_args(c, level, true, inside_h, inside_s, outside_s, ws, ob1);
+    const int64_t rows = (int64_t)B * s.L * s.N;
+    split_build_kernel<true><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+    CL_CHECK_LAUNCH("split_build_kernel<outside>");
+    const int64_t r0 = B * outside_rows_before(n, level);
+    CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, oW2, ob2, 1, ws + c.L.Yout + r0 * D));
+    CellArgs a = cell_args(c, level, true, ws, outside_h, outside_s);
+    CL_TRY(launch_cell_aggregate<false>(c, a));
+    if (level > 0) CL_TRY(project_level(c, level, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
+  }
+  return CLIORA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, const float* g_inside_s,
+                           const float* g_outside_h, const float* g_outside_s, float* bws,
+                           cliora_stream_t stream) {
+  Ctx c;
+  CL_TRY(make_ctx(dims, stream, c));
+  if (!bws) return CLIORA_ERR_NULL_POINTER;
+  const int64_t BC = (int64_t)c.d.B * c.C, D = c.d.D;
+  auto seed = [&](float* dst, const float* src, int64_t nfl) -> int {
+    if (src) CL_CUDA(cudaMemcpyAsync(dst, src, nfl * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+    else CL_CUDA(cudaMemsetAsync(dst, 0, nfl * sizeof(float), c.st));
+    return CLIORA_OK;
+  };
+  CL_TRY(seed(bws + c.L.Gh_in, g_inside_h, BC * D));
+  CL_TRY(seed(bws + c.L.Gs_in, g_inside_s, BC));
+  CL_TRY(seed(bws + c.L.Gh_out, g_outside_h, BC * D));
+  CL_TRY(seed(bws + c.L.Gs_out, g_outside_s, BC));
+  CL_CUDA(cudaMemsetAsync(bws + c.L.GP_in, 0, BC * c.L.PI * D * sizeof(float), c.st));
+  CL_CUDA(cudaMemsetAsync(bws + c.L.GP_out, 0, BC * 2 * D * sizeof(float), c.st));
+  return CLIORA_OK;
+}
+
+int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* inside_h,
+                       const float* inside_s, const float* outside_h, const float* outside_s, float* ws,
+                       float* bws, cliora_weight_grads* grads, cliora_stream_t stream) {
+  Ctx c;
+  CL_TRY(make_ctx(dims, stream, c));
+  if (!w || !inside_h || !inside_s || !outside_h || !outside_s || !ws || !bws || !grads)
+    return CLIORA_ERR_NULL_POINTER;
+  const int B = c.d.B, n = c.d.n, D = c.d.D;
+  const int64_t BC = (int64_t)B * c.C;
+  float* Wcat_out = ws + c.L.Wcat_out;
+  float* scratch = bws + c.L.splitk;
+  for (int level = 0; level <= n - 2; ++level) {
+    if (level > 0) CL_TRY(cellgrad_level(c, level, bws + c.L.GP_out, 2 * D, Wcat_out, bws + c.L.Gh_out));
+    CL_TRY((level_bwd<true, false>(c, level, w, inside_h, inside_s, outside_s, const_cast<float*>(outside_h),
+                                   const_cast<float*>(outside_s), nullptr, nullptr, ws, bws)));
+  }
+  if (n > 1) CL_TRY(cellgrad_level(c, n - 1, bws + c.L.GP_out, 2 * D, Wcat_out, bws + c.L.Gh_out));
+  if (grads->root) {
+    outside_root_bwd_kernel<<<1, 128, 0, c.st>>>(B, D, c.C, bws + c.L.Gh_out, outside_h, ws + c.L.nrm_out,
+                                                 grads->root);
+    CL_CHECK_LAUNCH("outside_root_bwd_kernel");
+  }
+  // weight gradients contributed by the outside pass
+  const bool sh = c.d.share != 0;
+  float* dW1 = sh ? grads->W1 : grads->oW1;
+  float* dW2 = sh ? grads->W2 : grads->oW2;
+  float* db2 = sh ? grads->b2 : grads->ob2;
+  float* dWb = sh ? grads->Wb : grads->oWb;
+  const float* GY = ws + c.L.Yout;
+  const float* Z = ws + c.L.Zout;
+  const float* GPo = bws + c.L.GP_out;
+  if (dW2) CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch));
+  if (db2) CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
+  if (dW1) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPo, 2 * D, outside_h, D, dW1 + D, 2 * D, 0, scratch));
+  if (dWb) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPo + D, 2 * D, outside_h, D, dWb, D, 0, scratch));
+  if (!sh) {
+    const float* GPi = bws + c.L.GP_in;
+    if (grads->oW1)
+      CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + 3 * D, 4 * D, inside_h, D, grads->oW1, 2 * D, 0, scratch));
+    if (grads->ob1) CL_TRY(colsum(c.st, GPi + 3 * D, 4 * D, BC, D, grads->ob1, 0, scratch));
+  }
+  return CLIORA_OK;
+}
+
+int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* x, const float* obj,
+                      const uint8_t* keep, const float* inside_h, const float* inside_s,
+                      const float* outside_h, float* ws, float* bws, int had_outside, float* grad_x,
+                      float* grad_obj, cliora_weight_grads* grads, cliora_stream_t stream) {
+  Ctx c;
+  CL_TRY(make_ctx(dims, stream, c));
+  if (!w || !x || !inside_h || !inside_s || !ws || !bws || !grads) return CLIORA_ERR_NULL_POINTER;
+  (void)outside_h;
+  const int B = c.d.B, n = c.d.n, D = c.d.D, R = c.d.R, PI = (int)c.L.PI;
+  const int64_t BC = (int64_t)B * c.C;
+  const bool vl = R > 0;
+  if (vl && obj == nullptr) return CLIORA_ERR_NULL_POINTER;
+  float* Wcat_in = ws + c.L.Wcat_in;
+  float* scratch = bws + c.L.splitk;
+  float* ih = const_cast<float*>(inside_h);
+  float* is_ = const_cast<float*>(inside_s);
+  for (int level = n - 1; level >= 0; --level) {
+    if (level < n - 1) CL_TRY(cellgrad_level(c, level, bws + c.L.GP_in, PI * D, Wcat_in, bws + c.L.Gh_in));
+    if (vl) CL_TRY((level_bwd<false, true>(c, level, w, inside_h, inside_s, nullptr, ih, is_, obj, keep, ws, bws)));
+    else CL_TRY((level_bwd<false, false>(c, level, w, inside_h, inside_s, nullptr, ih, is_, obj, keep, ws, bws)));
+  }
+  // leaf linear layer
+  const float* gu = bws + c.L.gu;
+  if (grad_x) {
+    GemmParams p{};
+    p.A = gu; p.lda = D; p.amap = dense_rows();
+    p.W = w->W_leaf; p.ldw = D;
+    p.C = grad_x; p.ldc = D; p.cmap = dense_rows();
+    p.M = B * n; p.N = D; p.K = D;
+    CL_TRY(launch_gemm(c.st, /*nt=*/false, p));
+  }
+  if (grads->W_leaf) CL_TRY(launch_gemm_tn(c.st, B * n, D, D, gu, D, x, D, grads->W_leaf, D, 0, scratch));
+  if (grads->b_leaf) CL_TRY(colsum(c.st, gu, D, (int64_t)B * n, D, grads->b_leaf, 0, scratch));
+
+  const int acc = (c.d.share && had_outside) ? 1 : 0;
+  const float* GY = ws + c.L.Yin;
+  const float* Z = ws + c.L.Zin;
+  const float* GPi = bws + c.L.GP_in;
+  const int ldp = PI * D;
+  if (grads->W2) CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch));
+  if (grads->b2) CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
+  if (grads->W1) {
+    CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi, ldp, inside_h, D, grads->W1, 2 * D, 0, scratch));
+    CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + D, ldp, inside_h, D, grads->W1 + D, 2 * D, acc, scratch));
+  }
+  if (grads->Wb) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + 2 * D, ldp, inside_h, D, grads->Wb, D, acc, scratch));
+  if (grads->b1) CL_TRY(colsum(c.st, GPi, ldp, BC, D, grads->b1, 0, scratch));
+  if (vl && grad_obj) {
+    dim3 grid(ceil_div(D, 128), B);
+    obj_grad_kernel<64><<<grid, 128, 0, c.st>>>(D, R, c.C, bws + c.L.GA2, ws + c.L.q_in, bws + c.L.coef, grad_obj, 0);
+    CL_CHECK_LAUNCH("obj_grad_kernel");
+  }
+  if (!had_outside) {
+    if (grads->root) CL_CUDA(cudaMemsetAsync(grads->root, 0, D * sizeof(float), c.st));
+    if (!c.d.share) {
+      if (grads->oW1) CL_CUDA(cudaMemsetAsync(grads->oW1, 0, (size_t)2 * D * D * sizeof(float), c.st));
+      if (grads->ob1) CL_CUDA(cudaMemsetAsync(grads->ob1, 0, D * sizeof(float), c.st));
+      if (grads->oW2) CL_CUDA(cudaMemsetAsync(grads->oW2, 0, (size_t)D * D * sizeof(float), c.st));
+      if (grads->ob2) CL_CUDA(cudaMemsetAsync(grads->ob2, 0, D * sizeof(float), c.st));
+      if (grads->oWb) CL_CUDA(cudaMemsetAsync(grads->oWb, 0, (size_t)D * D * sizeof(float), c.st));
+    }
+  }
+  return CLIORA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int cliora_atten_scores(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride, const float* obj,
+                        float* scores, cliora_stream_t stream) {
+  if (!h || !obj || !scores) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || ncell < 1 || D < 4 || D % 4 || R < 1) return CLIORA_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  // one GEMM per image c: scores[a, c, cell, :] = h[a, cell] . obj[c]^T
+  for (int cimg = 0; cimg < B; ++cimg) {
+    GemmParams p{};
+    p.A = h; p.lda = D; p.amap = RowMap{ncell, h_batch_stride, 0};
+    p.W = obj + (int64_t)cimg * R * D; p.ldw = D;
+    p.C = scores; p.ldc = R; p.cmap = RowMap{ncell, (int64_t)B * ncell, (int64_t)cimg * ncell};
+    p.M = B * ncell; p.N = R; p.K = D;
+    CL_TRY(launch_gemm(st, true, p));
+  }
+  return CLIORA_OK;
+}
+
+int cliora_atten_max_fwd(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride, const float* obj,
+                         float* smax, int32_t* amax, cliora_stream_t stream) {
+  if (!h || !obj || !smax || !amax) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || ncell < 0 || D < 4 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
+  if (ncell == 0) return CLIORA_OK;
+  dim3 grid(B, ceil_div((int64_t)B * ncell, 64));
+  atten_max_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, ncell, D, R, h, h_batch_stride, obj, smax, amax);
+  CL_CHECK_LAUNCH("atten_max_kernel");
+  return CLIORA_OK;
+}
+
+int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride, const float* obj,
+                         const float* g_smax, const int32_t* amax, float* g_h, int64_t gh_batch_stride,
+                         float* g_obj, cliora_stream_t stream) {
+  if (!h || !obj || !g_smax || !amax) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || ncell < 0 || D < 4 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
+  if (ncell == 0) return CLIORA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_h) {
+    atten_max_bwd_h_kernel<<<B * ncell, 128, 0, st>>>(B, ncell, D, R, obj, g_smax, amax, g_h, gh_batch_stride);
+    CL_CHECK_LAUNCH("atten_max_bwd_h_kernel");
+  }
+  if (g_obj) {
+    atten_max_bwd_obj_kernel<<<B * R, 128, 0, st>>>(B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
+    CL_CHECK_LAUNCH("atten_max_bwd_obj_kernel");
+  }
+  return CLIORA_OK;
+}
+
+int cliora_contrastive_loss(int B, int cells, int ncell, const float* smax, const float* inside_s,
+                            const float* outside_s, float margin, float alpha, float* loss_out, float* g_smax,
+                            float* g_inside_s, float* g_outside_s, float* scratch, cliora_stream_t stream) {
+  if (!smax || !inside_s || !outside_s || !loss_out || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || cells < 1 || ncell < 0 || ncell > cells) return CLIORA_ERR_BAD_SHAPE;
+  if (g_smax && (!g_inside_s || !g_outside_s)) return CLIORA_ERR_NULL_POINTER;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = scratch;                        // [ncell]
+  float* root_part = scratch + ((ncell + 3) & ~3); // [ncell, B]
+  const float scale = alpha / (float)B;
+  if (ncell > 0) {
+    const size_t smem = (size_t)(2 * B + 64) * sizeof(float);
+    contrastive_cell_kernel<<<ncell, 128, smem, st>>>(B, cells, ncell, smax, inside_s, outside_s, margin, scale,
+                                                      partial, g_smax, g_inside_s, g_outside_s,
+                                                      g_smax ? root_part : nullptr);
+    CL_CHECK_LAUNCH("contrastive_cell_kernel");
+  }
+  contrastive_finish_kernel<<<1, 128, 0, st>>>(B, cells, ncell, partial, scale, loss_out,
+                                               g_smax ? root_part : nullptr, g_inside_s);
+  CL_CHECK_LAUNCH("contrastive_finish_kernel");
+  return CLIORA_OK;
+}
+
+int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out, float* g_wmax, float* scratch,
+                   cliora_stream_t stream) {
+  if (!wmax || !loss_out || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || n < 1) return CLIORA_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)(B + 64) * sizeof(float);
+  vg_loss_kernel<<<B, 128, smem, st>>>(B, n, wmax, alpha, scratch, g_wmax);
+  CL_CHECK_LAUNCH("vg_loss_kernel");
+  sum_small_kernel<<<1, 128, 0, st>>>(scratch, B, loss_out);
+  CL_CHECK_LAUNCH("sum_small_kernel");
+  return CLIORA_OK;
+}
+
+int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float* best, cliora_stream_t stream) {
+  if (!backptr) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || n < 1 || n > 512) return CLIORA_ERR_BAD_SHAPE;
+  if (n > 1 && !split_scores) return CLIORA_ERR_NULL_POINTER;
+  const size_t smem = (size_t)num_cells(n) * sizeof(float);
+  if (smem > 48 * 1024)
+    CL_CUDA(cudaFuncSetAttribute(cky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cky_kernel<<<B, 64, smem, (cudaStream_t)stream>>>(B, n, split_scores, backptr, best);
+  CL_CHECK_LAUNCH("cky_kernel");
+  return CLIORA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int cliora_linear(int M, int N, int K, const float* A, const float* W, const float* bias, int act, float* C,
+                  cliora_stream_t stream) {
+  if (!A || !W || !C) return CLIORA_ERR_NULL_POINTER;
+  if (M < 0 || N < 1 || K < 1) return CLIORA_ERR_BAD_SHAPE;
+  return dense_linear((cudaStream_t)stream, M, N, K, A, W, bias, act, C);
+}
+
+int cliora_matmul_nn(int M, int N, int K, const float* A, const float* Bm, float* C, int accumulate,
+                     cliora_stream_t stream) {
+  if (!A || !Bm || !C) return CLIORA_ERR_NULL_POINTER;
+  if (M < 0 || N < 1 || K < 1) return CLIORA_ERR_BAD_SHAPE;
+  GemmParams p{};
+  p.A = A; p.lda = K; p.amap = dense_rows();
+  p.W = Bm; p.ldw = N;
+  p.C = C; p.ldc = N; p.cmap = dense_rows();
+  p.M = M; p.N = N; p.K = K;
+  p.accumulate = accumulate;
+  return launch_gemm((cudaStream_t)stream, false, p);
+}
+
+int64_t cliora_matmul_tn_scratch_floats(int M, int Ka, int Kb) { return tn_scratch_floats(M, Ka, Kb); }
+
+int cliora_matmul_tn(int M, int Ka, int Kb, const float* A, const float* Bm, float* C, int accumulate,
+                     float* scratch, cliora_stream_t stream) {
+  if (!A || !Bm || !C || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (M < 0 || Ka < 1 || Kb < 1) return CLIORA_ERR_BAD_SHAPE;
+  return launch_gemm_tn((cudaStream_t)stream, M, Ka, Kb, A, Ka, Bm, Kb, C, Kb, accumulate, scratch);
+}
+
+}  // extern "C"

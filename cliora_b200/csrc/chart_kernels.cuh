@@ -1,0 +1,537 @@
+// Chart kernels: everything of the inside/outside recursion that is not a dense GEMM.
+// Each kernel implements one phase of oracle/factored.py (the CPU emulator the maths was
+// validated with); names match the phase comments there.
+#pragma once
+#include "common.cuh"
+
+namespace cliora {
+
+// ------------------------------------------------------------------------------------------
+// pack_weights: Wcat_in [PI*D, D] = [W1[:, :D]; W1[:, D:]; Wb; (oW1[:, :D])],  Wcat_out [2D, D] = [oW1[:, D:]; oWb]
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(int D, int PI, const float* __restrict__ W1, const float* __restrict__ Wb,
+                                    const float* __restrict__ oW1, const float* __restrict__ oWb,
+                                    float* __restrict__ Wcat_in, float* __restrict__ Wcat_out) {
+  const int64_t total = (int64_t)(PI + 2) * D * D;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int blk = (int)(idx / ((int64_t)D * D));
+    const int rem = (int)(idx % ((int64_t)D * D));
+    const int i = rem / D, j = rem % D;
+    float v;
+    if (blk == 0) v = W1[(int64_t)i * 2 * D + j];
+    else if (blk == 1) v = W1[(int64_t)i * 2 * D + D + j];
+    else if (blk == 2) v = Wb[(int64_t)i * D + j];
+    else if (blk == 3 && PI == 4) v = oW1[(int64_t)i * 2 * D + j];
+    else if (blk == PI) v = oW1[(int64_t)i * 2 * D + D + j];
+    else v = oWb[(int64_t)i * D + j];
+    if (blk < PI) Wcat_in[idx] = v;
+    else Wcat_out[idx - (int64_t)PI * D * D] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// split_build: per split row, z = relu(Al[first] + Ar[second] + b1), e = h[first].V[second] + s[first] + s[second]
+// inside : first = left child (inside chart), second = right child (inside chart)
+// outside: first = sibling (inside chart),    second = parent (outside chart)
+// One warp per row; rows ordered (b,p,k) inside, (b,k,p) outside (the reference's order).
+// ------------------------------------------------------------------------------------------
+struct SplitArgs {
+  int B, n, level, L, N, D;
+  int64_t C;
+  const float* ih;    // inside_h [B,C,D]
+  const float* is_;   // inside_s [B,C]
+  const float* os_;   // outside_s [B,C] (outside only)
+  const float* Pin;   // [B,C,ldPin]
+  const float* Pout;  // [B,C,2D]
+  int ldPin;
+  int iAl;            // column offset of the "first argument" projection in Pin (0, or 3D when !share && outside)
+  const float* b1;
+  float* Z;           // level block [B*L*N, D]
+  float* E;           // level block [B*L*N]
+};
+
+template <bool OUTSIDE>
+CL_D void decode_row(const SplitArgs& a, int64_t m, int& b, int& first, int& second) {
+  const int per = a.L * a.N;
+  b = (int)(m / per);
+  const int rem = (int)(m % per);
+  if (!OUTSIDE) {
+    const int p = rem / a.N, k = rem % a.N;
+    inside_children(a.n, a.level, p, k, first, second);
+  } else {
+    const int k = rem / a.L, p = rem % a.L;
+    outside_parent_sibling(a.n, a.level, p, k, second, first);
+  }
+}
+
+template <bool OUTSIDE>
+__global__ __launch_bounds__(256) void split_build_kernel(const SplitArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t rows = (int64_t)a.B * a.L * a.N;
+  if (m >= rows) return;
+  int b, c1, c2;
+  decode_row<OUTSIDE>(a, m, b, c1, c2);
+  const int64_t g1 = (int64_t)b * a.C + c1, g2 = (int64_t)b * a.C + c2;
+  const float* Al = a.Pin + g1 * a.ldPin + a.iAl;
+  const float* Ar = OUTSIDE ? a.Pout + g2 * 2 * a.D : a.Pin + g2 * a.ldPin + a.D;
+  const float* V = OUTSIDE ? a.Pout + g2 * 2 * a.D + a.D : a.Pin + g2 * a.ldPin + 2 * a.D;
+  const float* h1 = a.ih + g1 * a.D;
+  float* z = a.Z + m * a.D;
+  float dot = 0.f;
+  for (int j = lane * 4; j < a.D; j += 128) {
+    const float4 x = ld4(Al + j), y = ld4(Ar + j), bb = ld4(a.b1 + j);
+    float4 o;
+    o.x = fmaxf(x.x + y.x + bb.x, 0.f);
+    o.y = fmaxf(x.y + y.y + bb.y, 0.f);
+    o.z = fmaxf(x.z + y.z + bb.z, 0.f);
+    o.w = fmaxf(x.w + y.w + bb.w, 0.f);
+    st4(z + j, o);
+    const float4 hv = ld4(h1 + j), vv = ld4(V + j);
+    dot = fmaf(hv.x, vv.x, dot);
+    dot = fmaf(hv.y, vv.y, dot);
+    dot = fmaf(hv.z, vv.z, dot);
+    dot = fmaf(hv.w, vv.w, dot);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    const float s2 = OUTSIDE ? a.os_[g2] : a.is_[g2];
+    a.E[m] = dot + a.is_[g1] + s2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// cell_aggregate (+ cell_finalize): one block per chart cell of a level.
+//   p = softmax_k(e_k);  a = sum_k p_k y_k;  sbar = sum_k p_k e_k;  q = a / max(|a|, eps)
+//   VL: att = softmax_r(q . obj_r); patt = att * keep / 0.9; a2 = q + sum_r patt_r obj_r; h = a2 / max(|a2|, eps)
+// Leaf mode (E == nullptr): N == 1, p = 1, sbar = 0, y = tanh(W_leaf x + b).
+// Dynamic shared memory: (D + N + 2R + 64) floats.
+// ------------------------------------------------------------------------------------------
+struct CellArgs {
+  int B, n, level, L, N, D, R;
+  int64_t C;
+  int sp, sk;          // row(b,p,k) = b*L*N + p*sp + k*sk   (inside: sp=N, sk=1; outside: sp=1, sk=L)
+  float* Y;            // level block [B*L*N, D]   (bwd: overwritten with its gradient)
+  const float* E;      // level block [B*L*N] or nullptr (leaf)
+  float* Pr;           // level block [B*L*N] softmax probabilities (fwd out, bwd in)
+  float* chart_h;      // [B,C,D]
+  float* chart_s;      // [B,C]
+  float* q;            // [B,C,D] or nullptr (then q == chart_h)
+  float* nrm;          // [B,C]
+  float* nrm2;         // [B,C]   (R > 0)
+  float* att;          // [B,C,R] (R > 0)
+  const float* obj;    // [B,R,D] (R > 0)
+  const uint8_t* keep; // [B,C,R] or nullptr
+};
+
+template <bool VL>
+__global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_a = sm;                 // [D]
+  float* s_p = s_a + a.D;          // [N]
+  float* s_att = s_p + a.N;        // [R]
+  float* s_patt = s_att + a.R;     // [R]
+  float* s_red = s_patt + a.R;     // [64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int b = blockIdx.x / a.L, p = blockIdx.x % a.L;
+  const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + p;
+  const int64_t row0 = (int64_t)b * a.L * a.N + (int64_t)p * a.sp;
+
+  // 1. softmax over the N splits (warp 0)
+  if (warp == 0) {
+    float sbar = 0.f;
+    if (a.E == nullptr) {
+      if (lane == 0) s_p[0] = 1.f;
+    } else {
+      float mx = -INFINITY;
+      for (int k = lane; k < a.N; k += 32) mx = fmaxf(mx, a.E[row0 + (int64_t)k * a.sk]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int k = lane; k < a.N; k += 32) {
+        const float ex = expf(a.E[row0 + (int64_t)k * a.sk] - mx);
+        s_p[k] = ex;
+        sum += ex;
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      for (int k = lane; k < a.N; k += 32) {
+        const float pk = s_p[k] * inv;
+        s_p[k] = pk;
+        a.Pr[row0 + (int64_t)k * a.sk] = pk;
+        sbar = fmaf(pk, a.E[row0 + (int64_t)k * a.sk], sbar);
+      }
+      sbar = warp_sum(sbar);
+    }
+    if (lane == 0) a.chart_s[cell] = sbar;
+  }
+  __syncthreads();
+
+  // 2. a = sum_k p_k y_k
+  float ss = 0.f;
+  for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < a.N; ++k) {
+      const float pk = s_p[k];
+      const float4 y = ld4(a.Y + (row0 + (int64_t)k * a.sk) * a.D + j);
+      acc.x = fmaf(pk, y.x, acc.x);
+      acc.y = fmaf(pk, y.y, acc.y);
+      acc.z = fmaf(pk, y.z, acc.z);
+      acc.w = fmaf(pk, y.w, acc.w);
+    }
+    st4(s_a + j, acc);
+    ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  }
+  ss = block_sum(ss, s_red);
+  const float nrm = fmaxf(sqrtf(ss), kTiny);
+  const float inv_nrm = 1.f / nrm;
+  // q = a / nrm
+  for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
+    float4 v = ld4(s_a + j);
+    v.x *= inv_nrm; v.y *= inv_nrm; v.z *= inv_nrm; v.w *= inv_nrm;
+    st4(s_a + j, v);
+    if (VL) st4(a.q + cell * a.D + j, v);
+    else st4(a.chart_h + cell * a.D + j, v);
+  }
+  if (tid == 0) a.nrm[cell] = nrm;
+  if (!VL) return;
+
+  __syncthreads();
+  // 3. region attention of this cell against its own image's R regions
+  const float* obj = a.obj + (int64_t)b * a.R * a.D;
+  for (int r = warp; r < a.R; r += nwarps) {
+    float d = 0.f;
+    for (int j = lane * 4; j < a.D; j += 128) {
+      const float4 qv = ld4(s_a + j), ov = ld4(obj + (int64_t)r * a.D + j);
+      d = fmaf(qv.x, ov.x, d); d = fmaf(qv.y, ov.y, d); d = fmaf(qv.z, ov.z, d); d = fmaf(qv.w, ov.w, d);
+    }
+    d = warp_sum(d);
+    if (lane == 0) s_att[r] = d;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int r = lane; r < a.R; r += 32) mx = fmaxf(mx, s_att[r]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int r = lane; r < a.R; r += 32) {
+      const float ex = expf(s_att[r] - mx);
+      s_att[r] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int r = lane; r < a.R; r += 32) {
+      const float pr = s_att[r] * inv;
+      s_att[r] = pr;
+      a.att[cell * a.R + r] = pr;
+      float sc = 1.f;
+      if (a.keep != nullptr) sc = a.keep[cell * a.R + r] ? kKeepScale : 0.f;
+      s_patt[r] = pr * sc;
+    }
+  }
+  __syncthreads();
+  float ss2 = 0.f;
+  for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
+    float4 acc = ld4(s_a + j);
+    for (int r = 0; r < a.R; ++r) {
+      const float w = s_patt[r];
+      const float4 ov = ld4(obj + (int64_t)r * a.D + j);
+      acc.x = fmaf(w, ov.x, acc.x); acc.y = fmaf(w, ov.y, acc.y);
+      acc.z = fmaf(w, ov.z, acc.z); acc.w = fmaf(w, ov.w, acc.w);
+    }
+    st4(s_a + j, acc);
+    ss2 += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  }
+  ss2 = block_sum(ss2, s_red);
+  const float nrm2 = fmaxf(sqrtf(ss2), kTiny);
+  const float inv2 = 1.f / nrm2;
+  for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
+    float4 v = ld4(s_a + j);
+    v.x *= inv2; v.y *= inv2; v.z *= inv2; v.w *= inv2;
+    st4(a.chart_h + cell * a.D + j, v);
+  }
+  if (tid == 0) a.nrm2[cell] = nrm2;
+}
+
+// outside root: outside_h[:, root] = unit(root_vector), outside_s[:, root] = 0   (diora.py:337-356)
+__global__ void outside_root_kernel(int B, int D, int64_t C, const float* __restrict__ root,
+                                    float* __restrict__ oh, float* __restrict__ os_, float* __restrict__ nrm_out) {
+  __shared__ float red[64];
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) ss += root[j] * root[j];
+  ss = block_sum(ss, red);
+  const float nrm = fmaxf(sqrtf(ss), kTiny);
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) oh[((int64_t)b * C + C - 1) * D + j] = root[j] / nrm;
+  if (threadIdx.x == 0) {
+    os_[(int64_t)b * C + C - 1] = 0.f;
+    nrm_out[(int64_t)b * C + C - 1] = nrm;
+  }
+}
+
+// ==========================================================================================
+// backward
+// ==========================================================================================
+
+// d/da of a / clamp(|a|, eps): live branch (g - h (h.g)) / nrm, clamped branch g / eps.
+CL_D float unit_bwd_coef(float nrm, float hdotg) { return (nrm > kTiny) ? hdotg : 0.f; }
+
+struct CellBwdArgs {
+  CellArgs c;            // same geometry; Y is overwritten with GY, Pr is read
+  const float* Gh;       // [B,C,D] total gradient wrt the cell vector
+  const float* Gs;       // [B,C]   total gradient wrt the cell score
+  float* GE;             // level block [B*L*N] out: gradient wrt split scores
+  float* GA2;            // [B,C,D] out (VL): gradient wrt the pre-second-normalisation vector
+  float* coef;           // [B,C,2R] out (VL): patt_r, g_logit_r
+  const float* leaf_t;   // leaf mode: tanh outputs [B*n, D]
+  float* gu;             // leaf mode out: gradient wrt the pre-tanh activations [B*n, D]
+};
+
+// One block per cell.  Dynamic shared memory: (2D + 3R + 64) floats.
+template <bool VL>
+__global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
+  const CellArgs& a = g.c;
+  extern __shared__ __align__(16) float sm[];
+  float* s_g = sm;                  // [D] working gradient
+  float* s_q = s_g + a.D;           // [D] q (VL)
+  float* s_r0 = s_q + a.D;          // [R] g_att -> g_logit
+  float* s_r1 = s_r0 + a.R;         // [R] att
+  float* s_r2 = s_r1 + a.R;         // [R] scale
+  float* s_red = s_r2 + a.R;        // [64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int b = blockIdx.x / a.L, p = blockIdx.x % a.L;
+  const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + p;
+  const int64_t row0 = (int64_t)b * a.L * a.N + (int64_t)p * a.sp;
+  const float* hvec = a.chart_h + cell * a.D;
+  const float* qvec = VL ? a.q + cell * a.D : hvec;
+  const float nrm = a.nrm[cell];
+
+  // ---- gradient wrt q (the first-normalised vector) ----
+  float hd = 0.f;
+  for (int j = tid; j < a.D; j += blockDim.x) {
+    const float gv = g.Gh[cell * a.D + j];
+    s_g[j] = gv;
+    hd = fmaf(hvec[j], gv, hd);
+    if (VL) s_q[j] = qvec[j];
+  }
+  hd = block_sum(hd, s_red);
+  if (VL) {
+    const float nrm2 = a.nrm2[cell];
+    const float coef = unit_bwd_coef(nrm2, hd);
+    const float inv2 = 1.f / nrm2;
+    for (int j = tid; j < a.D; j += blockDim.x) {
+      const float v = (s_g[j] - hvec[j] * coef) * inv2;   // ga2
+      s_g[j] = v;
+      g.GA2[cell * a.D + j] = v;
+    }
+    __syncthreads();
+    const float* obj = a.obj + (int64_t)b * a.R * a.D;
+    for (int r = warp; r < a.R; r += nwarps) {
+      float d = 0.f;
+      for (int j = lane; j < a.D; j += 32) d = fmaf(s_g[j], obj[(int64_t)r * a.D + j], d);
+      d = warp_sum(d);
+      if (lane == 0) {
+        float sc = 1.f;
+        if (a.keep != nullptr) sc = a.keep[cell * a.R + r] ? kKeepScale : 0.f;
+        const float at = a.att[cell * a.R + r];
+        s_r0[r] = d * sc;   // g_att
+        s_r1[r] = at;
+        s_r2[r] = sc;
+      }
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int r = tid; r < a.R; r += blockDim.x) part = fmaf(s_r1[r], s_r0[r], part);
+    const float dsum = block_sum(part, s_red);
+    for (int r = tid; r < a.R; r += blockDim.x) {
+      const float gl = s_r1[r] * (s_r0[r] - dsum);   // g_logit
+      s_r0[r] = gl;
+      g.coef[(cell * 2) * a.R + r] = s_r1[r] * s_r2[r];   // patt
+      g.coef[(cell * 2 + 1) * a.R + r] = gl;
+    }
+    __syncthreads();
+    // gq = ga2 + sum_r g_logit_r obj_r
+    float qd = 0.f;
+    for (int j = tid; j < a.D; j += blockDim.x) {
+      float v = s_g[j];
+      for (int r = 0; r < a.R; ++r) v = fmaf(s_r0[r], obj[(int64_t)r * a.D + j], v);
+      s_g[j] = v;
+      qd = fmaf(s_q[j], v, qd);
+    }
+    hd = block_sum(qd, s_red);
+  }
+  // ---- ga = unit_bwd(gq, q, nrm) ----
+  {
+    const float coef = unit_bwd_coef(nrm, hd);
+    const float inv = 1.f / nrm;
+    float ad = 0.f;
+    for (int j = tid; j < a.D; j += blockDim.x) {
+      const float qv = VL ? s_q[j] : hvec[j];
+      const float v = (s_g[j] - qv * coef) * inv;
+      s_g[j] = v;
+      ad = fmaf(qv, v, ad);
+    }
+    ad = block_sum(ad, s_red);   // q . ga   (also makes s_g visible)
+    if (a.E == nullptr) {
+      // leaf: gu = ga * (1 - t^2)
+      const int64_t row = (int64_t)b * a.L + p;
+      for (int j = tid; j < a.D; j += blockDim.x) {
+        const float t = g.leaf_t[row * a.D + j];
+        g.gu[row * a.D + j] = s_g[j] * (1.f - t * t);
+      }
+      return;
+    }
+    const float gs = g.Gs[cell];
+    const float cm = nrm * ad + a.chart_s[cell] * gs;   // sum_m p_m gp_m
+    // ---- per split: ge, gy ----
+    for (int k = warp; k < a.N; k += nwarps) {
+      const int64_t row = row0 + (int64_t)k * a.sk;
+      float* y = a.Y + row * a.D;
+      const float pk = a.Pr[row];
+      float d = 0.f;
+      for (int j = lane * 4; j < a.D; j += 128) {
+        const float4 yv = ld4(y + j), gv = ld4(s_g + j);
+        d = fmaf(yv.x, gv.x, d); d = fmaf(yv.y, gv.y, d); d = fmaf(yv.z, gv.z, d); d = fmaf(yv.w, gv.w, d);
+        float4 o;
+        o.x = yv.x > 0.f ? pk * gv.x : 0.f;
+        o.y = yv.y > 0.f ? pk * gv.y : 0.f;
+        o.z = yv.z > 0.f ? pk * gv.z : 0.f;
+        o.w = yv.w > 0.f ? pk * gv.w : 0.f;
+        st4(y + j, o);
+      }
+      d = warp_sum(d);
+      if (lane == 0) {
+        const float gp = d + a.E[row] * gs;
+        g.GE[row] = pk * (gs + gp - cm);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// split_scatter: push the per-split gradients into the accumulators of the two cells a split read.
+// ------------------------------------------------------------------------------------------
+struct ScatterArgs {
+  SplitArgs s;           // geometry + forward tensors (ih, Pin, Pout)
+  const float* GZ;       // level-local [rows, D]
+  const float* GE;       // level block [rows]
+  float* Gh_in;          // [B,C,D]
+  float* Gs_in;          // [B,C]
+  float* GP_in;          // [B,C,ldPin]
+  float* Gs_out;         // [B,C]
+  float* GP_out;         // [B,C,2D]
+};
+
+template <bool OUTSIDE>
+__global__ __launch_bounds__(256) void split_scatter_kernel(const ScatterArgs g) {
+  const SplitArgs& a = g.s;
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t rows = (int64_t)a.B * a.L * a.N;
+  if (m >= rows) return;
+  int b, c1, c2;
+  decode_row<OUTSIDE>(a, m, b, c1, c2);
+  const int64_t g1 = (int64_t)b * a.C + c1, g2 = (int64_t)b * a.C + c2;
+  const float ge = g.GE[m];
+  const float* gz = g.GZ + m * a.D;
+  const float* h1 = a.ih + g1 * a.D;
+  const float* V = OUTSIDE ? a.Pout + g2 * 2 * a.D + a.D : a.Pin + g2 * a.ldPin + 2 * a.D;
+  float* dAl = g.GP_in + g1 * a.ldPin + a.iAl;
+  float* dAr = OUTSIDE ? g.GP_out + g2 * 2 * a.D : g.GP_in + g2 * a.ldPin + a.D;
+  float* dV = OUTSIDE ? g.GP_out + g2 * 2 * a.D + a.D : g.GP_in + g2 * a.ldPin + 2 * a.D;
+  float* dh1 = g.Gh_in + g1 * a.D;
+  for (int j = lane * 4; j < a.D; j += 128) {
+    const float4 z = ld4(gz + j);
+    red_add4(dAl + j, z);
+    red_add4(dAr + j, z);
+    const float4 vv = ld4(V + j), hv = ld4(h1 + j);
+    red_add4(dh1 + j, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
+    red_add4(dV + j, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
+  }
+  if (lane == 0) {
+    atomicAdd(g.Gs_in + g1, ge);
+    atomicAdd((OUTSIDE ? g.Gs_out : g.Gs_in) + g2, ge);
+  }
+}
+
+// g_root = sum_b unit_bwd(Gh_out[b, root], h_root, nrm_root)
+__global__ void outside_root_bwd_kernel(int B, int D, int64_t C, const float* __restrict__ Gh_out,
+                                        const float* __restrict__ oh, const float* __restrict__ nrm_out,
+                                        float* __restrict__ g_root) {
+  __shared__ float red[64];
+  const float nrm = nrm_out[C - 1];
+  for (int j = threadIdx.x; j < D; j += blockDim.x) g_root[j] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* gh = Gh_out + ((int64_t)b * C + C - 1) * D;
+    const float* h = oh + ((int64_t)b * C + C - 1) * D;
+    float d = 0.f;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) d = fmaf(h[j], gh[j], d);
+    d = block_sum(d, red);
+    const float coef = unit_bwd_coef(nrm, d);
+    for (int j = threadIdx.x; j < D; j += blockDim.x) g_root[j] += (gh[j] - h[j] * coef) / nrm;
+  }
+}
+
+// g_obj[b,r,:] = sum_c patt[b,c,r] ga2[b,c,:] + g_logit[b,c,r] q[b,c,:]     grid (ceil(D/128), B), block 128
+template <int RMAX>
+__global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, const float* __restrict__ GA2,
+                                                       const float* __restrict__ q, const float* __restrict__ coef,
+                                                       float* __restrict__ g_obj, int accumulate) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_c[2 * RMAX];
+  float acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
+  for (int64_t c = 0; c < C; ++c) {
+    const int64_t cell = (int64_t)b * C + c;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * R; t += blockDim.x) s_c[t] = coef[cell * 2 * R + t];
+    __syncthreads();
+    if (j < D) {
+      const float gv = GA2[cell * D + j], qv = q[cell * D + j];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < R) acc[r] = fmaf(s_c[r], gv, fmaf(s_c[R + r], qv, acc[r]));
+    }
+  }
+  if (j < D) {
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) {
+        float* dst = g_obj + ((int64_t)b * R + r) * D + j;
+        *dst = accumulate ? *dst + acc[r] : acc[r];
+      }
+  }
+}
+
+// column sums: dst[j] (+)= sum_r src[r*ld + j].  Two deterministic stages through `part` [S, cols].
+__global__ void colsum_stage1_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols,
+                                     float* __restrict__ part) {
+  __shared__ float s[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int64_t chunk = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  float acc = 0.f;
+  if (j < cols)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += src[r * ld + j];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += s[y][threadIdx.x];
+    part[(int64_t)blockIdx.y * cols + j] = t;
+  }
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ part, int S, int cols, float* __restrict__ dst,
+                                     int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float t = 0.f;
+  for (int s = 0; s < S; ++s) t += part[(int64_t)s * cols + j];
+  dst[j] = accumulate ? dst[j] + t : t;
+}
+
+}  // namespace cliora

@@ -1,0 +1,133 @@
+// Shared helpers for the cliora_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cliora_b200.h"
+
+#define CL_HD __host__ __device__ __forceinline__
+#define CL_D __device__ __forceinline__
+
+namespace cliora {
+
+constexpr float kTiny = 1e-8f;       // cliora/net/utils.py:10 (UnitNorm clamp)
+constexpr float kKeepScale = 1.0f / 0.9f;  // nn.Dropout(0.1) in AttentionHead, cliora/net/cliora.py:32
+
+// ---- chart geometry (closed forms of cliora/net/offset_cache.py, inside_index.py, outside_index.py) ----
+CL_HD int64_t num_cells(int n) { return (int64_t)n * (n + 1) / 2; }
+CL_HD int lvl_off(int n, int l) { return l * n - l * (l - 1) / 2; }
+
+// Inside split (level, pos p, split k): left child (k, p), right child (level-1-k, p+k+1).
+CL_HD void inside_children(int n, int level, int p, int k, int& left, int& right) {
+  left = lvl_off(n, k) + p;
+  right = lvl_off(n, level - 1 - k) + p + k + 1;
+}
+
+// Outside entry k of cell (level, p): first Rn = n-1-level-p entries take the sibling on the right,
+// the remaining p entries take it on the left (order of cliora/net/outside_index.py:39-62).
+CL_HD void outside_parent_sibling(int n, int level, int p, int k, int& parent, int& sibling) {
+  const int Rn = n - 1 - level - p;
+  if (k < Rn) {
+    sibling = lvl_off(n, Rn - 1 - k) + p + level + 1;
+    parent = lvl_off(n, level + Rn - k) + p;
+  } else {
+    const int j = k - Rn;
+    sibling = lvl_off(n, j) + p - 1 - j;
+    parent = lvl_off(n, level + j + 1) + p - 1 - j;
+  }
+}
+
+// number of inside split rows per sentence in levels [1, level)
+CL_HD int64_t inside_rows_before(int n, int level) {
+  // sum_{j=1}^{m} (n-j) j with m = level-1
+  const int64_t m = level - 1;
+  return (int64_t)n * m * (m + 1) / 2 - m * (m + 1) * (2 * m + 1) / 6;
+}
+// number of outside split rows per sentence in levels [0, level): sum_{j<level} (n-j)(n-j-1)
+CL_HD int64_t outside_rows_before(int n, int level) {
+  int64_t s = 0;
+  for (int j = 0; j < level; ++j) s += (int64_t)(n - j) * (n - j - 1);
+  return s;
+}
+
+// Row r of a "virtual" [M, ld] matrix lives at physical row (r / L) * bstride + base + (r % L).
+// Lets a GEMM read / write one chart level ([B, L] cells inside [B, cells]) in place.
+struct RowMap {
+  int L;
+  int64_t bstride;
+  int64_t base;
+};
+CL_HD RowMap dense_rows() { return RowMap{1 << 30, 0, 0}; }
+CL_HD RowMap level_rows(int n, int level) { return RowMap{n - level, num_cells(n), lvl_off(n, level)}; }
+CL_HD int64_t map_row(const RowMap& m, int r) { return (int64_t)(r / m.L) * m.bstride + m.base + (r % m.L); }
+
+// ---- warp / block reductions ----
+CL_D float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+CL_D float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Sum over the whole block; every thread gets the result.  `red` is >= 33 floats of shared memory.
+CL_D float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+CL_D float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+CL_D void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 16-byte vector reduction to global memory (red.global.add.v4.f32, sm_90+)
+CL_D void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// ---- host-side error plumbing ----
+struct LaunchCtx {
+  cudaStream_t stream;
+  int status = CLIORA_OK;
+};
+extern thread_local char g_last_cuda_error[256];
+extern long long g_launch_count;
+
+inline int record_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+  return CLIORA_ERR_CUDA;
+}
+
+#define CL_CHECK_LAUNCH(name)                                       \
+  do {                                                              \
+    ++::cliora::g_launch_count;                                     \
+    cudaError_t e__ = cudaPeekAtLastError();                        \
+    if (e__ != cudaSuccess) {                                       \
+      cudaGetLastError();                                           \
+      return ::cliora::record_cuda_error(e__, name);                \
+    }                                                               \
+  } while (0)
+
+#define CL_CUDA(call)                                               \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return ::cliora::record_cuda_error(e__, #call); \
+  } while (0)
+
+#define CL_TRY(expr)                 \
+  do {                               \
+    int s__ = (expr);                \
+    if (s__ != CLIORA_OK) return s__; \
+  } while (0)
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace cliora

@@ -1,0 +1,109 @@
+"""Autograd bridges for the fused loss kernels (csrc/align_kernels.cuh)."""
+import torch
+
+from .. import _lib
+from .._lib import check, ptr
+
+
+class ContrastiveFn(torch.autograd.Function):
+    """ContrastiveLoss.forward of the reference (cliora/net/trainer.py:91-128) on the max-over-regions
+    scores smax [B,B,ncell]; the kernel produces the loss and its gradients in one pass."""
+
+    @staticmethod
+    def forward(ctx, smax, inside_s, outside_s, margin, alpha):
+        smax = smax.contiguous().float()
+        ins = inside_s.contiguous().float()
+        outs = outside_s.contiguous().float()
+        B, _, ncell = smax.shape
+        cells = ins.shape[1]
+        dev = smax.device
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        need = any(ctx.needs_input_grad[:3])
+        g_s = torch.empty_like(smax) if need else None
+        g_in = torch.zeros_like(ins) if need else None
+        g_out = torch.zeros_like(outs) if need else None
+        scratch = torch.empty(ncell * (B + 1) + 8, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cliora_contrastive_loss(B, cells, ncell, ptr(smax), ptr(ins), ptr(outs), float(margin),
+                                                     float(alpha), ptr(loss), ptr(g_s), ptr(g_in), ptr(g_out),
+                                                     ptr(scratch), _lib.stream()), 'cliora_contrastive_loss')
+        if need:
+            ctx.save_for_backward(g_s, g_in, g_out)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        g_s, g_in, g_out = ctx.saved_tensors
+        return g * g_s, g * g_in, g * g_out, None, None
+
+
+class VGLossFn(torch.autograd.Function):
+    """VGLoss.forward of the reference (trainer.py:139-171) on wmax [B,B,n] = max over regions."""
+
+    @staticmethod
+    def forward(ctx, wmax, alpha):
+        wmax = wmax.contiguous().float()
+        B, _, n = wmax.shape
+        dev = wmax.device
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        need = ctx.needs_input_grad[0]
+        g_w = torch.empty_like(wmax) if need else None
+        scratch = torch.empty(B + 8, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cliora_vg_loss(B, n, ptr(wmax), float(alpha), ptr(loss), ptr(g_w), ptr(scratch),
+                                            _lib.stream()), 'cliora_vg_loss')
+        if need:
+            ctx.save_for_backward(g_w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (g_w,) = ctx.saved_tensors
+        return g * g_w, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on the library's fp32 GEMM (Embed / ImageEncoder / reconstruction projections)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous().float()
+        w = weight.contiguous().float()
+        b = None if bias is None else bias.contiguous().float()
+        M, K = x2.shape
+        N = w.shape[0]
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().cliora_linear(M, N, K, ptr(x2), ptr(w), ptr(b), 0, ptr(out), _lib.stream()),
+                  'cliora_linear')
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = x.shape
+        return out.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        L = _lib.lib()
+        M, K = x2.shape
+        N = w.shape[0]
+        g2 = g.reshape(M, N).contiguous().float()
+        gx = gw = gb = None
+        with torch.cuda.device(g.device):
+            st = _lib.stream()
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty(M, K, device=g.device, dtype=torch.float32)
+                check(L.cliora_matmul_nn(M, K, N, ptr(g2), ptr(w), ptr(gx), 0, st), 'cliora_matmul_nn')
+                gx = gx.view(ctx.in_shape)
+            if ctx.needs_input_grad[1]:
+                gw = torch.empty(N, K, device=g.device, dtype=torch.float32)
+                scratch = torch.empty(int(L.cliora_matmul_tn_scratch_floats(M, N, K)) + 8, device=g.device,
+                                      dtype=torch.float32)
+                check(L.cliora_matmul_tn(M, N, K, ptr(g2), ptr(x2), ptr(gw), 0, ptr(scratch), st), 'cliora_matmul_tn')
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = g2.sum(0)
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    return LinearFn.apply(x, weight, bias)

@@ -1,0 +1,250 @@
+"""Losses, Embed, ImageEncoder, Net and a minimal Trainer: drop-ins for the hot-path pieces of the
+reference's cliora/net/trainer.py and cliora/net/utils.py:37-55, built on the fused kernels.
+
+Class names, constructor arguments, ``forward`` signatures, returned ``(loss, dict)`` pairs and
+``state_dict`` keys follow the reference so ``build_net`` / ``Trainer.step`` callers keep working.
+"""
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from .losses import ContrastiveFn, VGLossFn, linear
+
+
+class ImageEncoder(nn.Module):
+    """cliora/net/utils.py:37-55: two Linear(2048 -> D) heads, zero-initialised like the reference."""
+
+    def __init__(self, input_size, size):
+        super().__init__()
+        self.fc = nn.Linear(input_size, size)
+        self.fc_vis = nn.Linear(input_size, size)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for p in self.parameters():
+            if p.requires_grad:
+                p.data.zero_()
+
+    def forward(self, obj_feats):
+        f = obj_feats.float()
+        return linear(f, self.fc.weight, self.fc.bias), linear(f, self.fc_vis.weight, self.fc_vis.bias)
+
+
+class Embed(nn.Module):
+    """cliora/net/trainer.py:204-224: embedding gather + two E->D projections."""
+
+    def __init__(self, embeddings, input_size, size):
+        super().__init__()
+        self.input_size, self.size = input_size, size
+        self.embeddings = embeddings
+        self.mat = nn.Parameter(torch.FloatTensor(size, input_size))
+        self.mat1 = nn.Parameter(torch.FloatTensor(size, input_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for p in self.parameters():
+            if p.requires_grad:
+                p.data.normal_()
+
+    def forward(self, x):
+        B, n = x.shape
+        emb = self.embeddings(x.view(-1))
+        return linear(emb, self.mat).view(B, n, -1), linear(emb, self.mat1).view(B, n, -1)
+
+
+class ReconstructionSoftmaxLoss(nn.Module):
+    """cliora/net/trainer.py:25-78: CE over [positive, k_neg negatives] scored against outside_h leaves."""
+    name = 'reconstruct_softmax_loss'
+
+    def __init__(self, embeddings, input_size, size, margin=1, k_neg=3, cuda=False):
+        super().__init__()
+        self.k_neg, self.margin, self.input_size = k_neg, margin, input_size
+        self.embeddings = embeddings
+        self.mat = nn.Parameter(torch.FloatTensor(size, input_size))
+        self._cuda = cuda
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for p in self.parameters():
+            if p.requires_grad:
+                p.data.normal_()
+
+    def forward(self, sentences, neg_samples, diora, info=None):
+        B, n = sentences.shape
+        cell = diora.outside_h[:, :n]                                   # [B,n,D]
+        pos = linear(self.embeddings(sentences), self.mat)             # [B,n,D]
+        neg = linear(self.embeddings(neg_samples), self.mat)           # [K,D]
+        xp = (pos * cell).sum(-1, keepdim=True)
+        xn = linear(cell, neg)                                         # [B,n,K]
+        score = torch.cat([xp, xn], 2).view(B * n, -1)
+        target = torch.zeros(B * n, dtype=torch.int64, device=score.device)
+        loss = nn.functional.cross_entropy(score, target)
+        return loss, dict(reconstruction_softmax_loss=loss)
+
+
+class ContrastiveLoss(nn.Module):
+    """cliora/net/trainer.py:81-128.  Consumes max-over-regions scores of the first cells//2 cells
+    straight from the alignment kernel; the [B,B,cells,R] tensor is never built."""
+    name = 'contrastive_loss'
+
+    def __init__(self, margin=1.0, alpha_contr=0.01, use_contr_ce=False):
+        super().__init__()
+        self.min_val = 1e-8
+        self.margin, self.alpha_contr, self.use_contr_ce = margin, alpha_contr, use_contr_ce
+
+    def forward(self, batch, diora):
+        cells = diora.inside_s.shape[1]
+        smax, _ = diora.span_region_max(cells // 2)
+        loss = ContrastiveFn.apply(smax, diora.inside_s.squeeze(-1), diora.outside_s.squeeze(-1), self.margin,
+                                   self.alpha_contr)
+        return loss, dict(contrastive_loss=loss)
+
+
+class VGLoss(nn.Module):
+    """cliora/net/trainer.py:131-171.  ``vg`` is either the reference's 4-D vg_atten_score
+    [B,B,n,R] or the already max-reduced [B,B,n] from ``diora.word_region_max()``."""
+    name = 'vg_loss'
+
+    def __init__(self, alpha_vg=0.1):
+        super().__init__()
+        self.min_val = 1e-8
+        self.alpha_vg = alpha_vg
+
+    def forward(self, batch, vg):
+        wmax = vg.max(-1).values if vg.dim() == 4 else vg
+        loss = VGLossFn.apply(wmax, self.alpha_vg)
+        return loss, dict(vg_loss=loss)
+
+
+def get_loss_funcs(options, embedding_layer=None):
+    """cliora/net/trainer.py:174-201."""
+    input_dim = embedding_layer.weight.shape[1]
+    funcs = [ReconstructionSoftmaxLoss(embedding_layer, margin=options.margin, k_neg=options.k_neg,
+                                       input_size=input_dim, size=options.hidden_dim, cuda=options.cuda)]
+    if getattr(options, 'vg_loss', False):
+        funcs.append(VGLoss(options.alpha_vg))
+    if options.obj_feats and getattr(options, 'use_contr', False):
+        funcs.append(ContrastiveLoss(options.vl_margin, options.alpha_contr, getattr(options, 'use_contr_ce', False)))
+    return funcs
+
+
+class Net(nn.Module):
+    """cliora/net/trainer.py:227-304 (forward signature kept; visualisation is out of scope)."""
+
+    def __init__(self, embed, image_encoder, diora, obj_feats, visualize=False, loss_funcs=()):
+        super().__init__()
+        self.obj_feats = obj_feats
+        if self.obj_feats:
+            self.img_encoder = image_encoder
+        self.embed = embed
+        self.diora = diora
+        self.visualize = visualize
+        self.loss_func_names = [m.name for m in loss_funcs]
+        for m in loss_funcs:
+            setattr(self, m.name, m)
+
+    def compute_loss(self, batch, neg_samples, info=None, batch_parse=None):
+        ret, loss = {}, []
+        diora = self.diora
+        for name in self.loss_func_names:
+            func = getattr(self, name)
+            if 'reconstruct' in name:
+                sub, desc = func(batch, neg_samples, diora, info)
+            elif 'contrastive' in name:
+                sub, desc = func(batch, diora)
+            elif 'vg_loss' in name:
+                # training: max-reduced word scores straight from the kernel; eval: the reference's
+                # 4-D tensor (it mixes in all_atten_score, cliora.py:463-464)
+                vg = diora.word_region_max()[0] if diora.training else diora.vg_atten_score
+                sub, desc = func(batch, vg)
+            else:
+                continue
+            loss.append(sub.view(1, 1))
+            ret.update(desc)
+        return ret, torch.cat(loss, 1)
+
+    def forward(self, img_ids, idx2word, batch, image_feats, obj_feats, boxes, obj_cates, neg_samples=None,
+                compute_loss=True, info=None, batch_parse=None):
+        embed_span, embed_word = self.embed(batch)
+        obj_span = obj_word = None
+        if self.obj_feats:
+            obj_span, obj_word = self.img_encoder(obj_feats=obj_feats)
+        self.diora(embed_span, embed_word, obj_span, obj_word)
+        if compute_loss:
+            ret, loss = self.compute_loss(batch, neg_samples, info=info, batch_parse=batch_parse)
+        else:
+            ret, loss = {}, torch.full((1, 1), 1, dtype=torch.float32, device=embed_span.device)
+        ret['total_loss'] = loss
+        return ret
+
+
+class Trainer(object):
+    """The training-step part of cliora/net/trainer.py:337-501 (run_net, gradient_update, step)."""
+
+    def __init__(self, net, k_neg=None, ngpus=1, cuda=True):
+        self.net = net
+        self.optimizer = None
+        self.cuda = cuda
+        self.ngpus = ngpus
+        self.grad_sync = None     # set by cliora_b200.parallel for data-parallel runs
+
+    def init_optimizer(self, optimizer_cls=optim.Adam, optimizer_kwargs=None):
+        kw = optimizer_kwargs or dict(lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        self.optimizer = optimizer_cls(params, **kw)
+
+    def run_net(self, batch_map, idx2word=None, compute_loss=True):
+        batch = batch_map['sentences']
+        return self.net(batch_map.get('example_ids'), idx2word, batch, batch_map.get('image_feats'),
+                        batch_map.get('obj_feats'), batch_map.get('boxes'), batch_map.get('obj_cates'),
+                        neg_samples=batch_map.get('neg_samples'), compute_loss=compute_loss, info={},
+                        batch_parse=batch_map.get('GT'))
+
+    def gradient_update(self, loss):
+        self.optimizer.zero_grad()
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync()
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        self.optimizer.step()
+
+    def step(self, batch_map, idx2word=None, train=True, compute_loss=True, sync_result=True):
+        self.net.train() if train else self.net.eval()
+        with torch.set_grad_enabled(train):
+            out = self.run_net(batch_map, idx2word, compute_loss=compute_loss)
+        total = out['total_loss'].mean(dim=0).sum()
+        if train:
+            self.gradient_update(total)
+        if not sync_result:
+            return {'total_loss': total.detach()}
+        result = {'batch_size': batch_map.get('batch_size'), 'length': batch_map.get('length')}
+        for k, v in out.items():
+            if 'loss' in k:
+                result[k] = v.mean(dim=0).sum().item()
+        return result
+
+
+def build_net(options, embeddings=None, random_seed=None):
+    """cliora/net/trainer.py:504-582 minus process-group setup (see cliora_b200.parallel)."""
+    size = options.hidden_dim
+    if options.arch != 'mlp':
+        raise NotImplementedError
+    if options.obj_feats:
+        from .cliora import DioraMLP as Diora
+    else:
+        from .diora import DioraMLP as Diora
+    embedding_layer = embeddings
+    if options.obj_feats:
+        embedding_layer.weight.requires_grad = False
+    embed = Embed(embedding_layer, input_size=embedding_layer.weight.size(1), size=size)
+    image_encoder = ImageEncoder(input_size=2048, size=size)
+    diora = Diora(size, outside=True, normalize=options.normalize, compress=False, share=options.share)
+    loss_funcs = get_loss_funcs(options, embedding_layer)
+    net = Net(embed, image_encoder, diora, obj_feats=options.obj_feats, visualize=False, loss_funcs=loss_funcs)
+    if options.cuda:
+        net.cuda()
+        diora.cuda()
+    trainer = Trainer(net, k_neg=options.k_neg, ngpus=1, cuda=options.cuda)
+    trainer.init_optimizer(optim.Adam, dict(lr=options.lr, betas=(0.9, 0.999), eps=1e-8))
+    return trainer

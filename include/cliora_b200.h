@@ -1,0 +1,240 @@
+/*
+ * cliora_b200 -- C ABI of the B200-native CLIORA chart hot path.
+ *
+ * This is the drop-in boundary: a plain-C shared library (libcliora_b200.so)
+ * whose entry points take device pointers into caller-owned buffers, sizes and
+ * a CUDA stream.  No torch types.  The library allocates nothing persistent and
+ * keeps no pointer after a call returns.  The Python host side
+ * (cliora_b200/net/*.py) binds these with ctypes and mirrors the reference's
+ * cliora/net module API on top (INTEGRATION.md shows the binding).
+ *
+ * All tensors are fp32, row-major, contiguous.  Chart tensors are laid out
+ * exactly like the reference's Chart (cliora/net/diora.py:7-23): [B, cells, D]
+ * with cells level-major, cell (level l, pos p) at l*n - l(l-1)/2 + p
+ * (cliora/net/offset_cache.py:1-7).
+ *
+ * Every function returns 0 on success or a negative cliora_status; the Python
+ * wrapper raises RuntimeError (the reference lets exceptions propagate out of
+ * Trainer.step, cliora/net/trainer.py:469-481).  There is no CPU fallback.
+ */
+#ifndef CLIORA_B200_H_
+#define CLIORA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cliora_status {
+  CLIORA_OK = 0,
+  CLIORA_ERR_BAD_SHAPE = -1,    /* B,n,D,R out of range, D % 4 != 0, ... */
+  CLIORA_ERR_NULL_POINTER = -2, /* a required buffer is NULL */
+  CLIORA_ERR_CUDA = -3,         /* a CUDA runtime call or kernel launch failed */
+  CLIORA_ERR_NO_DEVICE = -4,    /* no sm_100 device: the library never falls back to the CPU */
+  CLIORA_ERR_UNSUPPORTED = -5
+} cliora_status;
+
+/* Opaque to C callers that only pass it through; identical to cudaStream_t. */
+typedef void* cliora_stream_t;
+
+const char* cliora_status_string(int status);
+/* Last CUDA error text recorded by this thread's most recent failing call. */
+const char* cliora_last_cuda_error(void);
+int cliora_abi_version(void);
+
+/* ------------------------------------------------------------------------
+ * Chart geometry (replaces cliora/net/offset_cache.py:1-7,
+ * cliora/net/inside_index.py:182-197, cliora/net/outside_index.py:93-127).
+ * Host-side, no GPU needed.  The kernels use the same closed forms inline
+ * instead of index tensors.
+ * ---------------------------------------------------------------------- */
+int64_t cliora_num_cells(int n);
+int64_t cliora_level_offset(int n, int level);
+/* left/right child chart indices of every (pos, split) of an inside level; out arrays hold (n-level)*level entries. */
+int cliora_inside_index(int n, int level, int64_t* left, int64_t* right);
+/* parent/sibling chart indices of an outside level in the reference's (split, pos) order; (n-level-1)*(n-level) entries. */
+int cliora_outside_index(int n, int level, int64_t* parent, int64_t* sibling);
+/* Row offset (in split rows, all B sentences) of a level's block inside the per-split buffers. */
+int64_t cliora_split_row_offset(int B, int n, int level, int outside);
+
+/* ------------------------------------------------------------------------
+ * Model weights = the reference DioraMLP state_dict tensors
+ * (cliora/net/diora.py:453-471; keys listed in SURVEY.md section 8b).
+ * nn.Linear layout [out, in].  When share != 0 the o* pointers are ignored.
+ * ---------------------------------------------------------------------- */
+typedef struct cliora_weights {
+  const float* W_leaf; /* inside_compose_func.leaf_fc.weight   [D, D]  */
+  const float* b_leaf; /* inside_compose_func.leaf_fc.bias     [D]     */
+  const float* W1;     /* inside_compose_func.h_fcs.0.weight   [D, 2D] */
+  const float* b1;     /* inside_compose_func.h_fcs.0.bias     [D]     */
+  const float* W2;     /* inside_compose_func.h_fcs.2.weight   [D, D]  */
+  const float* b2;     /* inside_compose_func.h_fcs.2.bias     [D]     */
+  const float* Wb;     /* inside_score_func.mat                [D, D]  */
+  const float* root;   /* root_vector_out_h                    [D]     */
+  const float* oW1;    /* outside_compose_func.h_fcs.0.weight  (share == 0) */
+  const float* ob1;
+  const float* oW2;
+  const float* ob2;
+  const float* oWb;    /* outside_score_func.mat */
+} cliora_weights;
+
+/* Same fields, writable: gradients.  Every non-NULL field is fully overwritten. */
+typedef struct cliora_weight_grads {
+  float *W_leaf, *b_leaf, *W1, *b1, *W2, *b2, *Wb, *root, *oW1, *ob1, *oW2, *ob2, *oWb;
+} cliora_weight_grads;
+
+typedef struct cliora_dims {
+  int B;       /* sentences in the batch */
+  int n;       /* words per sentence (all sentences in a batch share it, dataloader.py:52-91) */
+  int D;       /* hidden size, D % 4 == 0 */
+  int R;       /* regions per image; 0 = text-only DIORA (cliora/net/diora.py) */
+  int share;   /* 1: outside pass uses the inside weights (--share default) */
+  int flags;   /* CLIORA_FLAG_* */
+} cliora_dims;
+
+#define CLIORA_FLAG_DETERMINISTIC 1 /* reserved */
+
+/* Float offsets of every sub-buffer inside the single forward workspace `ws`
+ * (saved for backward) and the backward scratch `bws`.  -1 = not present. */
+typedef struct cliora_layout {
+  int64_t ws_floats;   /* size of the forward workspace, in floats */
+  int64_t bws_floats;  /* size of the backward scratch, in floats  */
+  int64_t rows_in;     /* inside split rows over the whole batch  = B (n-1)n(n+1)/6 */
+  int64_t rows_out;    /* outside split rows                      = 2 rows_in       */
+  int64_t PI;          /* projections per inside cell (3, or 4 when share == 0) */
+  /* forward workspace */
+  int64_t Pin, Pout;           /* [B,C,PI*D], [B,C,2D] per-cell projections */
+  int64_t q_in;                /* [B,C,D] pre-attention unit vectors (R > 0 only) */
+  int64_t nrm_in, nrm2_in;     /* [B,C] */
+  int64_t att_in;              /* [B,C,R] softmax over regions (R > 0 only) */
+  int64_t nrm_out;             /* [B,C] */
+  int64_t leaf_t;              /* [B*n, D] tanh(W_leaf x + b) */
+  int64_t Zin, Yin, Ein, Prin;     /* [rows_in, D] x2, [rows_in] x2 */
+  int64_t Zout, Yout, Eout, Prout; /* [rows_out, D] x2, [rows_out] x2 */
+  int64_t Wcat_in, Wcat_out;   /* packed projection weights [PI*D, D], [2D, D] */
+  /* backward scratch */
+  int64_t Gh_in, Gs_in, GP_in, Gh_out, Gs_out, GP_out;
+  int64_t GA2, coef;          /* [B,C,D], [B,C,2R] attention backward intermediates (R > 0 only) */
+  int64_t GE, GZ, splitk, gu; /* per-level split scratch, split-K partials, leaf pre-activation grads */
+} cliora_layout;
+
+int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);
+
+/* ------------------------------------------------------------------------
+ * Forward.  Replaces DioraBase.forward's leaf_transform + inside_pass
+ * (cliora/net/diora.py:283-331, cliora/net/cliora.py:290-341) and
+ * outside_pass (diora.py:337-398).
+ *
+ *  x          [B,n,D]     projected word embeddings (x_span)
+ *  obj        [B,R,D]     projected region features, NULL when R == 0
+ *  keep       [B,cells,R] uint8 dropout keep-mask of AttentionHead (cliora.py:32,40);
+ *                         NULL = dropout off (eval).  Kept probabilities are scaled 1/0.9.
+ *  inside_h   [B,cells,D] out;  inside_s [B,cells] out
+ *  ws         forward workspace of cliora_layout.ws_floats floats
+ *
+ * After the call, per-level views of ws give what the reference passes to
+ * inside_hook(level, h, c, s) (diora.py:333): h = Yin rows of the level
+ * [B*L*N, D] in (b,pos,split) order, s = Ein rows [B,L,N,1]; c is all zeros.
+ * ---------------------------------------------------------------------- */
+int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const float* x, const float* obj,
+                      const uint8_t* keep, float* inside_h, float* inside_s, float* ws, cliora_stream_t stream);
+
+int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const float* inside_h,
+                       const float* inside_s, float* outside_h, float* outside_s, float* ws,
+                       cliora_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Backward (replaces torch autograd over the reference graph; maths in
+ * SURVEY.md section 8a last row, derivation checked in oracle/factored.py).
+ *
+ * cliora_chart_bwd_begin  seeds the accumulators in bws from the incoming
+ *                         chart cotangents (any may be NULL = zero).
+ * cliora_outside_bwd      outside pass backward, levels 0 -> n-2, then the root vector.
+ * cliora_inside_bwd       inside pass backward, levels n-1 -> 1, leaves, weight grads.
+ *                         `had_outside` says whether cliora_outside_bwd ran on this bws.
+ * Destroys the Y buffers in ws (overwritten by their gradients).
+ * ---------------------------------------------------------------------- */
+int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, const float* g_inside_s,
+                           const float* g_outside_h, const float* g_outside_s, float* bws,
+                           cliora_stream_t stream);
+
+int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* inside_h,
+                       const float* inside_s, const float* outside_h, const float* outside_s, float* ws,
+                       float* bws, cliora_weight_grads* grads, cliora_stream_t stream);
+
+int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* x, const float* obj,
+                      const uint8_t* keep, const float* inside_h, const float* inside_s,
+                      const float* outside_h, float* ws, float* bws, int had_outside, float* grad_x,
+                      float* grad_obj, cliora_weight_grads* grads, cliora_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Span-region alignment (replaces the einsums of cliora/net/cliora.py:457-466
+ * and the losses of cliora/net/trainer.py:81-171).
+ * ---------------------------------------------------------------------- */
+
+/* scores[a, c, cell, r] = h[a, cell] . obj[c, r]   -> [B, B, ncell, R]   (cliora.py:457 with
+ * h = inside_h + outside_h summed by the caller; cliora.py:459 with h = x_word, ncell = n).
+ * h rows of sentence a start at row a * h_batch_stride.  Materialises the full tensor: only for
+ * callers that read diora.all_atten_score / vg_atten_score. */
+int cliora_atten_scores(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride,
+                        const float* obj, float* scores, cliora_stream_t stream);
+
+/* smax[a, c, cell] = max_r h[a,cell] . obj[c,r], amax = argmax (first max), WITHOUT materialising
+ * the scores.  Only the first `ncell` cells of each sentence are scored (R <= 64). */
+int cliora_atten_max_fwd(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride,
+                         const float* obj, float* smax, int32_t* amax, cliora_stream_t stream);
+
+/* Backward of cliora_atten_max_fwd: g_h[a,cell] += sum_c g_smax[a,c,cell] obj[c, amax];
+ * g_obj[c, r] += sum_{a,cell: amax == r} g_smax[a,c,cell] h[a,cell].  Both are ACCUMULATED into
+ * (caller zero-fills); either may be NULL. */
+int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride,
+                         const float* obj, const float* g_smax, const int32_t* amax, float* g_h,
+                         int64_t gh_batch_stride, float* g_obj, cliora_stream_t stream);
+
+/* ContrastiveLoss.forward (trainer.py:91-128) on smax [B,B,ncell] (ncell = cells//2 is what the
+ * loss reads): loss (1 float on device) and, when g_smax != NULL, gradients wrt smax [B,B,ncell],
+ * inside_s and outside_s ([B,cells], caller zero-fills).  scratch: ncell*(B+1)+4 floats. */
+int cliora_contrastive_loss(int B, int cells, int ncell, const float* smax, const float* inside_s,
+                            const float* outside_s, float margin, float alpha, float* loss_out,
+                            float* g_smax, float* g_inside_s, float* g_outside_s, float* scratch,
+                            cliora_stream_t stream);
+
+/* VGLoss.forward (trainer.py:139-171) on wmax [B,B,n] = max_r word-region scores:
+ * logits[a,c] = mean_w wmax[a,c,w]; loss = alpha * CE(logits, arange(B)).  g_wmax may be NULL.
+ * scratch: B floats. */
+int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out, float* g_wmax,
+                   float* scratch, cliora_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * CKY decode (replaces ParsePredictor.batched_cky, cliora/analysis/cky.py:31-99,
+ * fed by the hook of cliora/analysis/utils.py:78-95).
+ *  split_scores = the Ein region of ws (raw inside split scores, all levels)
+ *  backptr [B, cells] int32: best split k per cell (first max wins), -1 at leaves
+ *  best    [B, cells] fp32 : Viterbi scores (may be NULL)
+ * ---------------------------------------------------------------------- */
+int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float* best, cliora_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Dense helper used on both sides of the chart (Embed, ImageEncoder,
+ * reconstruction loss; trainer.py:219-224, utils.py:52-55):
+ *   C[M,N] = act(A[M,K] W[N,K]^T + bias)      act: 0 none, 1 relu, 2 tanh
+ * ---------------------------------------------------------------------- */
+int cliora_linear(int M, int N, int K, const float* A, const float* W, const float* bias, int act, float* C,
+                  cliora_stream_t stream);
+/* C[M,N] = A[M,K] B[K,N] (accumulate != 0: C += ...) */
+int cliora_matmul_nn(int M, int N, int K, const float* A, const float* B, float* C, int accumulate,
+                     cliora_stream_t stream);
+/* C[Ka,Kb] = A[M,Ka]^T B[M,Kb]; scratch >= cliora_matmul_tn_scratch_floats(M,Ka,Kb) floats */
+int64_t cliora_matmul_tn_scratch_floats(int M, int Ka, int Kb);
+int cliora_matmul_tn(int M, int Ka, int Kb, const float* A, const float* B, float* C, int accumulate,
+                     float* scratch, cliora_stream_t stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t cliora_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIORA_B200_H_ */

@@ -1,0 +1,164 @@
+"""Parity of the CUDA chart path (through the C ABI) against the reference-generated golden
+fixtures and, at D=400 sizes, against the CPU oracle run live on the same seeded inputs.
+
+Tolerance: fp32 path, per-tensor max|d|/max|ref| <= 1e-4 (BASELINE.json north_star); in practice ~1e-6.
+"""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _fill(model, params):
+    sd = model.state_dict()
+    for k in sd:
+        src = params[k] if k in params else params[k.replace('outside_', 'inside_')]
+        sd[k].copy_(src)
+
+
+def _grads(model):
+    return {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+
+
+DIORA = ['diora_b2_n5_d16_share.pt', 'diora_b3_n7_d32_noshare.pt', 'diora_b2_n2_d16_share.pt',
+         'diora_b1_n1_d16_share.pt', 'diora_b2_n6_d400_share.pt']
+
+
+@pytest.mark.parametrize('name', DIORA)
+def test_diora_vs_golden(golden, name):
+    from cliora_b200.net.diora import DioraMLP
+    from oracle.cliora_oracle import init_params
+    blob = golden(name)
+    m = DioraMLP(blob['D'], share=blob['share']).cuda()
+    _fill(m, blob['params'] if 'params' in blob else init_params(blob['D'], share=blob['share'], seed=blob['seed']))
+    x = blob['x'].cuda().requires_grad_()
+    m(x, x)
+    for k in ('inside_h', 'inside_s', 'outside_h', 'outside_s'):
+        assert rel_err(getattr(m, k), blob[k]) < TOL, k
+    loss = sum((getattr(m, k) * blob['g_' + k].cuda()).sum() for k in ('inside_h', 'inside_s', 'outside_h', 'outside_s'))
+    loss.backward()
+    assert rel_err(x.grad, blob['grad_x']) < TOL
+    st = blob.get('grads_strided')
+    mine = _grads(m)
+    for k, g in blob['grads'].items():
+        v = mine[k]
+        if st and v.dim() == 2:
+            v = v[::st, ::st]
+        if g.abs().max() == 0:
+            assert v.abs().max().item() == 0, k
+        else:
+            assert rel_err(v, g) < TOL, k
+
+
+def test_inside_only_when_outside_disabled(golden):
+    """run_eval toggles diora.outside (scripts/train.py:130): outside chart stays zero, inside unchanged."""
+    from cliora_b200.net.diora import DioraMLP
+    blob = golden('diora_b2_n5_d16_share.pt')
+    m = DioraMLP(blob['D']).cuda()
+    _fill(m, blob['params'])
+    m.outside = False
+    x = blob['x'].cuda().requires_grad_()
+    m(x, x)
+    assert rel_err(m.inside_h, blob['inside_h']) < TOL
+    assert m.outside_h.abs().max().item() == 0 and m.outside_s.abs().max().item() == 0
+    (m.inside_h * blob['g_inside_h'].cuda()).sum().backward()
+    assert torch.isfinite(x.grad).all()
+    assert m.root_vector_out_h.grad is None or m.root_vector_out_h.grad.abs().max().item() == 0
+
+
+CLIORA = ['cliora_b3_n6_d32_r5_eval.pt', 'cliora_b3_n6_d32_r5_train.pt', 'cliora_b4_n9_d48_r36_train.pt']
+
+
+@pytest.mark.parametrize('name', CLIORA)
+def test_cliora_chart_vs_golden(golden, name):
+    from cliora_b200.net.cliora import DioraMLP
+    blob = golden(name)
+    m = DioraMLP(blob['D']).cuda()
+    _fill(m, blob['params'])
+    m.train() if blob['train'] else m.eval()
+    if blob['train']:
+        m.set_dropout_mask(blob['keep'].cuda())
+    leaf = {k: blob[k].cuda().requires_grad_() for k in ('x_span', 'x_word', 'obj_span', 'obj_word')}
+    m(leaf['x_span'], leaf['x_word'], leaf['obj_span'], leaf['obj_word'])
+    for k in ('inside_h', 'inside_s', 'outside_h', 'outside_s', 'all_atten_score', 'vg_atten_score', 'atten_score'):
+        assert rel_err(getattr(m, k), blob[k]) < TOL, k
+
+
+@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True)])
+def test_chart_vs_oracle_live(B, n, D, R, share):
+    """Same seeded inputs through the CUDA path and the CPU oracle, fwd + bwd, at the real hidden size."""
+    from oracle import cliora_oracle as O
+    if R:
+        from cliora_b200.net.cliora import DioraMLP
+        m = DioraMLP(D, share=share).cuda()
+    else:
+        from cliora_b200.net.diora import DioraMLP
+        m = DioraMLP(D, share=share).cuda()
+    P0 = O.init_params(D, share=share, seed=7)
+    _fill(m, P0)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, n, D, generator=g)
+    obj = 0.05 * torch.randn(B, R, D, generator=g) if R else None
+    C = O.num_cells(n)
+    keep = (torch.rand(B, C, R, generator=g) >= 0.1) if R else None
+    ct = {k: torch.randn(B, C, D if k.endswith('h') else 1, generator=g)
+          for k in ('inside_h', 'inside_s', 'outside_h', 'outside_s')}
+    # oracle
+    P = {k: v.clone().requires_grad_() for k, v in P0.items() if share is False or not k.startswith('outside_')}
+    if share:
+        for k in list(P):
+            if k.startswith('inside_'):
+                P['outside_' + k[len('inside_'):]] = P[k]
+    xo = x.clone().requires_grad_()
+    oo = obj.clone().requires_grad_() if R else None
+    out = O.chart_forward(P, xo, oo, keep)
+    sum((getattr(out, k) * ct[k]).sum() for k in ct).backward()
+    # cuda
+    xc = x.cuda().requires_grad_()
+    oc = obj.cuda().requires_grad_() if R else None
+    m.train()
+    if R:
+        m.set_dropout_mask(keep.cuda())
+        m(xc, xc, oc, oc)
+    else:
+        m(xc, xc)
+    for k in ct:
+        assert rel_err(getattr(m, k), getattr(out, k)) < TOL, k
+    sum((getattr(m, k) * ct[k].cuda()).sum() for k in ct).backward()
+    assert rel_err(xc.grad, xo.grad) < TOL
+    if R:
+        assert rel_err(oc.grad, oo.grad) < TOL
+    for k, v in _grads(m).items():
+        if share and k.startswith('outside_'):
+            continue
+        assert rel_err(v, P[k].grad) < TOL, k
+
+
+def test_hooks_receive_reference_shapes(golden):
+    """inside_hook(level, h, c, s) gets h [B*L*N, D], s [B,L,N,1] (diora.py:331, analysis/utils.py:78-95)."""
+    import types
+    from cliora_b200.net.diora import DioraMLP
+    blob = golden('cky_b6_n9_d24.pt')
+    m = DioraMLP(blob['D']).cuda()
+    _fill(m, blob['params'])
+    seen = {}
+    m.inside_hook = types.MethodType(lambda self, level, h, c, s: seen.__setitem__(level, (h.shape, c.shape, s.clone())), m)
+    with torch.no_grad():
+        m(blob['x'].cuda(), blob['x'].cuda())
+    B, n, D = blob['B'], blob['n'], blob['D']
+    for level in range(1, n):
+        hs, cs, s = seen[level]
+        assert hs == (B * (n - level) * level, D) and cs == hs
+        assert rel_err(s, blob['split_scores'][level]) < TOL
+
+
+def test_bad_shape_raises():
+    from cliora_b200._lib import ClioraError
+    from cliora_b200.net.diora import DioraMLP
+    m = DioraMLP(6).cuda()   # D % 4 != 0
+    with pytest.raises(ClioraError):
+        m(torch.randn(2, 3, 6).cuda(), None)

@@ -1,0 +1,57 @@
+"""fp32 GEMM primitives of the library against torch (float64 reference)."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from cliora_b200 import _lib
+    return _lib
+
+
+@pytest.mark.parametrize('M,N,K,act', [(1, 4, 4, 0), (37, 400, 400, 1), (640, 400, 400, 2), (3200, 1200, 400, 0),
+                                       (100, 101, 48, 0), (65, 36, 24, 0), (40000, 400, 400, 1)])
+def test_linear(M, N, K, act):
+    L = _lib()
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    C = torch.empty(M, N, device='cuda')
+    L.check(L.lib().cliora_linear(M, N, K, L.ptr(A), L.ptr(W), L.ptr(b), act, L.ptr(C), L.stream()), 'linear')
+    ref = A.double() @ W.double().t() + b.double()
+    ref = {0: ref, 1: torch.relu(ref), 2: torch.tanh(ref)}[act]
+    assert rel_err(C, ref) < 2e-6
+
+
+@pytest.mark.parametrize('M,N,K', [(5, 8, 12), (3200, 400, 400), (640, 400, 1200), (77, 48, 101)])
+def test_matmul_nn(M, N, K):
+    L = _lib()
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn(M, K, generator=g).cuda()
+    Bm = torch.randn(K, N, generator=g).cuda()
+    C0 = torch.randn(M, N, generator=g).cuda()
+    C = C0.clone()
+    L.check(L.lib().cliora_matmul_nn(M, N, K, L.ptr(A), L.ptr(Bm), L.ptr(C), 1, L.stream()), 'nn')
+    assert rel_err(C, C0.double() + A.double() @ Bm.double()) < 2e-6
+
+
+@pytest.mark.parametrize('M,Ka,Kb', [(7, 8, 12), (6720, 400, 400), (42560, 400, 400), (300, 36, 48), (0, 8, 8)])
+def test_matmul_tn(M, Ka, Kb):
+    L = _lib()
+    g = torch.Generator().manual_seed(M + 1)
+    A = torch.randn(max(M, 1), Ka, generator=g).cuda()[:M]
+    Bm = torch.randn(max(M, 1), Kb, generator=g).cuda()[:M]
+    C = torch.full((Ka, Kb), 7.0, device='cuda')
+    scratch = torch.empty(int(L.lib().cliora_matmul_tn_scratch_floats(M, Ka, Kb)) + 8, device='cuda')
+    A2 = A.contiguous() if M else torch.zeros(1, Ka, device='cuda')
+    B2 = Bm.contiguous() if M else torch.zeros(1, Kb, device='cuda')
+    L.check(L.lib().cliora_matmul_tn(M, Ka, Kb, L.ptr(A2), L.ptr(B2), L.ptr(C), 0, L.ptr(scratch), L.stream()), 'tn')
+    ref = A.double().t() @ Bm.double()
+    if M == 0:
+        assert C.abs().max().item() == 0
+    else:
+        assert rel_err(C, ref) < 2e-6
