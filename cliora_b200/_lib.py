@@ -44,6 +44,11 @@ _L_FIELDS = ['ws_floats', 'bws_floats', 'rows_in', 'rows_out', 'PI', 'Pin', 'Pou
              'GE', 'GZ', 'splitk', 'gu']
 
 
+class ProfileRow(Structure):
+    _fields_ = [('name', ctypes.c_char * 48), ('launches', c_int64), ('ms', ctypes.c_double),
+                ('flops', ctypes.c_double), ('bytes', ctypes.c_double)]
+
+
 class Layout(Structure):
     _fields_ = [(k, c_int64) for k in _L_FIELDS]
 
@@ -109,6 +114,9 @@ def _declare(lib):
     lib.cliora_matmul_tn_scratch_floats.restype = c_int64
     lib.cliora_matmul_tn_scratch_floats.argtypes = [c_int, c_int, c_int]
     lib.cliora_matmul_tn.argtypes = [c_int, c_int, c_int, vp, vp, vp, c_int, vp, st]
+    lib.cliora_profile_start.restype = None
+    lib.cliora_profile_stop.restype = c_int
+    lib.cliora_profile_stop.argtypes = [POINTER(ProfileRow), c_int]
     for name in ('cliora_inside_index', 'cliora_outside_index', 'cliora_chart_layout', 'cliora_inside_fwd',
                  'cliora_outside_fwd', 'cliora_chart_bwd_begin', 'cliora_outside_bwd', 'cliora_inside_bwd',
                  'cliora_atten_scores', 'cliora_atten_max_fwd', 'cliora_atten_max_bwd', 'cliora_contrastive_loss',
@@ -122,7 +130,8 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_chart_layout', 'cliora_inside_fwd', 'cliora_outside_fwd', 'cliora_chart_bwd_begin',
            'cliora_outside_bwd', 'cliora_inside_bwd', 'cliora_atten_scores', 'cliora_atten_max_fwd',
            'cliora_atten_max_bwd', 'cliora_contrastive_loss', 'cliora_vg_loss', 'cliora_cky', 'cliora_linear',
-           'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count']
+           'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
+           'cliora_profile_start', 'cliora_profile_stop']
 
 
 def lib():
@@ -179,3 +188,15 @@ def layout(B, n, D, R, share) -> Layout:
 
 def launch_count() -> int:
     return int(lib().cliora_launch_count())
+
+
+def profile_start():
+    lib().cliora_profile_start()
+
+
+def profile_stop():
+    """-> {kernel class: dict(launches, ms, flops, bytes)} summed since profile_start()."""
+    rows = (ProfileRow * 64)()
+    n = lib().cliora_profile_stop(rows, 64)
+    return {rows[i].name.decode(): dict(launches=int(rows[i].launches), ms=rows[i].ms, flops=rows[i].flops,
+                                        bytes=rows[i].bytes) for i in range(n)}

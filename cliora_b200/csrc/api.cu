@@ -11,6 +11,7 @@
 namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
 long long g_launch_count = 0;
+Profiler g_prof;
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -98,6 +99,7 @@ static int project_level(const Ctx& c, int level, const float* chart_h, const fl
   p.W = Wcat; p.ldw = c.d.D;
   p.C = P; p.ldc = ncols; p.cmap = level_rows(c.d.n, level);
   p.M = c.d.B * (c.d.n - level); p.N = ncols; p.K = c.d.D;
+  p.tag = "gemm_cell_project";
   return launch_gemm(c.st, /*nt=*/true, p);
 }
 
@@ -109,17 +111,19 @@ static int cellgrad_level(const Ctx& c, int level, const float* GP, int ncols, c
   p.C = Gh; p.ldc = c.d.D; p.cmap = level_rows(c.d.n, level);
   p.M = c.d.B * (c.d.n - level); p.N = c.d.D; p.K = ncols;
   p.accumulate = 1;
+  p.tag = "gemm_cell_grad";
   return launch_gemm(c.st, /*nt=*/false, p);
 }
 
 static int dense_linear(cudaStream_t st, int M, int N, int K, const float* A, const float* W, const float* bias,
-                        int act, float* Cout) {
+                        int act, float* Cout, const char* tag = "gemm_linear") {
   GemmParams p{};
   p.A = A; p.lda = K; p.amap = dense_rows();
   p.W = W; p.ldw = K;
   p.C = Cout; p.ldc = N; p.cmap = dense_rows();
   p.bias = bias; p.act = act;
   p.M = M; p.N = N; p.K = K;
+  p.tag = tag;
   return launch_gemm(st, true, p);
 }
 
@@ -187,7 +191,11 @@ static SplitArgs split_args(const Ctx& c, int level, bool outside, const float* 
 template <bool VL>
 static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
   const size_t smem = (size_t)(a.D + a.N + 2 * a.R + 64) * sizeof(float);
-  cell_aggregate_kernel<VL><<<a.B * a.L, 128, smem, c.st>>>(a);
+  {
+    const double rows = (double)a.B * a.L * a.N;
+    ProfScope prof(c.st, "cell_aggregate", 2.0 * rows * a.D, 4.0 * (rows * (a.D + 2) + 2.0 * a.B * a.L * a.D));
+    cell_aggregate_kernel<VL><<<a.B * a.L, 128, smem, c.st>>>(a);
+  }
   CL_CHECK_LAUNCH("cell_aggregate_kernel");
   return CLIORA_OK;
 }
@@ -195,7 +203,11 @@ static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
 template <bool VL>
 static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
   const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64) * sizeof(float);
-  cell_bwd_kernel<VL><<<g.c.B * g.c.L, 256, smem, c.st>>>(g);
+  {
+    const double rows = (double)g.c.B * g.c.L * g.c.N;
+    ProfScope prof(c.st, "cell_bwd", 4.0 * rows * g.c.D, 4.0 * (2.0 * rows * (g.c.D + 2) + 3.0 * g.c.B * g.c.L * g.c.D));
+    cell_bwd_kernel<VL><<<g.c.B * g.c.L, 256, smem, c.st>>>(g);
+  }
   CL_CHECK_LAUNCH("cell_bwd_kernel");
   return CLIORA_OK;
 }
@@ -231,6 +243,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   p.C = bws + c.L.GZ; p.ldc = D; p.cmap = dense_rows();
   p.mask = s.Z; p.ldm = D;
   p.M = (int)rows; p.N = D; p.K = D;
+  p.tag = "gemm_compose_w2_bwd";
   CL_TRY(launch_gemm(c.st, /*nt=*/false, p));
 
   ScatterArgs sc{};
@@ -238,7 +251,10 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   sc.GZ = bws + c.L.GZ; sc.GE = bws + c.L.GE;
   sc.Gh_in = bws + c.L.Gh_in; sc.Gs_in = bws + c.L.Gs_in; sc.GP_in = bws + c.L.GP_in;
   sc.Gs_out = bws + c.L.Gs_out; sc.GP_out = bws + c.L.GP_out;
-  split_scatter_kernel<OUTSIDE><<<ceil_div(rows, 8), 256, 0, c.st>>>(sc);
+  {
+    ProfScope prof(c.st, "split_scatter", 2.0 * rows * D, 4.0 * rows * (7.0 * D + 3));
+    split_scatter_kernel<OUTSIDE><<<ceil_div(rows, 8), 256, 0, c.st>>>(sc);
+  }
   CL_CHECK_LAUNCH("split_scatter_kernel");
   (void)n;
   return CLIORA_OK;
@@ -264,6 +280,40 @@ const char* cliora_status_string(int s) {
 const char* cliora_last_cuda_error(void) { return g_last_cuda_error; }
 int cliora_abi_version(void) { return 1; }
 int64_t cliora_launch_count(void) { return g_launch_count; }
+
+void cliora_profile_start(void) {
+  for (auto& e : g_prof.entries) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  g_prof.entries.clear();
+  g_prof.on = true;
+}
+
+int cliora_profile_stop(cliora_profile_row* rows, int max_rows) {
+  g_prof.on = false;
+  cudaDeviceSynchronize();
+  int nrows = 0;
+  for (auto& e : g_prof.entries) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) ms = 0.f;
+    int r = -1;
+    for (int i = 0; i < nrows; ++i)
+      if (strncmp(rows[i].name, e.name, sizeof(rows[i].name)) == 0) { r = i; break; }
+    if (r < 0) {
+      if (nrows >= max_rows) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); continue; }
+      r = nrows++;
+      memset(&rows[r], 0, sizeof(rows[r]));
+      strncpy(rows[r].name, e.name, sizeof(rows[r].name) - 1);
+    }
+    rows[r].launches += 1;
+    rows[r].ms += ms;
+    rows[r].flops += e.flops;
+    rows[r].bytes += e.bytes;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_prof.entries.clear();
+  cudaGetLastError();
+  return nrows;
+}
 
 int64_t cliora_num_cells(int n) { return num_cells(n); }
 int64_t cliora_level_offset(int n, int level) { return lvl_off(n, level); }
@@ -328,10 +378,13 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
     if (level > 0) {
       SplitArgs s = split_args(c, level, false, inside_h, inside_s, nullptr, ws, w->b1);
       const int64_t rows = (int64_t)B * s.L * s.N;
-      split_build_kernel<false><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+      {
+        ProfScope prof(c.st, "split_build", 2.0 * rows * D, 4.0 * rows * (5.0 * D + 3));
+        split_build_kernel<false><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+      }
       CL_CHECK_LAUNCH("split_build_kernel<inside>");
       const int64_t r0 = B * inside_rows_before(n, level);
-      CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, w->W2, w->b2, 1, ws + c.L.Yin + r0 * D));
+      CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, w->W2, w->b2, 1, ws + c.L.Yin + r0 * D, "gemm_compose_w2"));
     }
     CellArgs a = cell_args(c, level, false, ws, inside_h, inside_s);
     a.obj = obj; a.keep = keep;
@@ -360,10 +413,13 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
   for (int level = n - 2; level >= 0; --level) {
     SplitArgs s = split_args(c, level, true, inside_h, inside_s, outside_s, ws, ob1);
     const int64_t rows = (int64_t)B * s.L * s.N;
-    split_build_kernel<true><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+    {
+      ProfScope prof(c.st, "split_build", 2.0 * rows * D, 4.0 * rows * (5.0 * D + 3));
+      split_build_kernel<true><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+    }
     CL_CHECK_LAUNCH("split_build_kernel<outside>");
     const int64_t r0 = B * outside_rows_before(n, level);
-    CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, oW2, ob2, 1, ws + c.L.Yout + r0 * D));
+    CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, oW2, ob2, 1, ws + c.L.Yout + r0 * D, "gemm_compose_w2"));
     CellArgs a = cell_args(c, level, true, ws, outside_h, outside_s);
     CL_TRY(launch_cell_aggregate<false>(c, a));
     if (level > 0) CL_TRY(project_level(c, level, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
@@ -526,7 +582,11 @@ int cliora_atten_max_fwd(int B, int ncell, int D, int R, const float* h, int64_t
   if (B < 1 || ncell < 0 || D < 4 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
   if (ncell == 0) return CLIORA_OK;
   dim3 grid(B, ceil_div((int64_t)B * ncell, 64));
-  atten_max_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, ncell, D, R, h, h_batch_stride, obj, smax, amax);
+  {
+    ProfScope prof((cudaStream_t)stream, "atten_max", 2.0 * B * ncell * (double)B * R * D,
+                   4.0 * ((double)B * ncell * D + (double)B * R * D + 2.0 * B * B * ncell));
+    atten_max_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, ncell, D, R, h, h_batch_stride, obj, smax, amax);
+  }
   CL_CHECK_LAUNCH("atten_max_kernel");
   return CLIORA_OK;
 }
@@ -538,6 +598,7 @@ int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t
   if (B < 1 || ncell < 0 || D < 4 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
   if (ncell == 0) return CLIORA_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, "atten_max_bwd", 4.0 * B * ncell * (double)B * D, 4.0 * 2.0 * B * ncell * (double)B * D);
   if (g_h) {
     atten_max_bwd_h_kernel<<<B * ncell, 128, 0, st>>>(B, ncell, D, R, obj, g_smax, amax, g_h, gh_batch_stride);
     CL_CHECK_LAUNCH("atten_max_bwd_h_kernel");
@@ -552,8 +613,9 @@ int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t
 int cliora_contrastive_loss(int B, int cells, int ncell, const float* smax, const float* inside_s,
                             const float* outside_s, float margin, float alpha, float* loss_out, float* g_smax,
                             float* g_inside_s, float* g_outside_s, float* scratch, cliora_stream_t stream) {
-  if (!smax || !inside_s || !outside_s || !loss_out || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (!inside_s || !outside_s || !loss_out || !scratch) return CLIORA_ERR_NULL_POINTER;
   if (B < 1 || cells < 1 || ncell < 0 || ncell > cells) return CLIORA_ERR_BAD_SHAPE;
+  if (ncell > 0 && !smax) return CLIORA_ERR_NULL_POINTER;
   if (g_smax && (!g_inside_s || !g_outside_s)) return CLIORA_ERR_NULL_POINTER;
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = scratch;                        // [ncell]

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/cliora_b200.h"
 
 #define CL_HD __host__ __device__ __forceinline__
@@ -129,5 +131,33 @@ inline int record_cuda_error(cudaError_t e, const char* what) {
   } while (0)
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- optional per-launch CUDA-event profiler (bench.py's roofline pass) ----
+struct ProfEntry {
+  const char* name;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+struct Profiler {
+  bool on = false;
+  std::vector<ProfEntry> entries;
+};
+extern Profiler g_prof;
+// Records an event before and after whatever is launched on `st` inside its lifetime.
+struct ProfScope {
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(cudaStream_t s, const char* name, double flops, double bytes) : st(s) {
+    if (!g_prof.on) return;
+    ProfEntry e{name, nullptr, nullptr, flops, bytes};
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, st);
+    g_prof.entries.push_back(e);
+    idx = (int)g_prof.entries.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof.entries[idx].b, st);
+  }
+};
 
 }  // namespace cliora

@@ -28,6 +28,7 @@ struct GemmParams {
   int k_chunk;     // split-K: K range per blockIdx.z (multiple of 16); 0 = no split
   int64_t split_stride;  // floats between split-K partial outputs
   int vec_a, vec_w, vec_c;  // 16-byte vector access allowed (alignment checked on the host)
+  const char* tag;          // profiler label (host only)
 };
 
 constexpr int kBN = 64;
@@ -286,6 +287,8 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p) {
   p.vec_c = aligned16(p.C) && (p.ldc % 4 == 0);
   const int64_t ctas128 = (int64_t)ceil_div(p.M, 128) * ceil_div(p.N, kBN);
   const bool big = ctas128 >= 2 * 148;
+  ProfScope prof(st, p.tag ? p.tag : "gemm", 2.0 * p.M * p.N * p.K,
+                 4.0 * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * (p.mask ? 2 : 1)));
   dim3 grid(ceil_div(p.N, kBN), ceil_div(p.M, big ? 128 : 64), 1);
   if (nt) {
     if (big) gemm_simt_kernel<8, false, false><<<grid, 256, 0, st>>>(p);
@@ -313,8 +316,10 @@ inline int64_t tn_scratch_floats(int rows, int Ka, int Kb) {
 
 // C[Ka,Kb] (+)= A[rows,Ka]^T B[rows,Kb]   (deterministic split-K: partials to scratch, then ordered sum)
 inline int launch_gemm_tn(cudaStream_t st, int rows, int Ka, int Kb, const float* A, int64_t lda, const float* B,
-                          int64_t ldb, float* C, int64_t ldc, int accumulate, float* scratch) {
+                          int64_t ldb, float* C, int64_t ldc, int accumulate, float* scratch,
+                          const char* tag = "gemm_wgrad") {
   if (Ka <= 0 || Kb <= 0) return CLIORA_OK;
+  ProfScope prof(st, tag, 2.0 * rows * Ka * Kb, 4.0 * ((double)rows * (Ka + Kb) + (double)Ka * Kb));
   const int splits = tn_splits(rows, Ka, Kb);
   GemmParams p{};
   p.A = A; p.lda = lda; p.amap = dense_rows();

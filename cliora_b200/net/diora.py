@@ -100,7 +100,7 @@ class DioraBase(nn.Module):
         super().cuda(device)
         if self.index is not None:
             self.index.cuda = True
-        # the reference returns None here (diora.py:272-275); returning self is a superset
+        return self   # the reference returns None here (diora.py:272-275); returning self is a superset
 
     def get(self, chart, level):
         off = self.index.get_offset(self.length)[level]

@@ -234,6 +234,20 @@ int cliora_matmul_tn(int M, int Ka, int Kb, const float* A, const float* B, floa
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t cliora_launch_count(void);
 
+/* Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+ * pass; off by default, adds two event records per launch when on).  flops / bytes are the
+ * ALGORITHMIC counts of the launches (DESIGN.md states the per-unit figures). */
+typedef struct cliora_profile_row {
+  char name[48];
+  int64_t launches;
+  double ms;     /* summed device time between the two events of every launch of this class */
+  double flops;
+  double bytes;
+} cliora_profile_row;
+void cliora_profile_start(void);
+/* Synchronises the device, aggregates by kernel class into rows[0..ret), returns the row count. */
+int cliora_profile_stop(cliora_profile_row* rows, int max_rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -380,3 +380,54 @@ def init_params(D: int, share=True, seed=0, dtype=torch.float32) -> Dict[str, to
         for k in ('h_fcs.0.weight', 'h_fcs.0.bias', 'h_fcs.2.weight', 'h_fcs.2.bias'):
             P['outside_compose_func.' + k] = rn(*P['inside_compose_func.' + k].shape)
     return P
+
+
+class CpuClioraStep(object):
+    """One full CLIORA training step on CPU in the reference's own dense formulation
+    (Net.forward -> losses -> backward -> clip 5.0 -> Adam; cliora/net/trainer.py:272-304,450-455,483-501).
+    Used ONLY as bench.py's cpu_baseline / ``--impl reference`` arm and by tests as a checker."""
+
+    def __init__(self, D=400, E=1024, V=8000, F=2048, k_neg=100, seed=1234, lr=2e-3, obj_feats=True,
+                 alpha_vg=1.0, alpha_contr=1.0, margin=0.2):
+        g = torch.Generator().manual_seed(seed)
+        self.obj_feats = obj_feats
+        self.P = {k: v.requires_grad_() for k, v in init_params(D, share=True, seed=seed).items()
+                  if not k.startswith('outside_')}
+        for k in list(self.P):
+            if k.startswith('inside_'):
+                self.P['outside_' + k[len('inside_'):]] = self.P[k]
+        self.emb = torch.randn(V, E, generator=g)                       # frozen with --obj_feats (trainer.py:538-541)
+        self.mat = torch.randn(D, E, generator=g).requires_grad_()
+        self.mat1 = torch.randn(D, E, generator=g).requires_grad_()
+        self.recon_mat = torch.randn(D, E, generator=g).requires_grad_()
+        self.enc = {'fc.weight': (0.02 * torch.randn(D, F, generator=g)).requires_grad_(),
+                    'fc.bias': (0.02 * torch.randn(D, generator=g)).requires_grad_(),
+                    'fc_vis.weight': (0.02 * torch.randn(D, F, generator=g)).requires_grad_(),
+                    'fc_vis.bias': (0.02 * torch.randn(D, generator=g)).requires_grad_()}
+        self.alpha_vg, self.alpha_contr, self.margin = alpha_vg, alpha_contr, margin
+        uniq = {id(v): v for v in list(self.P.values()) + [self.mat, self.mat1, self.recon_mat] + list(self.enc.values())}
+        self.params = list(uniq.values())
+        self.opt = torch.optim.Adam(self.params, lr=lr, betas=(0.9, 0.999), eps=1e-8)
+
+    def loss(self, sentences, neg_samples, obj_feats=None, keep=None):
+        x_span, x_word = embed(self.emb, self.mat, self.mat1, sentences)
+        if self.obj_feats:
+            obj_span, obj_word = image_encoder(self.enc, obj_feats)
+            out = chart_forward(self.P, x_span, obj_span, keep)
+            aas = all_atten_score(out.inside_h, out.outside_h, obj_span)
+            vg = vg_atten_score(x_word, obj_word, training=True)
+            losses = [reconstruction_loss(self.emb, self.recon_mat, sentences, neg_samples, out.outside_h),
+                      vg_loss(vg, self.alpha_vg),
+                      contrastive_loss(aas, out.inside_s, out.outside_s, self.margin, self.alpha_contr)]
+        else:
+            out = chart_forward(self.P, x_span)
+            losses = [reconstruction_loss(self.emb, self.recon_mat, sentences, neg_samples, out.outside_h)]
+        return sum(losses), losses
+
+    def step(self, sentences, neg_samples, obj_feats=None, keep=None):
+        self.opt.zero_grad()
+        total, losses = self.loss(sentences, neg_samples, obj_feats, keep)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, 5.0)
+        self.opt.step()
+        return total.item(), [l.item() for l in losses]

@@ -88,18 +88,9 @@ def test_cliora_chart_vs_golden(golden, name):
         assert rel_err(getattr(m, k), blob[k]) < TOL, k
 
 
-@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True)])
-def test_chart_vs_oracle_live(B, n, D, R, share):
-    """Same seeded inputs through the CUDA path and the CPU oracle, fwd + bwd, at the real hidden size."""
+def _oracle_run(dt, B, n, D, R, share):
     from oracle import cliora_oracle as O
-    if R:
-        from cliora_b200.net.cliora import DioraMLP
-        m = DioraMLP(D, share=share).cuda()
-    else:
-        from cliora_b200.net.diora import DioraMLP
-        m = DioraMLP(D, share=share).cuda()
     P0 = O.init_params(D, share=share, seed=7)
-    _fill(m, P0)
     g = torch.Generator().manual_seed(8)
     x = torch.randn(B, n, D, generator=g)
     obj = 0.05 * torch.randn(B, R, D, generator=g) if R else None
@@ -107,17 +98,41 @@ def test_chart_vs_oracle_live(B, n, D, R, share):
     keep = (torch.rand(B, C, R, generator=g) >= 0.1) if R else None
     ct = {k: torch.randn(B, C, D if k.endswith('h') else 1, generator=g)
           for k in ('inside_h', 'inside_s', 'outside_h', 'outside_s')}
-    # oracle
-    P = {k: v.clone().requires_grad_() for k, v in P0.items() if share is False or not k.startswith('outside_')}
+    P = {k: v.to(dt).clone().requires_grad_() for k, v in P0.items() if share is False or not k.startswith('outside_')}
     if share:
         for k in list(P):
             if k.startswith('inside_'):
                 P['outside_' + k[len('inside_'):]] = P[k]
-    xo = x.clone().requires_grad_()
-    oo = obj.clone().requires_grad_() if R else None
+    xo = x.to(dt).requires_grad_()
+    oo = obj.to(dt).requires_grad_() if R else None
     out = O.chart_forward(P, xo, oo, keep)
-    sum((getattr(out, k) * ct[k]).sum() for k in ct).backward()
-    # cuda
+    sum((getattr(out, k) * ct[k].to(dt)).sum() for k in ct).backward()
+    res = {k: getattr(out, k).detach() for k in ct}
+    res['grad_x'] = xo.grad
+    if R:
+        res['grad_obj'] = oo.grad
+    for k in P:
+        if not (share and k.startswith('outside_')):
+            res['grad:' + k] = P[k].grad
+    return P0, x, obj, keep, ct, res
+
+
+@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True)])
+def test_chart_vs_oracle_live(B, n, D, R, share):
+    """Same seeded inputs through the CUDA path and the CPU oracle, fwd + bwd, at the real hidden size.
+
+    The arbiter is the oracle in float64.  Chart tensors must be within 1e-4 (of max).  Gradients must be
+    within 1e-4 too, except where the reference's own precision (the oracle in float32 on CPU) is already
+    further than that from float64 (deep charts: ~5e-4 at n=20) -- there the CUDA path must be no worse
+    than 2x the float32 reference's own error."""
+    if R:
+        from cliora_b200.net.cliora import DioraMLP
+    else:
+        from cliora_b200.net.diora import DioraMLP
+    P0, x, obj, keep, ct, ref64 = _oracle_run(torch.float64, B, n, D, R, share)
+    _, _, _, _, _, ref32 = _oracle_run(torch.float32, B, n, D, R, share)
+    m = DioraMLP(D, share=share).cuda()
+    _fill(m, P0)
     xc = x.cuda().requires_grad_()
     oc = obj.cuda().requires_grad_() if R else None
     m.train()
@@ -127,15 +142,17 @@ def test_chart_vs_oracle_live(B, n, D, R, share):
     else:
         m(xc, xc)
     for k in ct:
-        assert rel_err(getattr(m, k), getattr(out, k)) < TOL, k
+        assert rel_err(getattr(m, k), ref64[k]) < TOL, k
     sum((getattr(m, k) * ct[k].cuda()).sum() for k in ct).backward()
-    assert rel_err(xc.grad, xo.grad) < TOL
+    mine = {'grad_x': xc.grad}
     if R:
-        assert rel_err(oc.grad, oo.grad) < TOL
+        mine['grad_obj'] = oc.grad
     for k, v in _grads(m).items():
-        if share and k.startswith('outside_'):
-            continue
-        assert rel_err(v, P[k].grad) < TOL, k
+        if not (share and k.startswith('outside_')):
+            mine['grad:' + k] = v
+    for k, v in mine.items():
+        floor = rel_err(ref32[k], ref64[k])
+        assert rel_err(v, ref64[k]) < max(TOL, 2 * floor), (k, floor)
 
 
 def test_hooks_receive_reference_shapes(golden):

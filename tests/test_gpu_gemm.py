@@ -18,13 +18,15 @@ def test_linear(M, N, K, act):
     L = _lib()
     g = torch.Generator().manual_seed(M + N)
     A = torch.randn(M, K, generator=g).cuda()
+    if act == 2:
+        A = A * 0.05   # keep tanh out of saturation so the check is about the GEMM, not tanh'(x) ~ 0
     W = torch.randn(N, K, generator=g).cuda()
     b = torch.randn(N, generator=g).cuda()
     C = torch.empty(M, N, device='cuda')
     L.check(L.lib().cliora_linear(M, N, K, L.ptr(A), L.ptr(W), L.ptr(b), act, L.ptr(C), L.stream()), 'linear')
     ref = A.double() @ W.double().t() + b.double()
     ref = {0: ref, 1: torch.relu(ref), 2: torch.tanh(ref)}[act]
-    assert rel_err(C, ref) < 2e-6
+    assert rel_err(C, ref) < (1e-5 if act == 2 else 2e-6)   # tanhf is a few ulp
 
 
 @pytest.mark.parametrize('M,N,K', [(5, 8, 12), (3200, 400, 400), (640, 400, 1200), (77, 48, 101)])
