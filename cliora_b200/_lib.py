@@ -41,7 +41,7 @@ class WeightGrads(Structure):
 _L_FIELDS = ['ws_floats', 'bws_floats', 'rows_in', 'rows_out', 'PI', 'Pin', 'Pout', 'q_in', 'nrm_in', 'nrm2_in',
              'att_in', 'nrm_out', 'leaf_t', 'Zin', 'Yin', 'Ein', 'Prin', 'Zout', 'Yout', 'Eout', 'Prout',
              'Wcat_in', 'Wcat_out', 'Gh_in', 'Gs_in', 'GP_in', 'Gh_out', 'Gs_out', 'GP_out', 'GA2', 'coef',
-             'GE', 'GZ', 'splitk', 'gu']
+             'GE', 'GZ', 'splitk', 'gu', 'W2p', 'W2Tp', 'oW2p', 'oW2Tp']
 
 
 class ProfileRow(Structure):
@@ -114,6 +114,12 @@ def _declare(lib):
     lib.cliora_matmul_tn_scratch_floats.restype = c_int64
     lib.cliora_matmul_tn_scratch_floats.argtypes = [c_int, c_int, c_int]
     lib.cliora_matmul_tn.argtypes = [c_int, c_int, c_int, vp, vp, vp, c_int, vp, st]
+    lib.cliora_split_tf32.argtypes = [vp, c_int64, vp, st]
+    lib.cliora_split_tf32.restype = c_int
+    lib.cliora_tc_linear.argtypes = [c_int, c_int, c_int, vp, vp, vp, c_int, vp, st]
+    lib.cliora_tc_linear.restype = c_int
+    lib.cliora_debug_set.argtypes = [c_int, c_int]
+    lib.cliora_debug_set.restype = None
     lib.cliora_profile_start.restype = None
     lib.cliora_profile_stop.restype = c_int
     lib.cliora_profile_stop.argtypes = [POINTER(ProfileRow), c_int]
@@ -131,7 +137,7 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_outside_bwd', 'cliora_inside_bwd', 'cliora_atten_scores', 'cliora_atten_max_fwd',
            'cliora_atten_max_bwd', 'cliora_contrastive_loss', 'cliora_vg_loss', 'cliora_cky', 'cliora_linear',
            'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
-           'cliora_profile_start', 'cliora_profile_stop']
+           'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set']
 
 
 def lib():

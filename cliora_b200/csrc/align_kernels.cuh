@@ -119,33 +119,74 @@ __global__ __launch_bounds__(128) void atten_max_bwd_h_kernel(int B, int ncell, 
   }
 }
 
-// g_obj[c,r,:] += sum_{a,cell : amax == r} g[a,c,cell] h[a,cell,:]    one block (128 thr) per (c,r); deterministic
+// g_obj[c,r,:] += sum_{a,cell : amax == r} g[a,c,cell] h[a,cell,:]    one block (128 thr) per (c,r).
+// The (a,cell) entries of image c are scanned 128 at a time; matches are compacted in index order with
+// warp ballots (deterministic), then their h rows are accumulated by all threads.
 __global__ __launch_bounds__(128) void atten_max_bwd_obj_kernel(int B, int ncell, int D, int R,
                                                                 const float* __restrict__ h, int64_t h_bstride,
                                                                 const float* __restrict__ g,
                                                                 const int32_t* __restrict__ amax,
                                                                 float* __restrict__ g_obj) {
+  __shared__ int s_row[128];
+  __shared__ float s_gv[128];
+  __shared__ int s_wcount[4];
   const int c = blockIdx.x / R, r = blockIdx.x % R;
-  float* dst = g_obj + ((int64_t)c * R + r) * D;
-  // D <= 4 * 128 * 4 handled by the j loop; accumulators live in registers per j chunk
-  for (int j = threadIdx.x * 4; j < D; j += blockDim.x * 4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int a = 0; a < B; ++a) {
-      const int64_t base = ((int64_t)a * B + c) * ncell;
-      for (int cell = 0; cell < ncell; ++cell) {
-        if (amax[base + cell] == r) {
-          const float gv = g[base + cell];
-          if (gv != 0.f) {
-            const float4 hv = ld4(h + ((int64_t)a * h_bstride + cell) * D + j);
-            acc.x = fmaf(gv, hv.x, acc.x); acc.y = fmaf(gv, hv.y, acc.y);
-            acc.z = fmaf(gv, hv.z, acc.z); acc.w = fmaf(gv, hv.w, acc.w);
-          }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = B * ncell;
+  // each thread owns columns j = tid*4 + t*512 (D <= 2048)
+  float4 acc[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e0 = 0; e0 < E; e0 += 128) {
+    const int e = e0 + tid;
+    bool hit = false;
+    float gv = 0.f;
+    int a = 0, cell = 0;
+    if (e < E) {
+      a = e / ncell;
+      cell = e % ncell;
+      const int64_t o = ((int64_t)a * B + c) * ncell + cell;
+      if (amax[o] == r) {
+        gv = g[o];
+        hit = gv != 0.f;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_wcount[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wcount[w];
+    const int total = s_wcount[0] + s_wcount[1] + s_wcount[2] + s_wcount[3];
+    if (hit) {
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      s_row[pos] = (int)((int64_t)a * h_bstride + cell);
+      s_gv[pos] = gv;
+    }
+    __syncthreads();
+    for (int i = 0; i < total; ++i) {
+      const float w = s_gv[i];
+      const float* hr = h + (int64_t)s_row[i] * D;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = tid * 4 + t * 512;
+        if (j < D) {
+          const float4 hv = ld4(hr + j);
+          acc[t].x = fmaf(w, hv.x, acc[t].x); acc[t].y = fmaf(w, hv.y, acc[t].y);
+          acc[t].z = fmaf(w, hv.z, acc[t].z); acc[t].w = fmaf(w, hv.w, acc[t].w);
         }
       }
     }
-    float4 old = ld4(dst + j);
-    old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += acc.w;
-    st4(dst + j, old);
+    __syncthreads();
+  }
+  float* dst = g_obj + ((int64_t)c * R + r) * D;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = tid * 4 + t * 512;
+    if (j < D) {
+      float4 old = ld4(dst + j);
+      old.x += acc[t].x; old.y += acc[t].y; old.z += acc[t].z; old.w += acc[t].w;
+      st4(dst + j, old);
+    }
   }
 }
 

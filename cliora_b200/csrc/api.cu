@@ -7,11 +7,13 @@
 #include "cky_kernels.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "tc_gemm.cuh"
 
 namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
 long long g_launch_count = 0;
 Profiler g_prof;
+int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -40,16 +42,20 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   L.att_in = R > 0 ? take(B * C * R) : -1;
   L.nrm_out = take(B * C);
   L.leaf_t = take(B * n * D);
-  L.Zin = take(L.rows_in * D);
-  L.Yin = take(L.rows_in * D);
+  L.Zin = take(2 * L.rows_in * D);   // split pairs: hi part, then lo part at + rows * D
+  L.Yin = take(2 * L.rows_in * D);
   L.Ein = take(L.rows_in);
   L.Prin = take(L.rows_in);
-  L.Zout = take(L.rows_out * D);
-  L.Yout = take(L.rows_out * D);
+  L.Zout = take(2 * L.rows_out * D);
+  L.Yout = take(2 * L.rows_out * D);
   L.Eout = take(L.rows_out);
   L.Prout = take(L.rows_out);
   L.Wcat_in = take(PI * D * D);
   L.Wcat_out = take(2 * D * D);
+  L.W2p = take(2 * D * D);
+  L.W2Tp = take(2 * D * D);
+  L.oW2p = d.share ? L.W2p : take(2 * D * D);
+  L.oW2Tp = d.share ? L.W2Tp : take(2 * D * D);
   L.ws_floats = o;
 
   const int64_t max_rows = B * n * (n - 1) > 0 ? B * n * (n - 1) : 4;
@@ -81,6 +87,7 @@ struct Ctx {
   cliora_layout L;
   int64_t C;
   cudaStream_t st;
+  bool use_tc;   // compose GEMMs on tcgen05 (3xTF32 split pairs) instead of the SIMT fp32 kernel
 };
 
 static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
@@ -89,6 +96,7 @@ static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
   CL_TRY(compute_layout(c.d, c.L));
   c.C = num_cells(dims->n);
   c.st = (cudaStream_t)stream;
+  c.use_tc = (dims->D >= 32) && (g_debug[1] == 0);
   return CLIORA_OK;
 }
 
@@ -154,6 +162,7 @@ static CellArgs cell_args(const Ctx& c, int level, bool outside, float* ws, floa
     } else {
       const int64_t r0 = c.d.B * inside_rows_before(n, level);
       a.Y = ws + c.L.Yin + r0 * c.d.D; a.E = ws + c.L.Ein + r0; a.Pr = ws + c.L.Prin + r0;
+      a.y_lo_off = c.use_tc ? c.L.rows_in * c.d.D : 0;
     }
     a.q = c.d.R > 0 ? ws + c.L.q_in : nullptr;
     a.nrm = ws + c.L.nrm_in;
@@ -164,6 +173,7 @@ static CellArgs cell_args(const Ctx& c, int level, bool outside, float* ws, floa
     a.sp = 1; a.sk = a.L;
     const int64_t r0 = c.d.B * outside_rows_before(n, level);
     a.Y = ws + c.L.Yout + r0 * c.d.D; a.E = ws + c.L.Eout + r0; a.Pr = ws + c.L.Prout + r0;
+    a.y_lo_off = c.use_tc ? c.L.rows_out * c.d.D : 0;
     a.q = nullptr;
     a.nrm = ws + c.L.nrm_out;
   }
@@ -185,7 +195,62 @@ static SplitArgs split_args(const Ctx& c, int level, bool outside, const float* 
   const int64_t r0 = outside ? c.d.B * outside_rows_before(n, level) : c.d.B * inside_rows_before(n, level);
   s.Z = ws + (outside ? c.L.Zout : c.L.Zin) + r0 * c.d.D;
   s.E = ws + (outside ? c.L.Eout : c.L.Ein) + r0;
+  s.z_lo_off = c.use_tc ? (outside ? c.L.rows_out : c.L.rows_in) * c.d.D : 0;
   return s;
+}
+
+// Y[level rows] = relu(Z[level rows] W2^T + b2): the dense contraction of the compose MLP (diora.py:65-72)
+static int compose_gemm(const Ctx& c, bool outside, int64_t r0, int64_t rows, const float* W2, const float* b2,
+                        float* ws) {
+  const int D = c.d.D;
+  const int64_t total = outside ? c.L.rows_out : c.L.rows_in;
+  float* Zb = ws + (outside ? c.L.Zout : c.L.Zin);
+  float* Yb = ws + (outside ? c.L.Yout : c.L.Yin);
+  if (c.use_tc) {
+    tc::PairRef A{Zb, total, D, total * D};
+    tc::PairRef W{ws + (outside ? c.L.oW2p : c.L.W2p), D, D, (int64_t)D * D};
+    tc::TcEpilogue ep{};
+    ep.C = Yb + r0 * D; ep.ldc = D; ep.cmap = dense_rows();
+    ep.bias = b2; ep.act = 1;
+    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2", g_debug[0]);
+  }
+  return dense_linear(c.st, (int)rows, D, D, Zb + r0 * D, W2, b2, 1, Yb + r0 * D, "gemm_compose_w2");
+}
+
+// GZ[level rows] = (GY[level rows] W2) * (Z > 0)
+static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows, const float* W2, float* ws,
+                            float* GZ) {
+  const int D = c.d.D;
+  const int64_t total = outside ? c.L.rows_out : c.L.rows_in;
+  float* Zb = ws + (outside ? c.L.Zout : c.L.Zin);
+  float* Yb = ws + (outside ? c.L.Yout : c.L.Yin);
+  if (c.use_tc) {
+    tc::PairRef A{Yb, total, D, total * D};
+    tc::PairRef W{ws + (outside ? c.L.oW2Tp : c.L.W2Tp), D, D, (int64_t)D * D};
+    tc::TcEpilogue ep{};
+    ep.C = GZ; ep.ldc = D; ep.cmap = dense_rows();
+    ep.mask = Zb + r0 * D; ep.ldm = D; ep.mask_lo_off = total * D;
+    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", g_debug[0]);
+  }
+  GemmParams p{};
+  p.A = Yb + r0 * D; p.lda = D; p.amap = dense_rows();
+  p.W = W2; p.ldw = D;
+  p.C = GZ; p.ldc = D; p.cmap = dense_rows();
+  p.mask = Zb + r0 * D; p.ldm = D;
+  p.M = (int)rows; p.N = D; p.K = D;
+  p.tag = "gemm_compose_w2_bwd";
+  return launch_gemm(c.st, /*nt=*/false, p);
+}
+
+static int prepare_w2_pairs(const Ctx& c, const float* W2, float* pair, float* pairT) {
+  const int D = c.d.D;
+  const int64_t n = (int64_t)D * D;
+  tc::split_tf32_kernel<<<ceil_div(n, 256), 256, 0, c.st>>>(W2, n, pair);
+  CL_CHECK_LAUNCH("split_tf32_kernel");
+  dim3 grid(ceil_div(D, 32), ceil_div(D, 32));
+  tc::split_tf32_transpose_kernel<<<grid, dim3(32, 8), 0, c.st>>>(W2, D, D, D, pairT);
+  CL_CHECK_LAUNCH("split_tf32_transpose_kernel");
+  return CLIORA_OK;
 }
 
 template <bool VL>
@@ -237,14 +302,8 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   const float* b1 = (OUTSIDE && !c.d.share) ? w->ob1 : w->b1;
   SplitArgs s = split_args(c, level, OUTSIDE, ih, is_, os_, ws, b1);
   const int64_t rows = (int64_t)B * s.L * s.N;
-  GemmParams p{};
-  p.A = g.c.Y; p.lda = D; p.amap = dense_rows();
-  p.W = W2; p.ldw = D;
-  p.C = bws + c.L.GZ; p.ldc = D; p.cmap = dense_rows();
-  p.mask = s.Z; p.ldm = D;
-  p.M = (int)rows; p.N = D; p.K = D;
-  p.tag = "gemm_compose_w2_bwd";
-  CL_TRY(launch_gemm(c.st, /*nt=*/false, p));
+  const int64_t r0 = OUTSIDE ? B * outside_rows_before(n, level) : B * inside_rows_before(n, level);
+  CL_TRY(compose_gemm_bwd(c, OUTSIDE, r0, rows, W2, ws, bws + c.L.GZ));
 
   ScatterArgs sc{};
   sc.s = s;
@@ -371,6 +430,10 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
 
   pack_weights_kernel<<<296, 256, 0, c.st>>>(D, PI, w->W1, w->Wb, oW1, oWb, Wcat_in, ws + c.L.Wcat_out);
   CL_CHECK_LAUNCH("pack_weights_kernel");
+  if (c.use_tc) {
+    CL_TRY(prepare_w2_pairs(c, w->W2, ws + c.L.W2p, ws + c.L.W2Tp));
+    if (!c.d.share) CL_TRY(prepare_w2_pairs(c, w->oW2, ws + c.L.oW2p, ws + c.L.oW2Tp));
+  }
 
   // leaves: t = tanh(W_leaf x + b); h = finalize(t)
   CL_TRY(dense_linear(c.st, B * n, D, D, x, w->W_leaf, w->b_leaf, 2, ws + c.L.leaf_t));
@@ -384,7 +447,7 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
       }
       CL_CHECK_LAUNCH("split_build_kernel<inside>");
       const int64_t r0 = B * inside_rows_before(n, level);
-      CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, w->W2, w->b2, 1, ws + c.L.Yin + r0 * D, "gemm_compose_w2"));
+      CL_TRY(compose_gemm(c, false, r0, rows, w->W2, w->b2, ws));
     }
     CellArgs a = cell_args(c, level, false, ws, inside_h, inside_s);
     a.obj = obj; a.keep = keep;
@@ -419,7 +482,7 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
     }
     CL_CHECK_LAUNCH("split_build_kernel<outside>");
     const int64_t r0 = B * outside_rows_before(n, level);
-    CL_TRY(dense_linear(c.st, (int)rows, D, D, s.Z, oW2, ob2, 1, ws + c.L.Yout + r0 * D, "gemm_compose_w2"));
+    CL_TRY(compose_gemm(c, true, r0, rows, oW2, ob2, ws));
     CellArgs a = cell_args(c, level, true, ws, outside_h, outside_s);
     CL_TRY(launch_cell_aggregate<false>(c, a));
     if (level > 0) CL_TRY(project_level(c, level, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
@@ -480,8 +543,13 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
   const float* GY = ws + c.L.Yout;
   const float* Z = ws + c.L.Zout;
   const float* GPo = bws + c.L.GP_out;
-  if (dW2) CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch));
-  if (db2) CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
+  const int64_t lo_out = c.use_tc ? c.L.rows_out * D : 0;
+  if (dW2)
+    CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch, "gemm_wgrad", lo_out, lo_out));
+  if (db2) {
+    CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
+    if (lo_out) CL_TRY(colsum(c.st, GY + lo_out, D, c.L.rows_out, D, db2, 1, scratch));
+  }
   if (dW1) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPo, 2 * D, outside_h, D, dW1 + D, 2 * D, 0, scratch));
   if (dWb) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPo + D, 2 * D, outside_h, D, dWb, D, 0, scratch));
   if (!sh) {
@@ -532,8 +600,13 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   const float* Z = ws + c.L.Zin;
   const float* GPi = bws + c.L.GP_in;
   const int ldp = PI * D;
-  if (grads->W2) CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch));
-  if (grads->b2) CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
+  const int64_t lo_in = c.use_tc ? c.L.rows_in * D : 0;
+  if (grads->W2)
+    CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch, "gemm_wgrad", lo_in, lo_in));
+  if (grads->b2) {
+    CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
+    if (lo_in) CL_TRY(colsum(c.st, GY + lo_in, D, c.L.rows_in, D, grads->b2, 1, scratch));
+  }
   if (grads->W1) {
     CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi, ldp, inside_h, D, grads->W1, 2 * D, 0, scratch));
     CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + D, ldp, inside_h, D, grads->W1 + D, 2 * D, acc, scratch));
@@ -541,8 +614,8 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   if (grads->Wb) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + 2 * D, ldp, inside_h, D, grads->Wb, D, acc, scratch));
   if (grads->b1) CL_TRY(colsum(c.st, GPi, ldp, BC, D, grads->b1, 0, scratch));
   if (vl && grad_obj) {
-    dim3 grid(ceil_div(D, 128), B);
-    obj_grad_kernel<64><<<grid, 128, 0, c.st>>>(D, R, c.C, bws + c.L.GA2, ws + c.L.q_in, bws + c.L.coef, grad_obj, 0);
+    dim3 grid(ceil_div(D, 32), B);
+    obj_grad_kernel<64><<<grid, dim3(32, 4), 0, c.st>>>(D, R, c.C, bws + c.L.GA2, ws + c.L.q_in, bws + c.L.coef, grad_obj, 0);
     CL_CHECK_LAUNCH("obj_grad_kernel");
   }
   if (!had_outside) {
@@ -678,6 +751,32 @@ int cliora_matmul_nn(int M, int N, int K, const float* A, const float* Bm, float
   p.M = M; p.N = N; p.K = K;
   p.accumulate = accumulate;
   return launch_gemm((cudaStream_t)stream, false, p);
+}
+
+void cliora_debug_set(int key, int value) {
+  if (key >= 0 && key < 8) g_debug[key] = value;
+}
+
+int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_t stream) {
+  if (!x || !out_pair) return CLIORA_ERR_NULL_POINTER;
+  if (n <= 0) return CLIORA_OK;
+  tc::split_tf32_kernel<<<ceil_div(n, 256 * 4) < 1184 ? ceil_div(n, 256 * 4) : 1184, 256, 0, (cudaStream_t)stream>>>(
+      x, n, out_pair);
+  CL_CHECK_LAUNCH("split_tf32_kernel");
+  return CLIORA_OK;
+}
+
+int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pair, const float* bias, int act,
+                     float* C, cliora_stream_t stream) {
+  if (!A_pair || !W_pair || !C) return CLIORA_ERR_NULL_POINTER;
+  if (M < 0 || N < 1 || K < 1) return CLIORA_ERR_BAD_SHAPE;
+  tc::PairRef A{A_pair, M, K, (int64_t)M * K};
+  tc::PairRef W{W_pair, N, K, (int64_t)N * K};
+  if (!tc::tc_supported(N, K, A, W)) return CLIORA_ERR_UNSUPPORTED;
+  tc::TcEpilogue ep{};
+  ep.C = C; ep.ldc = N; ep.cmap = dense_rows();
+  ep.bias = bias; ep.act = act;
+  return tc::launch_tc_gemm_nt((cudaStream_t)stream, A, 0, W, M, N, K, ep, "tc_gemm_linear", g_debug[0]);
 }
 
 int64_t cliora_matmul_tn_scratch_floats(int M, int Ka, int Kb) { return tn_scratch_floats(M, Ka, Kb); }

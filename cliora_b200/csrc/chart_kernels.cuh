@@ -47,8 +47,9 @@ struct SplitArgs {
   int ldPin;
   int iAl;            // column offset of the "first argument" projection in Pin (0, or 3D when !share && outside)
   const float* b1;
-  float* Z;           // level block [B*L*N, D]
+  float* Z;           // level block [B*L*N, D] (hi part of the split pair when z_lo_off != 0)
   float* E;           // level block [B*L*N]
+  int64_t z_lo_off;   // floats from Z to the lo part of the pair (0: store plain fp32)
 };
 
 template <bool OUTSIDE>
@@ -87,7 +88,14 @@ __global__ __launch_bounds__(256) void split_build_kernel(const SplitArgs a) {
     o.y = fmaxf(x.y + y.y + bb.y, 0.f);
     o.z = fmaxf(x.z + y.z + bb.z, 0.f);
     o.w = fmaxf(x.w + y.w + bb.w, 0.f);
-    st4(z + j, o);
+    if (a.z_lo_off != 0) {
+      float4 hi, lo;
+      split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+      st4(z + j, hi);
+      st4(z + a.z_lo_off + j, lo);
+    } else {
+      st4(z + j, o);
+    }
     const float4 hv = ld4(h1 + j), vv = ld4(V + j);
     dot = fmaf(hv.x, vv.x, dot);
     dot = fmaf(hv.y, vv.y, dot);
@@ -113,6 +121,7 @@ struct CellArgs {
   int64_t C;
   int sp, sk;          // row(b,p,k) = b*L*N + p*sp + k*sk   (inside: sp=N, sk=1; outside: sp=1, sk=L)
   float* Y;            // level block [B*L*N, D]   (bwd: overwritten with its gradient)
+  int64_t y_lo_off;    // bwd: floats from Y to the lo part of the gradient pair (0: plain fp32)
   const float* E;      // level block [B*L*N] or nullptr (leaf)
   float* Pr;           // level block [B*L*N] softmax probabilities (fwd out, bwd in)
   float* chart_h;      // [B,C,D]
@@ -398,7 +407,14 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
         o.y = yv.y > 0.f ? pk * gv.y : 0.f;
         o.z = yv.z > 0.f ? pk * gv.z : 0.f;
         o.w = yv.w > 0.f ? pk * gv.w : 0.f;
-        st4(y + j, o);
+        if (a.y_lo_off != 0) {
+          float4 hi, lo;
+          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+          st4(y + j, hi);
+          st4(y + a.y_lo_off + j, lo);
+        } else {
+          st4(y + j, o);
+        }
       }
       d = warp_sum(d);
       if (lane == 0) {
@@ -473,36 +489,59 @@ __global__ void outside_root_bwd_kernel(int B, int D, int64_t C, const float* __
   }
 }
 
-// g_obj[b,r,:] = sum_c patt[b,c,r] ga2[b,c,:] + g_logit[b,c,r] q[b,c,:]     grid (ceil(D/128), B), block 128
+// g_obj[b,r,:] = sum_c patt[b,c,r] ga2[b,c,:] + g_logit[b,c,r] q[b,c,:]     grid (ceil(D/32), B), block (32, 4)
+// threadIdx.x = column within a 32-wide slab, threadIdx.y = quarter of the region list; cells are staged
+// 16 at a time (coefficients in smem, the two vectors prefetched in registers) so loads overlap.
 template <int RMAX>
 __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, const float* __restrict__ GA2,
                                                        const float* __restrict__ q, const float* __restrict__ coef,
                                                        float* __restrict__ g_obj, int accumulate) {
+  constexpr int RQ = (RMAX + 3) / 4;   // regions per threadIdx.y
+  constexpr int CH = 16;               // cells per chunk
   const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ float s_c[2 * RMAX];
-  float acc[RMAX];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  __shared__ float s_c[CH][2 * RMAX];
+  float acc[RQ];
 #pragma unroll
-  for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
-  for (int64_t c = 0; c < C; ++c) {
-    const int64_t cell = (int64_t)b * C + c;
+  for (int i = 0; i < RQ; ++i) acc[i] = 0.f;
+  const int r0 = threadIdx.y * RQ;
+  for (int64_t c0 = 0; c0 < C; c0 += CH) {
+    const int nc = (int)min((int64_t)CH, C - c0);
     __syncthreads();
-    for (int t = threadIdx.x; t < 2 * R; t += blockDim.x) s_c[t] = coef[cell * 2 * R + t];
-    __syncthreads();
-    if (j < D) {
-      const float gv = GA2[cell * D + j], qv = q[cell * D + j];
+    for (int t = tid; t < nc * 2 * R; t += 128) {
+      const int cc = t / (2 * R), k = t % (2 * R);
+      s_c[cc][k] = coef[((int64_t)b * C + c0 + cc) * 2 * R + k];
+    }
+    float gv[CH], qv[CH];
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r)
-        if (r < R) acc[r] = fmaf(s_c[r], gv, fmaf(s_c[R + r], qv, acc[r]));
+    for (int cc = 0; cc < CH; ++cc) {
+      const bool ok = cc < nc && j < D;
+      const int64_t cell = (int64_t)b * C + c0 + cc;
+      gv[cc] = ok ? GA2[cell * D + j] : 0.f;
+      qv[cc] = ok ? q[cell * D + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc) {
+      if (cc < nc) {
+#pragma unroll
+        for (int i = 0; i < RQ; ++i) {
+          const int r = r0 + i;
+          if (r < R) acc[i] = fmaf(s_c[cc][r], gv[cc], fmaf(s_c[cc][R + r], qv[cc], acc[i]));
+        }
+      }
     }
   }
   if (j < D) {
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r)
+    for (int i = 0; i < RQ; ++i) {
+      const int r = r0 + i;
       if (r < R) {
         float* dst = g_obj + ((int64_t)b * R + r) * D + j;
-        *dst = accumulate ? *dst + acc[r] : acc[r];
+        *dst = accumulate ? *dst + acc[i] : acc[i];
       }
+    }
   }
 }
 

@@ -87,6 +87,14 @@ CL_D float block_sum(float v, float* red) {
   return t;
 }
 
+// x = hi + lo exactly, hi = x rounded to tf32 (low 13 mantissa bits zero)
+CL_D void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
 CL_D float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 CL_D void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 // 16-byte vector reduction to global memory (red.global.add.v4.f32, sm_90+)

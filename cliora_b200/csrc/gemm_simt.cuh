@@ -29,6 +29,7 @@ struct GemmParams {
   int64_t split_stride;  // floats between split-K partial outputs
   int vec_a, vec_w, vec_c;  // 16-byte vector access allowed (alignment checked on the host)
   const char* tag;          // profiler label (host only)
+  int64_t a_lo_off, w_lo_off;  // operands stored as split pairs: value = X[i] + X[i + lo_off] (0: plain)
 };
 
 constexpr int kBN = 64;
@@ -120,6 +121,19 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
           }
         }
       }
+      if (p.a_lo_off != 0) {
+        // split-pair operand (vector path only; pairs are always 16-byte aligned)
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!A_KMAJOR) {
+          const int k = k0 + a_c[i];
+          if (a_valid[i] && k + 3 < k_end) w = ld4(a_base[i] + p.a_lo_off + k);
+        } else {
+          const int k = k0 + a_r[i];
+          const int c = m0 + a_c[i];
+          if (k < k_end && c + 3 < p.M) w = ld4(a_base[i] + (int64_t)k * p.lda + p.a_lo_off);
+        }
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
       ra[i] = v;
     }
     {
@@ -150,6 +164,18 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
             if (c + 3 < p.N) v.w = src[3];
           }
         }
+      }
+      if (p.w_lo_off != 0) {
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!B_KMAJOR) {
+          const int k = k0 + b_c;
+          if (b_valid && k + 3 < k_end) w = ld4(b_base + p.w_lo_off + k);
+        } else {
+          const int k = k0 + b_r;
+          const int c = n0 + b_c;
+          if (k < k_end && c + 3 < p.N) w = ld4(b_base + (int64_t)k * p.ldw + p.w_lo_off);
+        }
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
       }
       rb = v;
     }
@@ -317,7 +343,7 @@ inline int64_t tn_scratch_floats(int rows, int Ka, int Kb) {
 // C[Ka,Kb] (+)= A[rows,Ka]^T B[rows,Kb]   (deterministic split-K: partials to scratch, then ordered sum)
 inline int launch_gemm_tn(cudaStream_t st, int rows, int Ka, int Kb, const float* A, int64_t lda, const float* B,
                           int64_t ldb, float* C, int64_t ldc, int accumulate, float* scratch,
-                          const char* tag = "gemm_wgrad") {
+                          const char* tag = "gemm_wgrad", int64_t a_lo_off = 0, int64_t b_lo_off = 0) {
   if (Ka <= 0 || Kb <= 0) return CLIORA_OK;
   ProfScope prof(st, tag, 2.0 * rows * Ka * Kb, 4.0 * ((double)rows * (Ka + Kb) + (double)Ka * Kb));
   const int splits = tn_splits(rows, Ka, Kb);
@@ -328,6 +354,7 @@ inline int launch_gemm_tn(cudaStream_t st, int rows, int Ka, int Kb, const float
   p.bias = nullptr; p.mask = nullptr; p.ldm = 0;
   p.M = Ka; p.N = Kb; p.K = rows;
   p.act = 0; p.accumulate = 0;
+  p.a_lo_off = a_lo_off; p.w_lo_off = b_lo_off;
   int chunk = (rows + splits - 1) / splits;
   chunk = ((chunk + kBK - 1) / kBK) * kBK;
   if (chunk < kBK) chunk = kBK;

@@ -1,0 +1,433 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fp32-grade accuracy ("3xTF32").
+//
+// Every operand is a SPLIT PAIR: two fp32 arrays hi, lo with hi = tf32-rounded x (low 13 mantissa bits
+// zero) and lo = x - hi (exact), stored back to back as a [2, rows, K] tensor.  The kernel accumulates
+//     lo_a*hi_b + hi_a*lo_b + hi_a*hi_b
+// into one fp32 TMEM accumulator with kind::tf32 UMMAs; the dropped lo*lo term and the truncation of lo
+// are ~2^-22 relative, so results agree with an fp32 FMA chain to ~1e-6 (single-pass TF32 is 3.5e-3 of
+// max on the chart, 35x over the 1e-4 budget -- BASELINE.md section 2).
+//
+// Structure (one 128 x BLOCK_N output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 3-D boxes {32 k, rows, part} with 128-byte swizzle
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem stages
+//   warps 2-5: epilogue      -- tcgen05.ld 32x32b from the accumulator, bias / ReLU / mask, global stores
+// Layouts: NT (A[m,k], W[n,k] both K-major).  NN is served by passing a pre-transposed weight pair.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace cliora {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;          // fp32 elements = one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+CL_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+CL_D void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+CL_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CL_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+CL_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+CL_D void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+CL_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+CL_D void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+CL_D void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+CL_D void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+CL_D void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle, rows packed at a 128-byte pitch: SBO = 8 rows * 128 B.
+CL_D uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major; CUTLASS writes 1)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=n
+CL_HD uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+CL_D void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+CL_D void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+CL_D void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcEpilogue {
+  float* C;
+  int64_t ldc;
+  RowMap cmap;
+  const float* bias;    // [N] or null
+  const float* mask;    // dense [M, ldm]: result zeroed where mask <= 0; or null
+  int64_t ldm;
+  int64_t mask_lo_off;  // mask stored as a split pair: value = mask[i] + mask[i + mask_lo_off] (0: plain)
+  float* C_lo;          // optional: also emit the split pair of the result (C gets hi, C_lo gets lo); or null
+  int act;              // 0 none, 1 relu, 2 tanh
+  int accumulate;       // C += result
+};
+
+CL_HD constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int BLOCK_N, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = kBlockM * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+// C[m0.., n0..] = epi( sum_k A[a_row0 + m, k] * W[n, k] ),  A pair [2, a_rows_total, K], W pair [2, N, K]
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const TcEpilogue ep, int a_row0, int M, int N, int K, int mode) {
+  using S = TcSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBlockM, n0 = blockIdx.x * BLOCK_N;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  // accumulator sets: kSets x (main, cross); consecutive k-steps rotate over the sets so back-to-back UMMAs
+  // never depend on each other's TMEM write-back, and each accumulator sees 1/kSets of the truncating adds
+  constexpr int kSets = (6 * BLOCK_N <= 512) ? 3 : ((4 * BLOCK_N <= 512) ? 2 : 1);
+  constexpr uint32_t TMEM_COLS = tmem_cols(2 * kSets * BLOCK_N);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      mbar_init(tmem_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        uint8_t* s = smem + stage * S::STAGE_BYTES;
+        tma_load_3d(s, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 0);
+        tma_load_3d(s + S::A_BYTES, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 1);
+        tma_load_3d(s + 2 * S::A_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 0);
+        tma_load_3d(s + 2 * S::A_BYTES + S::B_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(BLOCK_N);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc_k_sw128(sa), a_lo = umma_desc_k_sw128(sa + S::A_BYTES);
+        const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * S::A_BYTES);
+        const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * S::A_BYTES + S::B_BYTES);
+        // small terms first, then the main product; 4 k-steps of 8 tf32 (32 bytes -> +2 in 16-byte units)
+        // mode 0: all three products into one accumulator; mode 1: hi*hi only (plain TF32, for reference);
+        // mode 2: cross terms (lo*hi + hi*lo) into a second accumulator, added in fp32 by the epilogue.
+#pragma unroll
+        for (int k = 0; k < kBlockK / 8; ++k) {
+          if (mode == 0) {
+            umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, acc);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+          } else if (mode == 1) {
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+          } else if (mode == 2) {
+            umma_tf32(tmem_base + BLOCK_N, a_lo + 2 * k, b_hi + 2 * k, idesc, acc);
+            umma_tf32(tmem_base + BLOCK_N, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+          } else {
+            // mode 3: rotate over kSets independent (main, cross) accumulator pairs
+            const int step = kb * (kBlockK / 8) + k;
+            const int set = step % kSets;
+            const uint32_t first = step < kSets ? 0u : 1u;
+            const uint32_t tm = tmem_base + (uint32_t)(2 * set * BLOCK_N);
+            umma_tf32(tm, a_hi + 2 * k, b_hi + 2 * k, idesc, first);
+            umma_tf32(tm + BLOCK_N, a_lo + 2 * k, b_hi + 2 * k, idesc, first);
+            umma_tf32(tm + BLOCK_N, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+          }
+          acc = 1;
+        }
+        umma_commit(&empty[stage]);   // arrives when the MMAs above have finished reading this stage
+      }
+      umma_commit(tmem_full);         // accumulator complete
+    }
+  } else {
+    // ---- epilogue warps: TMEM lane quarter q = warp % 4 ----
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int r = m0 + q * 32 + lane;
+    const bool row_ok = r < M;
+    float* crow = row_ok ? ep.C + map_row(ep.cmap, r) * ep.ldc : nullptr;
+    float* clo = (row_ok && ep.C_lo) ? ep.C_lo + map_row(ep.cmap, r) * ep.ldc : nullptr;
+    const float* mrow = (row_ok && ep.mask) ? ep.mask + (int64_t)r * ep.ldm : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective: no early exit
+      if (mode == 2) {
+        float x[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += x[i];
+      } else if (mode == 3) {
+        const int nsteps = num_kb * (kBlockK / 8);
+        float cross[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), cross);
+#pragma unroll
+        for (int st = 1; st < kSets; ++st) {
+          if (st < nsteps) {
+            float x[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * st * BLOCK_N + c), x);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += x[i];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 * st + 1) * BLOCK_N + c), x);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cross[i] += x[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += cross[i];
+      }
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= N) continue;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const int col = col0 + j;
+        if (col >= N) break;     // N % 4 == 0
+        float o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float x = v[j + t];
+          if (ep.bias) x += ep.bias[col + t];
+          if (ep.act == 1) x = fmaxf(x, 0.f);
+          else if (ep.act == 2) x = tanhf(x);
+          if (mrow) {
+            float mv = mrow[col + t];
+            if (ep.mask_lo_off != 0) mv += mrow[col + t + ep.mask_lo_off];
+            if (!(mv > 0.f)) x = 0.f;
+          }
+          o[t] = x;
+        }
+        if (ep.accumulate) {
+          const float4 old = ld4(crow + col);
+          o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+        }
+        if (clo) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint32_t h;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(o[t]));
+            hi[t] = __uint_as_float(h);
+            lo[t] = o[t] - hi[t];
+          }
+          st4(crow + col, make_float4(hi[0], hi[1], hi[2], hi[3]));
+          st4(clo + col, make_float4(lo[0], lo[1], lo[2], lo[3]));
+        } else {
+          st4(crow + col, make_float4(o[0], o[1], o[2], o[3]));
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// x -> split pair (hi at out, lo at out + n)
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hi = __uint_as_float(h);
+    out[i] = hi;
+    out[n + i] = v - hi;
+  }
+}
+// W[rows, cols] -> split pair of W^T ([2, cols, rows])
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
+                                            float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? W[(int64_t)r * ldw + c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t n = (int64_t)rows * cols;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;   // out[c, r]
+    if (c < cols && r < rows) {
+      const float v = tile[threadIdx.x][i];
+      uint32_t h;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+      const float hi = __uint_as_float(h);
+      out[(int64_t)c * rows + r] = hi;
+      out[n + (int64_t)c * rows + r] = v - hi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a split pair [2, rows, K] (fp32, K contiguous, row pitch ld floats, part pitch part_stride
+// floats), box {32, box_rows, 1}, 128-byte swizzle, zero fill out of bounds.
+inline int make_pair_map(CUtensorMap* tm, const float* base, int64_t rows, int K, int64_t ld, int64_t part_stride,
+                         int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not available");
+    return CLIORA_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)part_stride * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CLIORA_ERR_CUDA;
+  }
+  return CLIORA_OK;
+}
+
+struct PairRef {            // a split-pair operand in global memory
+  const float* base;        // hi part; lo part at base + part_stride
+  int64_t rows;             // rows of the whole tensor (TMA bound)
+  int64_t ld;               // floats between rows
+  int64_t part_stride;      // floats between hi and lo
+};
+
+constexpr int kTcBlockN = 80;
+constexpr int kTcStages = 4;
+
+inline bool tc_supported(int N, int K, const PairRef& A, const PairRef& W) {
+  return (N % 4 == 0) && (K % 4 == 0) && (A.ld % 4 == 0) && (W.ld % 4 == 0) && (A.part_stride % 4 == 0) &&
+         (W.part_stride % 4 == 0) && aligned16(A.base) && aligned16(W.base);
+}
+
+// C[M,N] = epi(A[a_row0 : a_row0+M, :K] @ W[:N, :K]^T)
+inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, const PairRef& W, int M, int N, int K,
+                             const TcEpilogue& ep, const char* tag, int mode = 2) {
+  if (M <= 0 || N <= 0) return CLIORA_OK;
+  using S = TcSmem<kTcBlockN, kTcStages>;
+  CUtensorMap tmA, tmB;
+  CL_TRY(make_pair_map(&tmA, A.base, A.rows, K, A.ld, A.part_stride, kBlockM));
+  CL_TRY(make_pair_map(&tmB, W.base, W.rows, K, W.ld, W.part_stride, kTcBlockN));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CL_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<kTcBlockN, kTcStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(N, kTcBlockN), ceil_div(M, kBlockM));
+  ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
+  tc_gemm_nt_kernel<kTcBlockN, kTcStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, ep, a_row0, M, N, K, mode);
+  CL_CHECK_LAUNCH("tc_gemm_nt_kernel");
+  return CLIORA_OK;
+}
+
+}  // namespace tc
+}  // namespace cliora

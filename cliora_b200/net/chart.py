@@ -66,6 +66,14 @@ class ChartRun(object):
         D = self.D
         return self.ws[base + r0 * D: base + (r0 + rows) * D].view(rows, D)
 
+    def split_z(self, level, outside=False):
+        """Hidden activations relu(W1 [l;r] + b1) of a level, [rows, D] (tf32-rounded part when the
+        tensor-core path stores split pairs; its sign pattern is exact)."""
+        r0, rows = self.level_rows(level, outside)
+        base = self.layout.Zout if outside else self.layout.Zin
+        D = self.D
+        return self.ws[base + r0 * D: base + (r0 + rows) * D].view(rows, D)
+
     def split_s(self, level, outside=False):
         """Raw split scores of a level, [B,L,N,1] inside / [B,N,L,1] outside -- the ``s`` of the hooks."""
         r0, rows = self.level_rows(level, outside)

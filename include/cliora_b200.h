@@ -111,13 +111,15 @@ typedef struct cliora_layout {
   int64_t att_in;              /* [B,C,R] softmax over regions (R > 0 only) */
   int64_t nrm_out;             /* [B,C] */
   int64_t leaf_t;              /* [B*n, D] tanh(W_leaf x + b) */
-  int64_t Zin, Yin, Ein, Prin;     /* [rows_in, D] x2, [rows_in] x2 */
-  int64_t Zout, Yout, Eout, Prout; /* [rows_out, D] x2, [rows_out] x2 */
+  int64_t Zin, Yin, Ein, Prin;     /* [2, rows_in, D] x2 (split pairs hi|lo), [rows_in] x2 */
+  int64_t Zout, Yout, Eout, Prout; /* [2, rows_out, D] x2, [rows_out] x2 */
   int64_t Wcat_in, Wcat_out;   /* packed projection weights [PI*D, D], [2D, D] */
   /* backward scratch */
   int64_t Gh_in, Gs_in, GP_in, Gh_out, Gs_out, GP_out;
   int64_t GA2, coef;          /* [B,C,D], [B,C,2R] attention backward intermediates (R > 0 only) */
   int64_t GE, GZ, splitk, gu; /* per-level split scratch, split-K partials, leaf pre-activation grads */
+  /* forward workspace, tensor-core operands: split pairs [2, D, D] of W2 and W2^T (o* alias when share) */
+  int64_t W2p, W2Tp, oW2p, oW2Tp;
 } cliora_layout;
 
 int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);
@@ -230,6 +232,17 @@ int cliora_matmul_nn(int M, int N, int K, const float* A, const float* B, float*
 int64_t cliora_matmul_tn_scratch_floats(int M, int Ka, int Kb);
 int cliora_matmul_tn(int M, int Ka, int Kb, const float* A, const float* B, float* C, int accumulate,
                      float* scratch, cliora_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Tensor-core (tcgen05, 3xTF32) primitives.  Operands are SPLIT PAIRS: [2, rows, K] fp32 with
+ * part 0 = tf32-rounded value, part 1 = exact remainder (cliora_split_tf32 builds one).
+ *   C[M,N] = act(A[M,K] W[N,K]^T + bias)   with fp32-grade accuracy (~1e-6 of max)
+ * ---------------------------------------------------------------------- */
+int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_t stream);
+/* Development knob (key 0: accumulation mode of the tensor-core GEMM). */
+void cliora_debug_set(int key, int value);
+int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pair, const float* bias, int act,
+                     float* C, cliora_stream_t stream);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t cliora_launch_count(void);

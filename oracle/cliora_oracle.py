@@ -115,12 +115,14 @@ def region_attention(q, obj, keep=None, p_drop=0.1):
     return torch.bmm(prob, obj)
 
 
-def compose(P: Dict[str, torch.Tensor], prefix: str, a: torch.Tensor, b: torch.Tensor):
+def compose(P: Dict[str, torch.Tensor], prefix: str, a: torch.Tensor, b: torch.Tensor, pre=None):
     """cliora/net/diora.py:65-72 (ComposeMLP.forward): ReLU(W2 ReLU(W1 [a;b] + b1) + b2)."""
     x = torch.cat([a, b], dim=1)
-    x = torch.relu(torch.addmm(P[prefix + '.h_fcs.0.bias'], x, P[prefix + '.h_fcs.0.weight'].t()))
-    x = torch.relu(torch.addmm(P[prefix + '.h_fcs.2.bias'], x, P[prefix + '.h_fcs.2.weight'].t()))
-    return x
+    u1 = torch.addmm(P[prefix + '.h_fcs.0.bias'], x, P[prefix + '.h_fcs.0.weight'].t())
+    u2 = torch.addmm(P[prefix + '.h_fcs.2.bias'], torch.relu(u1), P[prefix + '.h_fcs.2.weight'].t())
+    if pre is not None:
+        pre.append((u1.detach(), u2.detach()))
+    return torch.relu(u2)
 
 
 def bilinear(mat: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
@@ -140,6 +142,8 @@ class ChartOut(object):
         self.split_scores = {}   # level -> [B, L, N, 1] raw inside split scores (inside_hook's ``s``)
         self.split_h = {}        # level -> [B*L*N, D]  pre-aggregation vectors (inside_hook's ``h``)
         self.out_split_scores = {}
+        self.pre_in = {}         # level -> (u1, u2): pre-activations of the two ReLUs (kink detection in tests)
+        self.pre_out = {}
 
 
 def leaf_transform(P, x, obj=None, keep=None, mode='unit'):
@@ -170,7 +174,10 @@ def inside_pass(P, leaf_h, obj=None, keep=None, mode='unit', out: Optional[Chart
         li, ri = inside_pairs(n, level)
         lh, rh = H.index_select(1, li).reshape(-1, D), H.index_select(1, ri).reshape(-1, D)
         ls, rs = S.index_select(1, li).reshape(-1, 1), S.index_select(1, ri).reshape(-1, 1)
-        h = compose(P, 'inside_compose_func', lh, rh)
+        pre = [] if out is not None else None
+        h = compose(P, 'inside_compose_func', lh, rh, pre)
+        if out is not None:
+            out.pre_in[level] = pre[0]
         s = (bilinear(P['inside_score_func.mat'], lh, rh) + ls + rs).view(B, L, N, 1)
         p = torch.softmax(s, dim=2)
         hbar = normalize((h.view(B, L, N, D) * p).sum(2), mode)
@@ -208,7 +215,10 @@ def outside_pass(P, inside_h, inside_s, mode='unit', out: Optional[ChartOut] = N
         pi, si = outside_pairs(n, level)
         ph, sh = OH.index_select(1, pi).reshape(-1, D), inside_h.index_select(1, si).reshape(-1, D)
         ps, ss = OS.index_select(1, pi).reshape(-1, 1), inside_s.index_select(1, si).reshape(-1, 1)
-        h = compose(P, 'outside_compose_func', sh, ph)
+        pre = [] if out is not None else None
+        h = compose(P, 'outside_compose_func', sh, ph, pre)
+        if out is not None:
+            out.pre_out[level] = pre[0]
         s = (bilinear(P['outside_score_func.mat'], sh, ph) + ss + ps).view(B, -1, L, 1)
         p = torch.softmax(s, dim=1)
         N = s.shape[1]

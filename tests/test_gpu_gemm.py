@@ -57,3 +57,27 @@ def test_matmul_tn(M, Ka, Kb):
         assert C.abs().max().item() == 0
     else:
         assert rel_err(C, ref) < 2e-6
+
+
+@pytest.mark.parametrize('M,N,K,act', [(128, 80, 32, 0), (128, 80, 400, 0), (37, 400, 400, 1), (3200, 400, 400, 1),
+                                       (12160, 400, 400, 1), (640, 1200, 400, 0), (500, 400, 1200, 0)])
+def test_tc_linear_3xtf32(M, N, K, act):
+    """tcgen05 3xTF32 GEMM: fp32-grade accuracy (single-pass TF32 would be ~1e-3)."""
+    L = _lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    Ap = torch.empty(2, M, K, device='cuda')
+    Wp = torch.empty(2, N, K, device='cuda')
+    L.check(L.lib().cliora_split_tf32(L.ptr(A), A.numel(), L.ptr(Ap), L.stream()), 'split')
+    L.check(L.lib().cliora_split_tf32(L.ptr(W), W.numel(), L.ptr(Wp), L.stream()), 'split')
+    assert torch.equal(Ap[0] + Ap[1], A)
+    C = torch.full((M, N), float('nan'), device='cuda')
+    L.check(L.lib().cliora_tc_linear(M, N, K, L.ptr(Ap), L.ptr(Wp), L.ptr(b), act, L.ptr(C), L.stream()), 'tc_linear')
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    if act == 1:
+        ref = torch.relu(ref)
+    err = rel_err(C, ref)
+    assert err < 5e-6, err   # K=1200: 3.2e-6 (truncating TMEM accumulation), cuBLAS fp32 is 1.3e-6
