@@ -118,6 +118,10 @@ def _declare(lib):
     lib.cliora_split_tf32.restype = c_int
     lib.cliora_tc_linear.argtypes = [c_int, c_int, c_int, vp, vp, vp, c_int, vp, st]
     lib.cliora_tc_linear.restype = c_int
+    lib.cliora_tc_matmul_tn_scratch_floats.restype = c_int64
+    lib.cliora_tc_matmul_tn_scratch_floats.argtypes = [c_int, c_int, c_int]
+    lib.cliora_tc_matmul_tn.argtypes = [c_int, c_int, c_int, vp, vp, vp, c_int, vp, st]
+    lib.cliora_tc_matmul_tn.restype = c_int
     lib.cliora_debug_set.argtypes = [c_int, c_int]
     lib.cliora_debug_set.restype = None
     lib.cliora_profile_start.restype = None
@@ -137,7 +141,8 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_outside_bwd', 'cliora_inside_bwd', 'cliora_atten_scores', 'cliora_atten_max_fwd',
            'cliora_atten_max_bwd', 'cliora_contrastive_loss', 'cliora_vg_loss', 'cliora_cky', 'cliora_linear',
            'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
-           'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set']
+           'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set',
+           'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn']
 
 
 def lib():

@@ -119,73 +119,97 @@ __global__ __launch_bounds__(128) void atten_max_bwd_h_kernel(int B, int ncell, 
   }
 }
 
-// g_obj[c,r,:] += sum_{a,cell : amax == r} g[a,c,cell] h[a,cell,:]    one block (128 thr) per (c,r).
+// g_obj[c,r,:] += sum_{a,cell : amax == r} g[a,c,cell] h[a,cell,:]    one block (4 warps) per (c,r).
 // The (a,cell) entries of image c are scanned 128 at a time; matches are compacted in index order with
-// warp ballots (deterministic), then their h rows are accumulated by all threads.
+// warp ballots (deterministic), then warp w accumulates matches w, w+4, ... four rows at a time (one dominant
+// region can own most cells of an image, so the row loads must overlap), partials summed in fixed order.
+// Dynamic smem: 4 * D floats.
 __global__ __launch_bounds__(128) void atten_max_bwd_obj_kernel(int B, int ncell, int D, int R,
                                                                 const float* __restrict__ h, int64_t h_bstride,
                                                                 const float* __restrict__ g,
                                                                 const int32_t* __restrict__ amax,
                                                                 float* __restrict__ g_obj) {
+  extern __shared__ __align__(16) float s_part[];   // [4][D]
   __shared__ int s_row[128];
   __shared__ float s_gv[128];
   __shared__ int s_wcount[4];
   const int c = blockIdx.x / R, r = blockIdx.x % R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int E = B * ncell;
-  // each thread owns columns j = tid*4 + t*512 (D <= 2048)
-  float4 acc[4];
+  // lane owns columns j = lane*4 + t*128, t < 4 (D <= 512), looping beyond for larger D
+  for (int jbase = 0; jbase < D; jbase += 512) {
+    float4 acc[4];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int e0 = 0; e0 < E; e0 += 128) {
-    const int e = e0 + tid;
-    bool hit = false;
-    float gv = 0.f;
-    int a = 0, cell = 0;
-    if (e < E) {
-      a = e / ncell;
-      cell = e % ncell;
-      const int64_t o = ((int64_t)a * B + c) * ncell + cell;
-      if (amax[o] == r) {
-        gv = g[o];
-        hit = gv != 0.f;
+    for (int t = 0; t < 4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = 0; e0 < E; e0 += 128) {
+      const int e = e0 + tid;
+      bool hit = false;
+      float gv = 0.f;
+      int a = 0, cell = 0;
+      if (e < E) {
+        a = e / ncell;
+        cell = e % ncell;
+        const int64_t o = ((int64_t)a * B + c) * ncell + cell;
+        if (amax[o] == r) {
+          gv = g[o];
+          hit = gv != 0.f;
+        }
       }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_wcount[warp] = __popc(bal);
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < warp; ++w) base += s_wcount[w];
-    const int total = s_wcount[0] + s_wcount[1] + s_wcount[2] + s_wcount[3];
-    if (hit) {
-      const int pos = base + __popc(bal & ((1u << lane) - 1u));
-      s_row[pos] = (int)((int64_t)a * h_bstride + cell);
-      s_gv[pos] = gv;
-    }
-    __syncthreads();
-    for (int i = 0; i < total; ++i) {
-      const float w = s_gv[i];
-      const float* hr = h + (int64_t)s_row[i] * D;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      __syncthreads();   // previous chunk's list fully consumed
+      if (lane == 0) s_wcount[warp] = __popc(bal);
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < warp; ++w) base += s_wcount[w];
+      const int total = s_wcount[0] + s_wcount[1] + s_wcount[2] + s_wcount[3];
+      if (hit) {
+        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+        s_row[pos] = (int)((int64_t)a * h_bstride + cell);
+        s_gv[pos] = gv;
+      }
+      __syncthreads();
+      for (int i = warp; i < total; i += 16) {
+        float w[4];
+        const float* hr[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int j = tid * 4 + t * 512;
-        if (j < D) {
-          const float4 hv = ld4(hr + j);
-          acc[t].x = fmaf(w, hv.x, acc[t].x); acc[t].y = fmaf(w, hv.y, acc[t].y);
-          acc[t].z = fmaf(w, hv.z, acc[t].z); acc[t].w = fmaf(w, hv.w, acc[t].w);
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + 4 * u;
+          w[u] = ii < total ? s_gv[ii] : 0.f;
+          hr[u] = h + (int64_t)s_row[ii < total ? ii : i] * D + jbase;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (jbase + j < D) {
+            float4 hv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) hv[u] = ld4(hr[u] + j);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[t].x = fmaf(w[u], hv[u].x, acc[t].x); acc[t].y = fmaf(w[u], hv[u].y, acc[t].y);
+              acc[t].z = fmaf(w[u], hv[u].z, acc[t].z); acc[t].w = fmaf(w[u], hv[u].w, acc[t].w);
+            }
+          }
         }
       }
     }
+    const int Dc = min(512, D - jbase);
     __syncthreads();
-  }
-  float* dst = g_obj + ((int64_t)c * R + r) * D;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int j = tid * 4 + t * 512;
-    if (j < D) {
-      float4 old = ld4(dst + j);
-      old.x += acc[t].x; old.y += acc[t].y; old.z += acc[t].z; old.w += acc[t].w;
-      st4(dst + j, old);
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < Dc) st4(s_part + warp * 512 + j, acc[t]);
+    }
+    __syncthreads();
+    float* dst = g_obj + ((int64_t)c * R + r) * D + jbase;
+    for (int j = tid * 4; j < Dc; j += 512) {
+      float4 o = ld4(dst + j);
+#pragma unroll
+      for (int w2 = 0; w2 < 4; ++w2) {
+        const float4 pv = ld4(s_part + w2 * 512 + j);
+        o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+      }
+      st4(dst + j, o);
     }
   }
 }

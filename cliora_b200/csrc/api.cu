@@ -76,6 +76,8 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   if ((t = tn_scratch_floats((int)L.rows_out, (int)D, (int)D)) > sk) sk = t;
   if ((t = tn_scratch_floats((int)(B * n), (int)D, (int)D)) > sk) sk = t;
   if ((t = 64 * PI * D) > sk) sk = t;
+  if ((t = tc::tn_tc_scratch_floats((int)L.rows_in, (int)D, (int)D)) > sk) sk = t;
+  if ((t = tc::tn_tc_scratch_floats((int)L.rows_out, (int)D, (int)D)) > sk) sk = t;
   L.splitk = take(sk);
   L.gu = take(B * n * D);
   L.bws_floats = o;
@@ -108,7 +110,8 @@ static int project_level(const Ctx& c, int level, const float* chart_h, const fl
   p.C = P; p.ldc = ncols; p.cmap = level_rows(c.d.n, level);
   p.M = c.d.B * (c.d.n - level); p.N = ncols; p.K = c.d.D;
   p.tag = "gemm_cell_project";
-  return launch_gemm(c.st, /*nt=*/true, p);
+  p.accumulate = 1;   // P was zero-filled at the start of the pass: lets small levels split K with red.add
+  return launch_gemm(c.st, /*nt=*/true, p, /*atomic_ok=*/true);
 }
 
 // Gh[rows of level] += GP[rows of level] @ Wcat
@@ -120,7 +123,7 @@ static int cellgrad_level(const Ctx& c, int level, const float* GP, int ncols, c
   p.M = c.d.B * (c.d.n - level); p.N = c.d.D; p.K = ncols;
   p.accumulate = 1;
   p.tag = "gemm_cell_grad";
-  return launch_gemm(c.st, /*nt=*/false, p);
+  return launch_gemm(c.st, /*nt=*/false, p, /*atomic_ok=*/true);
 }
 
 static int dense_linear(cudaStream_t st, int M, int N, int K, const float* A, const float* W, const float* bias,
@@ -132,6 +135,11 @@ static int dense_linear(cudaStream_t st, int M, int N, int K, const float* A, co
   p.bias = bias; p.act = act;
   p.M = M; p.N = N; p.K = K;
   p.tag = tag;
+  if (act == 0 && K >= 512 && (int64_t)ceil_div(M, 64) * ceil_div(N, kBN) < 148) {
+    CL_CUDA(cudaMemsetAsync(Cout, 0, (size_t)M * N * sizeof(float), st));
+    p.accumulate = 1;
+    return launch_gemm(st, true, p, /*atomic_ok=*/true);
+  }
   return launch_gemm(st, true, p);
 }
 
@@ -428,6 +436,7 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
   const float* oWb = c.d.share ? w->Wb : w->oWb;
   float* Wcat_in = ws + c.L.Wcat_in;
 
+  CL_CUDA(cudaMemsetAsync(ws + c.L.Pin, 0, (size_t)B * c.C * PI * D * sizeof(float), c.st));
   pack_weights_kernel<<<296, 256, 0, c.st>>>(D, PI, w->W1, w->Wb, oW1, oWb, Wcat_in, ws + c.L.Wcat_out);
   CL_CHECK_LAUNCH("pack_weights_kernel");
   if (c.use_tc) {
@@ -470,6 +479,7 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
   const float* ob2 = c.d.share ? w->b2 : w->ob2;
   float* Wcat_out = ws + c.L.Wcat_out;
 
+  CL_CUDA(cudaMemsetAsync(ws + c.L.Pout, 0, (size_t)B * c.C * 2 * D * sizeof(float), c.st));
   outside_root_kernel<<<B, 128, 0, c.st>>>(B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out);
   CL_CHECK_LAUNCH("outside_root_kernel");
   if (n > 1) CL_TRY(project_level(c, n - 1, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
@@ -544,8 +554,14 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
   const float* Z = ws + c.L.Zout;
   const float* GPo = bws + c.L.GP_out;
   const int64_t lo_out = c.use_tc ? c.L.rows_out * D : 0;
-  if (dW2)
-    CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch, "gemm_wgrad", lo_out, lo_out));
+  if (dW2) {
+    if (c.use_tc) {
+      tc::PairRef Ap{GY, c.L.rows_out, D, lo_out}, Bp{Z, c.L.rows_out, D, lo_out};
+      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)c.L.rows_out, D, D, dW2, D, 0, scratch, "tc_gemm_wgrad_w2"));
+    } else {
+      CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch, "gemm_wgrad", 0, 0));
+    }
+  }
   if (db2) {
     CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
     if (lo_out) CL_TRY(colsum(c.st, GY + lo_out, D, c.L.rows_out, D, db2, 1, scratch));
@@ -601,8 +617,14 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   const float* GPi = bws + c.L.GP_in;
   const int ldp = PI * D;
   const int64_t lo_in = c.use_tc ? c.L.rows_in * D : 0;
-  if (grads->W2)
-    CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch, "gemm_wgrad", lo_in, lo_in));
+  if (grads->W2) {
+    if (c.use_tc) {
+      tc::PairRef Ap{GY, c.L.rows_in, D, lo_in}, Bp{Z, c.L.rows_in, D, lo_in};
+      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)c.L.rows_in, D, D, grads->W2, D, acc, scratch, "tc_gemm_wgrad_w2"));
+    } else {
+      CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch, "gemm_wgrad", 0, 0));
+    }
+  }
   if (grads->b2) {
     CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
     if (lo_in) CL_TRY(colsum(c.st, GY + lo_in, D, c.L.rows_in, D, grads->b2, 1, scratch));
@@ -677,7 +699,7 @@ int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t
     CL_CHECK_LAUNCH("atten_max_bwd_h_kernel");
   }
   if (g_obj) {
-    atten_max_bwd_obj_kernel<<<B * R, 128, 0, st>>>(B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
+    atten_max_bwd_obj_kernel<<<B * R, 128, 4 * 512 * sizeof(float), st>>>(B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
     CL_CHECK_LAUNCH("atten_max_bwd_obj_kernel");
   }
   return CLIORA_OK;
@@ -777,6 +799,17 @@ int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pa
   ep.C = C; ep.ldc = N; ep.cmap = dense_rows();
   ep.bias = bias; ep.act = act;
   return tc::launch_tc_gemm_nt((cudaStream_t)stream, A, 0, W, M, N, K, ep, "tc_gemm_linear", g_debug[0]);
+}
+
+int64_t cliora_tc_matmul_tn_scratch_floats(int M, int Ka, int Kb) { return tc::tn_tc_scratch_floats(M, Ka, Kb); }
+
+int cliora_tc_matmul_tn(int M, int Ka, int Kb, const float* A_pair, const float* B_pair, float* C, int accumulate,
+                        float* scratch, cliora_stream_t stream) {
+  if (!A_pair || !B_pair || !C || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (M < 0 || Ka < 1 || Kb < 1 || (Ka % 4) || (Kb % 4)) return CLIORA_ERR_BAD_SHAPE;
+  tc::PairRef A{A_pair, M, Ka, (int64_t)M * Ka};
+  tc::PairRef B{B_pair, M, Kb, (int64_t)M * Kb};
+  return tc::launch_tc_gemm_tn((cudaStream_t)stream, A, B, M, Ka, Kb, C, Kb, accumulate, scratch, "tc_gemm_wgrad");
 }
 
 int64_t cliora_matmul_tn_scratch_floats(int M, int Ka, int Kb) { return tn_scratch_floats(M, Ka, Kb); }

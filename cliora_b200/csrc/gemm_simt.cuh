@@ -30,6 +30,7 @@ struct GemmParams {
   int vec_a, vec_w, vec_c;  // 16-byte vector access allowed (alignment checked on the host)
   const char* tag;          // profiler label (host only)
   int64_t a_lo_off, w_lo_off;  // operands stored as split pairs: value = X[i] + X[i + lo_off] (0: plain)
+  int atomic_splitk;           // k_chunk > 0 and partials are red.add'ed straight into C (bias by split 0)
 };
 
 constexpr int kBN = 64;
@@ -244,7 +245,7 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
   const int c0 = n0 + tx * 4;
   if (c0 >= p.N) return;
   float bias[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p.bias != nullptr) {
+  if (p.bias != nullptr && (!p.atomic_splitk || blockIdx.z == 0)) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (c0 + j < p.N) bias[j] = p.bias[c0 + j];
@@ -262,6 +263,18 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
       v[j] = t;
     }
     float* dst;
+    if (p.atomic_splitk) {
+      dst = p.C + map_row(p.cmap, r) * p.ldc + c0;
+      const bool fullv = (c0 + 3 < p.N) && p.vec_c;
+      if (fullv) {
+        red_add4(dst, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < p.N) atomicAdd(dst + j, v[j]);
+      }
+      continue;
+    }
     if (p.k_chunk > 0) {
       dst = p.C + (int64_t)blockIdx.z * p.split_stride + (int64_t)r * p.N + c0;  // dense partial
     } else {
@@ -304,10 +317,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // NT / NN launcher.  W is [N,K] (nt) or [K,N] (!nt).
-inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p) {
+// `atomic_ok`: C already holds the value to accumulate onto (zeros or a running sum) and there is no
+// activation / mask, so a small-M problem may be split along K over blockIdx.z with red.add epilogues.
+inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = false) {
   if (p.M <= 0 || p.N <= 0) return CLIORA_OK;
   p.k_chunk = 0;
   p.split_stride = 0;
+  p.atomic_splitk = 0;
   p.vec_a = aligned16(p.A) && (p.lda % 4 == 0);
   p.vec_w = aligned16(p.W) && (p.ldw % 4 == 0);
   p.vec_c = aligned16(p.C) && (p.ldc % 4 == 0);
@@ -316,6 +332,17 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p) {
   ProfScope prof(st, p.tag ? p.tag : "gemm", 2.0 * p.M * p.N * p.K,
                  4.0 * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * (p.mask ? 2 : 1)));
   dim3 grid(ceil_div(p.N, kBN), ceil_div(p.M, big ? 128 : 64), 1);
+  if (atomic_ok && !big && p.act == 0 && p.mask == nullptr) {
+    const int ctas = grid.x * grid.y;
+    const int ktiles = ceil_div(p.K, kBK);
+    int splits = (2 * 148 + ctas - 1) / ctas;
+    if (splits > ktiles / 4) splits = ktiles / 4;   // at least 4 k-tiles (64 k) per split
+    if (splits > 1) {
+      p.k_chunk = ceil_div(ktiles, splits) * kBK;
+      grid.z = ceil_div(p.K, p.k_chunk);
+      p.atomic_splitk = 1;
+    }
+  }
   if (nt) {
     if (big) gemm_simt_kernel<8, false, false><<<grid, 256, 0, st>>>(p);
     else gemm_simt_kernel<4, false, false><<<grid, 256, 0, st>>>(p);

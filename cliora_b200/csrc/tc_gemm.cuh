@@ -275,19 +275,28 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int j = 0; j < 16; j += 4) {
         const int col = col0 + j;
         if (col >= N) break;     // N % 4 == 0
-        float o[4];
+        float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+        if (ep.bias) {
+          const float4 bv = ld4(ep.bias + col);
+          o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+        }
+        if (ep.act == 1) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float x = v[j + t];
-          if (ep.bias) x += ep.bias[col + t];
-          if (ep.act == 1) x = fmaxf(x, 0.f);
-          else if (ep.act == 2) x = tanhf(x);
-          if (mrow) {
-            float mv = mrow[col + t];
-            if (ep.mask_lo_off != 0) mv += mrow[col + t + ep.mask_lo_off];
-            if (!(mv > 0.f)) x = 0.f;
+          for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+        } else if (ep.act == 2) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o[t] = tanhf(o[t]);
+        }
+        if (mrow) {
+          float4 mv = ld4(mrow + col);
+          if (ep.mask_lo_off != 0) {
+            const float4 ml = ld4(mrow + col + ep.mask_lo_off);
+            mv.x += ml.x; mv.y += ml.y; mv.z += ml.z; mv.w += ml.w;
           }
-          o[t] = x;
+          if (!(mv.x > 0.f)) o[0] = 0.f;
+          if (!(mv.y > 0.f)) o[1] = 0.f;
+          if (!(mv.z > 0.f)) o[2] = 0.f;
+          if (!(mv.w > 0.f)) o[3] = 0.f;
         }
         if (ep.accumulate) {
           const float4 old = ld4(crow + col);
@@ -296,16 +305,169 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (clo) {
           float hi[4], lo[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint32_t h;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(o[t]));
-            hi[t] = __uint_as_float(h);
-            lo[t] = o[t] - hi[t];
-          }
+          for (int t = 0; t < 4; ++t) split_tf32(o[t], hi[t], lo[t]);
           st4(crow + col, make_float4(hi[0], hi[1], hi[2], hi[3]));
           st4(clo + col, make_float4(lo[0], lo[1], lo[2], lo[3]));
         } else {
           st4(crow + col, make_float4(o[0], o[1], o[2], o[3]));
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// TN (weight gradient):  C[i, j] = sum_r A[r, i] * B[r, j]   with A pair [2, rows, Ka], B pair [2, rows, Kb]
+// Both operands are MN-major for the UMMA (the reduction index r is the slow memory dimension).
+// TMA boxes are {32 columns, kTnBlockK rows}: one 128-byte-swizzled MN chunk each; chunk g of an operand sits
+// at g * kTnBlockK * 128 B (LBO); 32-bit MN-major operands need the 32-byte-atom swizzle (K atoms of 4 rows,
+// SBO = 512 B; one UMMA k-step of 8 rows spans two of them).  Split-K over blockIdx.z; each CTA
+// writes a dense fp32 partial [Ka, Kb] tile to scratch, reduced in order by splitk_reduce_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kTnBlockK = 32;   // rows of the reduction per stage (4 UMMA k-steps)
+
+CL_D uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 32-element MN chunks
+  d |= (uint64_t)(512 >> 4) << 32;                    // stride between K atoms (4 rows x 128 B)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                             // SWIZZLE_128B_BASE32B: 32-bit MN-major operands swizzle
+  return d;                                           // 32-byte atoms (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+}
+CL_HD uint32_t umma_idesc_tf32_mn(int n) { return umma_idesc_tf32(n) | (1u << 15) | (1u << 16); }
+
+template <int BLOCK_N, int STAGES>
+struct TnSmem {
+  static constexpr int CHUNK = kTnBlockK * 128;            // one {32 x kTnBlockK} box
+  static constexpr int A_BYTES = (kBlockM / 32) * CHUNK;   // one part
+  static constexpr int B_BYTES = (BLOCK_N / 32) * CHUNK;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ partial, int rows, int Ka, int Kb, int rows_per_split) {
+  using S = TnSmem<BLOCK_N, STAGES>;
+  static_assert(BLOCK_N % 32 == 0 && 2 * BLOCK_N <= 512, "BLOCK_N");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.y * kBlockM, j0 = blockIdx.x * BLOCK_N;
+  const int r_begin = blockIdx.z * rows_per_split;
+  const int r_end = min(rows, r_begin + rows_per_split);
+  const int num_kb = r_end > r_begin ? (r_end - r_begin + kTnBlockK - 1) / kTnBlockK : 0;
+  constexpr uint32_t TMEM_COLS = tmem_cols(2 * BLOCK_N);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      mbar_init(tmem_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        uint8_t* s = smem + stage * S::STAGE_BYTES;
+        const int r = r_begin + kb * kTnBlockK;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int g = 0; g < kBlockM / 32; ++g)
+            tma_load_3d(s + part * S::A_BYTES + g * S::CHUNK, &tmA, &full[stage], i0 + g * 32, r, part);
+#pragma unroll
+          for (int g = 0; g < BLOCK_N / 32; ++g)
+            tma_load_3d(s + 2 * S::A_BYTES + part * S::B_BYTES + g * S::CHUNK, &tmB, &full[stage], j0 + g * 32, r,
+                        part);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32_mn(BLOCK_N);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc_mn_sw128(sa, S::CHUNK), a_lo = umma_desc_mn_sw128(sa + S::A_BYTES, S::CHUNK);
+        const uint64_t b_hi = umma_desc_mn_sw128(sa + 2 * S::A_BYTES, S::CHUNK);
+        const uint64_t b_lo = umma_desc_mn_sw128(sa + 2 * S::A_BYTES + S::B_BYTES, S::CHUNK);
+#pragma unroll
+        for (int k = 0; k < kTnBlockK / 8; ++k) {   // one 8-row K group = 1024 B = 64 x 16 B
+          umma_tf32(tmem_base + BLOCK_N, a_lo + 64 * k, b_hi + 64 * k, idesc, acc);
+          umma_tf32(tmem_base + BLOCK_N, a_hi + 64 * k, b_lo + 64 * k, idesc, 1);
+          umma_tf32(tmem_base, a_hi + 64 * k, b_hi + 64 * k, idesc, acc);
+          acc = 1;
+        }
+        umma_commit(&empty[stage]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int i = i0 + q * 32 + lane;
+    float* prow = partial + (int64_t)blockIdx.z * Ka * Kb + (int64_t)i * Kb;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full, 0);
+      tcgen05_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      float v[16];
+      if (num_kb > 0) {
+        float x[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), x);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] += x[t];
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = 0.f;
+      }
+      if (i < Ka) {
+#pragma unroll
+        for (int t = 0; t < 16; t += 4) {
+          const int col = j0 + c + t;
+          if (col < Kb) st4(prow + col, make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));   // Kb % 4 == 0
         }
       }
     }
@@ -373,7 +535,7 @@ inline EncodeTiledFn encode_fn() {
 // Tensor map over a split pair [2, rows, K] (fp32, K contiguous, row pitch ld floats, part pitch part_stride
 // floats), box {32, box_rows, 1}, 128-byte swizzle, zero fill out of bounds.
 inline int make_pair_map(CUtensorMap* tm, const float* base, int64_t rows, int K, int64_t ld, int64_t part_stride,
-                         int box_rows) {
+                         int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not available");
@@ -384,7 +546,7 @@ inline int make_pair_map(CUtensorMap* tm, const float* base, int64_t rows, int K
   cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -426,6 +588,52 @@ inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, cons
   ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
   tc_gemm_nt_kernel<kTcBlockN, kTcStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, ep, a_row0, M, N, K, mode);
   CL_CHECK_LAUNCH("tc_gemm_nt_kernel");
+  return CLIORA_OK;
+}
+
+constexpr int kTnBlockN = 224;
+constexpr int kTnStages = 2;
+
+// box {32 columns, box_rows rows, 1 part} over a pair whose contiguous dimension is the MN dimension
+inline int make_pair_map_mn(CUtensorMap* tm, const float* base, int64_t rows, int cols, int64_t ld,
+                            int64_t part_stride) {
+  return make_pair_map(tm, base, rows, cols, ld, part_stride, kTnBlockK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+inline int tn_tc_splits(int rows, int Ka, int Kb) {
+  const int tiles = ceil_div(Ka, kBlockM) * ceil_div(Kb, kTnBlockN);
+  int s = (148 + tiles - 1) / tiles;
+  const int kb = ceil_div(rows, kTnBlockK);
+  if (s > kb) s = kb;
+  if (s < 1) s = 1;
+  return s;
+}
+inline int64_t tn_tc_scratch_floats(int rows, int Ka, int Kb) { return (int64_t)tn_tc_splits(rows, Ka, Kb) * Ka * Kb; }
+
+// C[Ka,Kb] (+)= A[rows,Ka]^T B[rows,Kb], operands as split pairs
+inline int launch_tc_gemm_tn(cudaStream_t st, const PairRef& A, const PairRef& B, int rows, int Ka, int Kb, float* C,
+                             int64_t ldc, int accumulate, float* scratch, const char* tag) {
+  if (Ka <= 0 || Kb <= 0) return CLIORA_OK;
+  using S = TnSmem<kTnBlockN, kTnStages>;
+  CUtensorMap tmA, tmB;
+  CL_TRY(make_pair_map_mn(&tmA, A.base, A.rows, Ka, A.ld, A.part_stride));
+  CL_TRY(make_pair_map_mn(&tmB, B.base, B.rows, Kb, B.ld, B.part_stride));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CL_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<kTnBlockN, kTnStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S::TOTAL));
+    attr_set = true;
+  }
+  const int splits = tn_tc_splits(rows, Ka, Kb);
+  int per = ceil_div(ceil_div(rows, kTnBlockK), splits) * kTnBlockK;
+  if (per < kTnBlockK) per = kTnBlockK;
+  dim3 grid(ceil_div(Kb, kTnBlockN), ceil_div(Ka, kBlockM), splits);
+  ProfScope prof(st, tag, 2.0 * rows * Ka * Kb, 4.0 * ((double)rows * (Ka + Kb) * 2 + (double)Ka * Kb));
+  tc_gemm_tn_kernel<kTnBlockN, kTnStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, scratch, rows, Ka, Kb, per);
+  CL_CHECK_LAUNCH("tc_gemm_tn_kernel");
+  const int64_t total = (int64_t)Ka * Kb;
+  splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(scratch, splits, total, Ka, Kb, C, ldc, accumulate);
+  CL_CHECK_LAUNCH("splitk_reduce_kernel");
   return CLIORA_OK;
 }
 

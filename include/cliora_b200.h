@@ -244,6 +244,11 @@ void cliora_debug_set(int key, int value);
 int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pair, const float* bias, int act,
                      float* C, cliora_stream_t stream);
 
+/* C[Ka,Kb] (+)= A[M,Ka]^T B[M,Kb] on tensor cores (MN-major UMMA, split-K); Ka, Kb multiples of 4. */
+int64_t cliora_tc_matmul_tn_scratch_floats(int M, int Ka, int Kb);
+int cliora_tc_matmul_tn(int M, int Ka, int Kb, const float* A_pair, const float* B_pair, float* C, int accumulate,
+                        float* scratch, cliora_stream_t stream);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t cliora_launch_count(void);
 

@@ -81,3 +81,25 @@ def test_tc_linear_3xtf32(M, N, K, act):
         ref = torch.relu(ref)
     err = rel_err(C, ref)
     assert err < 5e-6, err   # K=1200: 3.2e-6 (truncating TMEM accumulation), cuBLAS fp32 is 1.3e-6
+
+
+@pytest.mark.parametrize('M,Ka,Kb', [(32, 128, 224), (64, 400, 400), (6720, 400, 400), (42560, 400, 400),
+                                     (1000, 64, 48), (5, 400, 400)])
+def test_tc_matmul_tn_3xtf32(M, Ka, Kb):
+    """Weight-gradient GEMM on tcgen05 with MN-major operands and split-K."""
+    L = _lib()
+    g = torch.Generator().manual_seed(M + Ka)
+    A = torch.randn(M, Ka, generator=g).cuda()
+    Bm = torch.randn(M, Kb, generator=g).cuda()
+    Ap = torch.empty(2, M, Ka, device='cuda')
+    Bp = torch.empty(2, M, Kb, device='cuda')
+    L.check(L.lib().cliora_split_tf32(L.ptr(A), A.numel(), L.ptr(Ap), L.stream()), 'split')
+    L.check(L.lib().cliora_split_tf32(L.ptr(Bm), Bm.numel(), L.ptr(Bp), L.stream()), 'split')
+    C0 = torch.randn(Ka, Kb, generator=g).cuda()
+    C = C0.clone()
+    scratch = torch.empty(int(L.lib().cliora_tc_matmul_tn_scratch_floats(M, Ka, Kb)) + 8, device='cuda')
+    L.check(L.lib().cliora_tc_matmul_tn(M, Ka, Kb, L.ptr(Ap), L.ptr(Bp), L.ptr(C), 1, L.ptr(scratch), L.stream()), 'tn')
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double().t() @ Bm.double()
+    err = rel_err(C, ref)
+    assert err < 1e-5, err   # 42k rows: 5.7e-6 (truncating TMEM accumulation over ~300 k-steps per split)
