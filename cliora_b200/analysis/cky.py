@@ -20,8 +20,10 @@ def backpointers(diora):
     bp = torch.empty(B, C, device=dev, dtype=torch.int32)
     best = torch.empty(B, C, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        check(_lib.lib().cliora_cky(B, n, ptr(run.all_split_scores()), ptr(bp), ptr(best), _lib.stream()),
-              'cliora_cky')
+        for b0, b1, ws, lay in run.parts:      # one launch per forward chain (each owns its split-score region)
+            scores = ws[lay.Ein: lay.Ein + max(int(lay.rows_in), 1)]
+            check(_lib.lib().cliora_cky(b1 - b0, n, ptr(scores), ptr(bp) + b0 * C * 4, ptr(best) + b0 * C * 4,
+                                        _lib.stream()), 'cliora_cky')
     return bp, best
 
 

@@ -13,7 +13,7 @@ namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
 long long g_launch_count = 0;
 Profiler g_prof;
-int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs
+int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide)
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -220,7 +220,7 @@ static int compose_gemm(const Ctx& c, bool outside, int64_t r0, int64_t rows, co
     tc::TcEpilogue ep{};
     ep.C = Yb + r0 * D; ep.ldc = D; ep.cmap = dense_rows();
     ep.bias = b2; ep.act = 1;
-    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2", g_debug[0]);
+    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2", g_debug[0], g_debug[2]);
   }
   return dense_linear(c.st, (int)rows, D, D, Zb + r0 * D, W2, b2, 1, Yb + r0 * D, "gemm_compose_w2");
 }
@@ -238,7 +238,7 @@ static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows
     tc::TcEpilogue ep{};
     ep.C = GZ; ep.ldc = D; ep.cmap = dense_rows();
     ep.mask = Zb + r0 * D; ep.ldm = D; ep.mask_lo_off = total * D;
-    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", g_debug[0]);
+    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", g_debug[0], g_debug[2]);
   }
   GemmParams p{};
   p.A = Yb + r0 * D; p.lda = D; p.amap = dense_rows();
@@ -798,7 +798,7 @@ int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pa
   tc::TcEpilogue ep{};
   ep.C = C; ep.ldc = N; ep.cmap = dense_rows();
   ep.bias = bias; ep.act = act;
-  return tc::launch_tc_gemm_nt((cudaStream_t)stream, A, 0, W, M, N, K, ep, "tc_gemm_linear", g_debug[0]);
+  return tc::launch_tc_gemm_nt((cudaStream_t)stream, A, 0, W, M, N, K, ep, "tc_gemm_linear", g_debug[0], g_debug[2]);
 }
 
 int64_t cliora_tc_matmul_tn_scratch_floats(int M, int Ka, int Kb) { return tc::tn_tc_scratch_floats(M, Ka, Kb); }

@@ -144,6 +144,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBlockM, n0 = blockIdx.x * BLOCK_N;
   const int num_kb = (K + kBlockK - 1) / kBlockK;
+  // columns this CTA really owns, rounded up to the UMMA granularity (N % 16 == 0 for M = 128)
+  const int n_cur = min(BLOCK_N, ((N - n0 + 15) / 16) * 16);
   // accumulator sets: kSets x (main, cross); consecutive k-steps rotate over the sets so back-to-back UMMAs
   // never depend on each other's TMEM write-back, and each accumulator sees 1/kSets of the truncating adds
   constexpr int kSets = (6 * BLOCK_N <= 512) ? 3 : ((4 * BLOCK_N <= 512) ? 2 : 1);
@@ -189,7 +191,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(BLOCK_N);
+      const uint32_t idesc = umma_idesc_tf32(n_cur);
       uint32_t acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int stage = kb % STAGES;
@@ -242,7 +244,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* clo = (row_ok && ep.C_lo) ? ep.C_lo + map_row(ep.cmap, r) * ep.ldc : nullptr;
     const float* mrow = (row_ok && ep.mask) ? ep.mask + (int64_t)r * ep.ldm : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
+    for (int c = 0; c < n_cur; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective: no early exit
       if (mode == 2) {
@@ -562,33 +564,48 @@ struct PairRef {            // a split-pair operand in global memory
   int64_t part_stride;      // floats between hi and lo
 };
 
-constexpr int kTcBlockN = 80;
-constexpr int kTcStages = 4;
+// Two tile configurations.  Wide (256 columns, 2 stages): 21.8 MAC per shared-memory byte read by the UMMAs, main +
+// cross accumulators fill the 512 TMEM columns -- used whenever the narrow grid would exceed one wave.  Narrow (80
+// columns, 4 stages): 5 CTAs per 128 rows at N = 400, more SMs busy on the small chart levels.
+constexpr int kTcNarrowN = 80, kTcNarrowStages = 4;
+constexpr int kTcWideN = 256, kTcWideStages = 2;
 
 inline bool tc_supported(int N, int K, const PairRef& A, const PairRef& W) {
   return (N % 4 == 0) && (K % 4 == 0) && (A.ld % 4 == 0) && (W.ld % 4 == 0) && (A.part_stride % 4 == 0) &&
          (W.part_stride % 4 == 0) && aligned16(A.base) && aligned16(W.base);
 }
 
-// C[M,N] = epi(A[a_row0 : a_row0+M, :K] @ W[:N, :K]^T)
-inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, const PairRef& W, int M, int N, int K,
-                             const TcEpilogue& ep, const char* tag, int mode = 2) {
-  if (M <= 0 || N <= 0) return CLIORA_OK;
-  using S = TcSmem<kTcBlockN, kTcStages>;
+template <int BLOCK_N, int STAGES>
+inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, const PairRef& W, int M, int N, int K,
+                                 const TcEpilogue& ep, const char* tag, int mode) {
+  using S = TcSmem<BLOCK_N, STAGES>;
   CUtensorMap tmA, tmB;
   CL_TRY(make_pair_map(&tmA, A.base, A.rows, K, A.ld, A.part_stride, kBlockM));
-  CL_TRY(make_pair_map(&tmB, W.base, W.rows, K, W.ld, W.part_stride, kTcBlockN));
+  CL_TRY(make_pair_map(&tmB, W.base, W.rows, K, W.ld, W.part_stride, BLOCK_N));
   static bool attr_set = false;
   if (!attr_set) {
-    CL_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<kTcBlockN, kTcStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CL_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  S::TOTAL));
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, kTcBlockN), ceil_div(M, kBlockM));
+  dim3 grid(ceil_div(N, BLOCK_N), ceil_div(M, kBlockM));
   ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
-  tc_gemm_nt_kernel<kTcBlockN, kTcStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, ep, a_row0, M, N, K, mode);
+  tc_gemm_nt_kernel<BLOCK_N, STAGES><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, ep, a_row0, M, N, K, mode);
   CL_CHECK_LAUNCH("tc_gemm_nt_kernel");
   return CLIORA_OK;
+}
+
+// C[M,N] = epi(A[a_row0 : a_row0+M, :K] @ W[:N, :K]^T)
+inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, const PairRef& W, int M, int N, int K,
+                             const TcEpilogue& ep, const char* tag, int mode = 2, int force_cfg = 0) {
+  if (M <= 0 || N <= 0) return CLIORA_OK;
+  const int64_t narrow_ctas = (int64_t)ceil_div(M, kBlockM) * ceil_div(N, kTcNarrowN);
+  const bool wide = force_cfg == 2 || (force_cfg == 0 && narrow_ctas > 148);
+  if (wide) {
+    if (mode == 3) mode = 2;   // the wide tile has no room for rotating accumulator sets
+    return launch_tc_gemm_nt_cfg<kTcWideN, kTcWideStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
+  }
+  return launch_tc_gemm_nt_cfg<kTcNarrowN, kTcNarrowStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
 }
 
 constexpr int kTnBlockN = 224;

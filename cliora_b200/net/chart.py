@@ -44,47 +44,57 @@ class Chart(object):
 
 
 class ChartRun(object):
-    """Per-forward bookkeeping the module needs after the kernels ran (workspace views for hooks, CKY)."""
+    """Per-forward bookkeeping the module needs after the kernels ran (workspace views for hooks, CKY).
+
+    The batch is processed as ``len(parts)`` independent chains (contiguous sentence ranges) on separate
+    CUDA streams; each chain has its own workspace."""
 
     def __init__(self):
-        self.ws = None
-        self.layout = None
+        self.parts = []          # [(b0, b1, ws, layout)]
         self.B = self.n = self.D = self.R = None
         self.consumed = False
 
-    def level_rows(self, level, outside=False):
+    # first chain's workspace/layout (single-chain callers and tests)
+    @property
+    def ws(self):
+        return self.parts[0][2]
+
+    @property
+    def layout(self):
+        return self.parts[0][3]
+
+    def _level_view(self, level, outside, what):
         L = _lib.lib()
-        r0 = int(L.cliora_split_row_offset(self.B, self.n, level, 1 if outside else 0))
-        Lc = self.n - level
-        N = (self.n - level - 1) if outside else level
-        return r0, self.B * Lc * N
+        n, D = self.n, self.D
+        Lc = n - level
+        N = (n - level - 1) if outside else level
+        out = []
+        for b0, b1, ws, lay in self.parts:
+            Bp = b1 - b0
+            r0 = int(L.cliora_split_row_offset(Bp, n, level, 1 if outside else 0))
+            rows = Bp * Lc * N
+            if what == 'E':
+                base = lay.Eout if outside else lay.Ein
+                out.append(ws[base + r0: base + r0 + rows])
+            else:
+                base = {'Y': (lay.Yin, lay.Yout), 'Z': (lay.Zin, lay.Zout)}[what][1 if outside else 0]
+                out.append(ws[base + r0 * D: base + (r0 + rows) * D].view(rows, D))
+        return out[0] if len(out) == 1 else torch.cat(out, 0)
 
     def split_h(self, level, outside=False):
         """Pre-aggregation vectors of a level, [B*L*N, D] -- the ``h`` of inside_hook (diora.py:331)."""
-        r0, rows = self.level_rows(level, outside)
-        base = self.layout.Yout if outside else self.layout.Yin
-        D = self.D
-        return self.ws[base + r0 * D: base + (r0 + rows) * D].view(rows, D)
+        return self._level_view(level, outside, 'Y')
 
     def split_z(self, level, outside=False):
         """Hidden activations relu(W1 [l;r] + b1) of a level, [rows, D] (tf32-rounded part when the
         tensor-core path stores split pairs; its sign pattern is exact)."""
-        r0, rows = self.level_rows(level, outside)
-        base = self.layout.Zout if outside else self.layout.Zin
-        D = self.D
-        return self.ws[base + r0 * D: base + (r0 + rows) * D].view(rows, D)
+        return self._level_view(level, outside, 'Z')
 
     def split_s(self, level, outside=False):
         """Raw split scores of a level, [B,L,N,1] inside / [B,N,L,1] outside -- the ``s`` of the hooks."""
-        r0, rows = self.level_rows(level, outside)
-        base = self.layout.Eout if outside else self.layout.Ein
-        s = self.ws[base + r0: base + r0 + rows]
+        s = self._level_view(level, outside, 'E')
         Lc = self.n - level
         return s.view(self.B, -1, Lc, 1) if outside else s.view(self.B, Lc, -1, 1)
-
-    def all_split_scores(self):
-        """The whole inside split-score region (input of the CKY kernel)."""
-        return self.ws[self.layout.Ein: self.layout.Ein + max(int(self.layout.rows_in), 1)]
 
 
 def _weights_struct(cls, tensors, share):
@@ -95,11 +105,43 @@ def _weights_struct(cls, tensors, share):
     return s
 
 
+_side_streams = {}
+
+
+def _streams(dev, k):
+    pool = _side_streams.setdefault(dev.index, [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:k]
+
+
+def _ranges(B, chains):
+    chains = max(1, min(int(chains), B))
+    base, rem = divmod(B, chains)
+    out, b0 = [], 0
+    for i in range(chains):
+        b1 = b0 + base + (1 if i < rem else 0)
+        out.append((b0, b1))
+        b0 = b1
+    return out
+
+
+def _off(t, nelem):
+    """Device pointer of ``t`` advanced by nelem elements (None stays NULL)."""
+    if t is None:
+        return None
+    return ptr(t) + nelem * t.element_size()
+
+
 class ChartFunction(torch.autograd.Function):
-    """(x, obj, weights) -> (inside_h, inside_s, outside_h, outside_s) with a hand-written backward."""
+    """(x, obj, weights) -> (inside_h, inside_s, outside_h, outside_s) with a hand-written backward.
+
+    Sentences are independent, and at batch 32 every kernel of the 76-level chain is latency-bound; the batch
+    is therefore cut into ``chains`` contiguous ranges that run as independent chains on side streams
+    (fork/join around the calls; under CUDA-graph capture they become parallel branches)."""
 
     @staticmethod
-    def forward(ctx, run, share, outside, x, obj, keep, *weights):
+    def forward(ctx, run, share, outside, chains, x, obj, keep, *weights):
         L = _lib.lib()
         if not x.is_cuda:
             raise _lib.ClioraError('cliora_b200: the chart runs on CUDA only (input is on %s); no CPU fallback'
@@ -111,10 +153,9 @@ class ChartFunction(torch.autograd.Function):
         B, n, D = x.shape
         R = 0 if obj is None else obj.shape[1]
         C = n * (n + 1) // 2
-        lay = _lib.layout(B, n, D, R, share)
         dev = x.device
+        ranges = _ranges(B, chains)
         with torch.cuda.device(dev):
-            ws = torch.empty(int(lay.ws_floats), device=dev, dtype=torch.float32)
             inside_h = torch.empty(B, C, D, device=dev, dtype=torch.float32)
             inside_s = torch.empty(B, C, 1, device=dev, dtype=torch.float32)
             if outside:
@@ -123,23 +164,40 @@ class ChartFunction(torch.autograd.Function):
             else:  # the reference leaves the outside chart at its zero fill (diora.py:19-22)
                 outside_h = torch.zeros(B, C, D, device=dev, dtype=torch.float32)
                 outside_s = torch.zeros(B, C, 1, device=dev, dtype=torch.float32)
-            dims = Dims(B, n, D, R, 1 if share else 0, 0)
             W = _weights_struct(Weights, weights, share)
-            st = _lib.stream()
-            check(L.cliora_inside_fwd(ctypes.byref(dims), ctypes.byref(W), ptr(x), ptr(obj), ptr(keep),
-                                      ptr(inside_h), ptr(inside_s), ptr(ws), st), 'cliora_inside_fwd')
-            if outside:
-                check(L.cliora_outside_fwd(ctypes.byref(dims), ctypes.byref(W), ptr(inside_h), ptr(inside_s),
-                                           ptr(outside_h), ptr(outside_s), ptr(ws), st), 'cliora_outside_fwd')
-        run.ws, run.layout, run.B, run.n, run.D, run.R = ws, lay, B, n, D, R
+            parts = []
+            for b0, b1 in ranges:
+                lay = _lib.layout(b1 - b0, n, D, R, share)
+                parts.append((b0, b1, torch.empty(int(lay.ws_floats), device=dev, dtype=torch.float32), lay))
+            cur = torch.cuda.current_stream(dev)
+            streams = [cur] if len(parts) == 1 else _streams(dev, len(parts))
+            for (b0, b1, ws, lay), st in zip(parts, streams):
+                if st is not cur:
+                    st.wait_stream(cur)
+                dims = Dims(b1 - b0, n, D, R, 1 if share else 0, 0)
+                with torch.cuda.stream(st):
+                    h = st.cuda_stream
+                    check(L.cliora_inside_fwd(ctypes.byref(dims), ctypes.byref(W), _off(x, b0 * n * D),
+                                              _off(obj, b0 * R * D), _off(keep, b0 * C * R),
+                                              _off(inside_h, b0 * C * D), _off(inside_s, b0 * C), ptr(ws), h),
+                          'cliora_inside_fwd')
+                    if outside:
+                        check(L.cliora_outside_fwd(ctypes.byref(dims), ctypes.byref(W), _off(inside_h, b0 * C * D),
+                                                   _off(inside_s, b0 * C), _off(outside_h, b0 * C * D),
+                                                   _off(outside_s, b0 * C), ptr(ws), h), 'cliora_outside_fwd')
+            for st in streams:
+                if st is not cur:
+                    cur.wait_stream(st)
+        run.parts, run.B, run.n, run.D, run.R = parts, B, n, D, R
         ctx.run, ctx.share, ctx.outside, ctx.dims_t = run, share, outside, (B, n, D, R)
         ctx.has_obj, ctx.has_keep = obj is not None, keep is not None
-        saved = [x, ws, inside_h, inside_s, outside_h, outside_s]
+        saved = [x, inside_h, inside_s, outside_h, outside_s]
         if obj is not None:
             saved.append(obj)
         if keep is not None:
             saved.append(keep)
-        ctx.save_for_backward(*saved, *weights)
+        ctx.n_ws = len(parts)
+        ctx.save_for_backward(*saved, *[p[2] for p in parts], *weights)
         return inside_h, inside_s, outside_h, outside_s
 
     @staticmethod
@@ -149,40 +207,60 @@ class ChartFunction(torch.autograd.Function):
             raise _lib.ClioraError('cliora_b200: the chart backward consumes its workspace; '
                                    'backward through the same forward twice is not supported')
         saved = list(ctx.saved_tensors)
-        x, ws, inside_h, inside_s, outside_h, outside_s = saved[:6]
-        i = 6
+        x, inside_h, inside_s, outside_h, outside_s = saved[:5]
+        i = 5
         obj = keep = None
         if ctx.has_obj:
             obj = saved[i]; i += 1
         if ctx.has_keep:
             keep = saved[i]; i += 1
-        weights = saved[i:]
+        wss = saved[i:i + ctx.n_ws]
+        weights = saved[i + ctx.n_ws:]
         B, n, D, R = ctx.dims_t
+        C = n * (n + 1) // 2
         share, outside = ctx.share, ctx.outside
-        lay = ctx.run.layout
         dev = x.device
         cont = lambda g: None if g is None else g.contiguous().float()
         g_ih, g_is, g_oh, g_os = cont(g_ih), cont(g_is), cont(g_oh), cont(g_os)
         if not outside:
             g_oh = g_os = None
+        parts = ctx.run.parts
         with torch.cuda.device(dev):
-            bws = torch.empty(int(lay.bws_floats), device=dev, dtype=torch.float32)
-            grads = [torch.empty_like(w) for w in weights]
             gx = torch.empty_like(x)
             gobj = torch.empty_like(obj) if obj is not None else None
-            dims = Dims(B, n, D, R, 1 if share else 0, 0)
             W = _weights_struct(Weights, weights, share)
-            G = _weights_struct(WeightGrads, grads, share)
-            st = _lib.stream()
-            check(L.cliora_chart_bwd_begin(ctypes.byref(dims), ptr(g_ih), ptr(g_is), ptr(g_oh), ptr(g_os),
-                                           ptr(bws), st), 'cliora_chart_bwd_begin')
-            if outside:
-                check(L.cliora_outside_bwd(ctypes.byref(dims), ctypes.byref(W), ptr(inside_h), ptr(inside_s),
-                                           ptr(outside_h), ptr(outside_s), ptr(ws), ptr(bws), ctypes.byref(G), st),
-                      'cliora_outside_bwd')
-            check(L.cliora_inside_bwd(ctypes.byref(dims), ctypes.byref(W), ptr(x), ptr(obj), ptr(keep),
-                                      ptr(inside_h), ptr(inside_s), ptr(outside_h), ptr(ws), ptr(bws),
-                                      1 if outside else 0, ptr(gx), ptr(gobj), ctypes.byref(G), st),
-                  'cliora_inside_bwd')
+            cur = torch.cuda.current_stream(dev)
+            streams = [cur] if len(parts) == 1 else _streams(dev, len(parts))
+            # scratch and per-chain weight grads are allocated on the current stream BEFORE the fork, so the
+            # caching allocator ties their lifetime to `cur` (all side-stream work is joined back into it)
+            all_bws = [torch.empty(int(p[3].bws_floats), device=dev, dtype=torch.float32) for p in parts]
+            all_grads = [[torch.empty_like(w) for w in weights] for _ in parts]
+            for (b0, b1, _, lay), ws, st, bws, grads in zip(parts, wss, streams, all_bws, all_grads):
+                if st is not cur:
+                    st.wait_stream(cur)
+                dims = Dims(b1 - b0, n, D, R, 1 if share else 0, 0)
+                with torch.cuda.stream(st):
+                    h = st.cuda_stream
+                    G = _weights_struct(WeightGrads, grads, share)
+                    check(L.cliora_chart_bwd_begin(ctypes.byref(dims), _off(g_ih, b0 * C * D), _off(g_is, b0 * C),
+                                                   _off(g_oh, b0 * C * D), _off(g_os, b0 * C), ptr(bws), h),
+                          'cliora_chart_bwd_begin')
+                    if outside:
+                        check(L.cliora_outside_bwd(ctypes.byref(dims), ctypes.byref(W), _off(inside_h, b0 * C * D),
+                                                   _off(inside_s, b0 * C), _off(outside_h, b0 * C * D),
+                                                   _off(outside_s, b0 * C), ptr(ws), ptr(bws), ctypes.byref(G), h),
+                              'cliora_outside_bwd')
+                    check(L.cliora_inside_bwd(ctypes.byref(dims), ctypes.byref(W), _off(x, b0 * n * D),
+                                              _off(obj, b0 * R * D), _off(keep, b0 * C * R),
+                                              _off(inside_h, b0 * C * D), _off(inside_s, b0 * C),
+                                              _off(outside_h, b0 * C * D), ptr(ws), ptr(bws), 1 if outside else 0,
+                                              _off(gx, b0 * n * D), _off(gobj, b0 * R * D), ctypes.byref(G), h),
+                          'cliora_inside_bwd')
+            for st in streams:
+                if st is not cur:
+                    cur.wait_stream(st)
+            grads = all_grads[0]
+            for other in all_grads[1:]:
+                torch._foreach_add_(grads, other)
         ctx.run.consumed = True
-        return (None, None, None, gx, gobj, None) + tuple(grads)
+        return (None, None, None, None, gx, gobj, None) + tuple(grads)

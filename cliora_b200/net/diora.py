@@ -57,6 +57,7 @@ class DioraBase(nn.Module):
         self._run = None
         self._pending = None
         self._keep_override = None
+        self.chains = None     # concurrent sentence sub-batches (None: pick from the batch size)
         self.init_parameters()
         self.reset_parameters()
         self.reset()
@@ -157,11 +158,15 @@ class DioraBase(nn.Module):
         keep = None
         if obj is not None and self.training:
             keep = self._keep_override
-            if keep is None:   # nn.Dropout(0.1) of AttentionHead (cliora.py:32), one draw per forward
-                keep = torch.rand(B, n * (n + 1) // 2, obj.shape[1], device=x_span.device) >= 0.1
+            p_drop = self.atten_head.dropout.p
+            if p_drop not in (0.0, 0.1):
+                raise NotImplementedError('the attention kernels hard-wire Dropout(0.1) (cliora.py:32); p=%r' % p_drop)
+            if keep is None and p_drop > 0:   # one draw per forward instead of one per level
+                keep = torch.rand(B, n * (n + 1) // 2, obj.shape[1], device=x_span.device) >= p_drop
         self._keep_override = None
         run = ChartRun()
-        outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), x_span, obj, keep,
+        chains = self.chains if self.chains is not None else max(1, min(4, B // 8))
+        outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, x_span, obj, keep,
                                    *self._weight_list())
         self._run = run
         self._pending = outs

@@ -103,3 +103,15 @@ def test_tc_matmul_tn_3xtf32(M, Ka, Kb):
     ref = C0.double() + A.double().t() @ Bm.double()
     err = rel_err(C, ref)
     assert err < 1e-5, err   # 42k rows: 5.7e-6 (truncating TMEM accumulation over ~300 k-steps per split)
+
+
+@pytest.mark.parametrize('cfg', [1, 2])
+@pytest.mark.parametrize('M,N,K', [(300, 400, 400), (1000, 1200, 400), (129, 144, 64)])
+def test_tc_linear_both_tile_configs(cfg, M, N, K):
+    """Narrow (80-column) and wide (256-column, runtime UMMA N on the ragged tile) configurations agree with fp64."""
+    L = _lib()
+    L.lib().cliora_debug_set(2, cfg)
+    try:
+        test_tc_linear_3xtf32(M, N, K, 1)
+    finally:
+        L.lib().cliora_debug_set(2, 0)

@@ -1,0 +1,83 @@
+"""Whole training step through the public API: eager vs CUDA-graph replay, and against the CPU oracle step."""
+import argparse
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(D=64, V=200, E=32, k_neg=10, seed=5):
+    from cliora_b200.net.trainer import build_net
+    torch.manual_seed(seed)
+    opts = argparse.Namespace(arch='mlp', hidden_dim=D, k_neg=k_neg, margin=1.0, vl_margin=0.2, alpha_contr=1.0,
+                              alpha_vg=1.0, vg_loss=True, use_contr=True, use_contr_ce=False, obj_feats=True,
+                              normalize='unit', share=True, cuda=True, lr=2e-3)
+    tr = build_net(opts, torch.nn.Embedding(V, E))
+    with torch.no_grad():
+        for p in tr.net.img_encoder.parameters():
+            p.normal_(0, 0.02)
+    return tr
+
+
+def _batch(B=6, n=7, V=200, R=9, F=2048, k_neg=10, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return dict(sentences=torch.randint(0, V, (B, n), generator=g).cuda(),
+                neg_samples=torch.randperm(V, generator=g)[:k_neg].cuda(),
+                obj_feats=torch.rand(B, R, F, generator=g).cuda(), batch_size=B, length=n)
+
+
+def test_graphed_step_matches_eager_step():
+    """Same weights, same batches, dropout off: CUDA-graph replay must reproduce the eager losses and weights."""
+    batches = [_batch(seed=i) for i in range(4)]
+    eager, graphed = _trainer(), _trainer()
+    for tr in (eager, graphed):
+        tr.net.diora.atten_head.dropout.p = 0.0
+    sd = {k: v.clone() for k, v in eager.net.state_dict().items()}
+    graphed.capture(batches[0], warmup=2)          # warm-up steps update the weights and Adam state ...
+    graphed.net.load_state_dict(sd)                # ... so reset both before comparing
+    for st in graphed.optimizer.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    la = [eager.step(x, train=True, sync_result=False)['total_loss'].item() for x in batches]
+    lb = [graphed.step_graphed(x).item() for x in batches]
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-4 * abs(x), (la, lb)
+    for (k, p), (_, q) in zip(eager.net.named_parameters(), graphed.net.named_parameters()):
+        # Adam divides by sqrt(v): near-zero gradients turn fp noise into +-lr moves, so only gross errors are checked
+        assert torch.allclose(p, q, rtol=1e-2, atol=1e-2), k
+
+
+def test_train_step_losses_vs_cpu_oracle_step():
+    """Net.forward + three losses through the fused product path == the oracle's dense CPU step (first step)."""
+    from oracle.cliora_oracle import CpuClioraStep
+    D, V, E, K, F = 64, 200, 32, 10, 2048
+    tr = _trainer(D, V, E, K)
+    cpu = CpuClioraStep(D=D, E=E, V=V, F=F, k_neg=K, seed=3)
+    net = tr.net
+    with torch.no_grad():
+        sd = net.diora.state_dict()
+        for k in sd:
+            sd[k].copy_(cpu.P[k if k in cpu.P else k.replace('outside_', 'inside_')])
+        net.embed.embeddings.weight.copy_(cpu.emb)
+        net.embed.mat.copy_(cpu.mat); net.embed.mat1.copy_(cpu.mat1)
+        net.reconstruct_softmax_loss.mat.copy_(cpu.recon_mat)
+        net.img_encoder.fc.weight.copy_(cpu.enc['fc.weight']); net.img_encoder.fc.bias.copy_(cpu.enc['fc.bias'])
+        net.img_encoder.fc_vis.weight.copy_(cpu.enc['fc_vis.weight']); net.img_encoder.fc_vis.bias.copy_(cpu.enc['fc_vis.bias'])
+    bt = _batch(V=V, k_neg=K)
+    B, n = bt['sentences'].shape
+    keep = torch.rand(B, n * (n + 1) // 2, bt['obj_feats'].shape[1]) >= 0.1
+    net.train()
+    net.diora.set_dropout_mask(keep.cuda())
+    out = tr.run_net(bt, None, compute_loss=True)
+    total, parts = cpu.loss(bt['sentences'].cpu(), bt['neg_samples'].cpu(), bt['obj_feats'].cpu(), keep)
+    mine = out['total_loss'].view(-1).cpu()
+    for x, y in zip(mine.tolist(), [p.item() for p in parts]):
+        assert abs(x - y) <= 1e-4 * max(abs(y), 1e-3), (mine, parts)
+    out['total_loss'].sum().backward()
+    total.backward()
+    from conftest import rel_err
+    assert rel_err(net.embed.mat.grad, cpu.mat.grad) < 2e-4
+    assert rel_err(net.img_encoder.fc.weight.grad, cpu.enc['fc.weight'].grad) < 2e-4
+    assert rel_err(net.diora.inside_compose_func.h_fcs[2].weight.grad, cpu.P['inside_compose_func.h_fcs.2.weight'].grad) < 2e-4
