@@ -212,13 +212,22 @@ class Trainer(object):
         self.optimizer.step()
 
     # ---- CUDA-graph replay of the whole training step (forward, losses, backward, clip, Adam) ----
+    def _optimizer_update(self):
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        self.optimizer.step()
+
     def capture(self, batch_map, warmup=3):
-        """Capture one training step for the shapes of ``batch_map`` into a CUDA graph.
+        """Capture one training step for the shapes of ``batch_map`` into CUDA graph(s).
 
         The step is ~500 dependent small kernels at batch 32 / length 20; replaying a graph removes the
         per-launch host cost and most inter-kernel gaps.  Batches of the same shape are then run with
         ``step_graphed`` (inputs are copied into static device buffers).  Needs an optimizer created with
-        ``capturable=True`` (``init_optimizer`` does that when ``cuda`` is set)."""
+        ``capturable=True`` (``init_optimizer`` does that when ``cuda`` is set).
+
+        Single GPU: one graph holds the whole step.  Data parallel (``grad_sync`` set): the NCCL all-reduce
+        stays outside -- graph A = forward + backward, eager all-reduce, graph B = clip + Adam."""
+        from .. import _lib
         self.net.train()
         dev = next(self.net.parameters()).device
         self._static = {k: (v.to(dev).clone() if torch.is_tensor(v) else v) for k, v in batch_map.items()}
@@ -230,16 +239,24 @@ class Trainer(object):
                 self.gradient_update(out['total_loss'].mean(dim=0).sum())
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        from .. import _lib
+        split = self.grad_sync is not None
         self._graph = torch.cuda.CUDAGraph()
+        self._graph_opt = torch.cuda.CUDAGraph() if split else None
         self.optimizer.zero_grad(set_to_none=True)
         before = _lib.launch_count()
         with torch.cuda.graph(self._graph):
             out = self.run_net(self._static, None, compute_loss=True)
             self._static_loss = out['total_loss'].mean(dim=0).sum()
-            self.gradient_update(self._static_loss)
+            if split:
+                self._static_loss.backward()
+            else:
+                self.gradient_update(self._static_loss)
             self._static_out = {k: v.detach() for k, v in out.items() if 'loss' in k}
         self.launches_per_step = _lib.launch_count() - before   # library kernels baked into the graph
+        if split:
+            self.grad_sync()
+            with torch.cuda.graph(self._graph_opt):
+                self._optimizer_update()
         return self
 
     def step_graphed(self, batch_map):
@@ -248,6 +265,9 @@ class Trainer(object):
             if torch.is_tensor(v):
                 self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
+        if self._graph_opt is not None:
+            self.grad_sync()          # one flat fp32 all-reduce over NVLink (NCCL), then 1/N
+            self._graph_opt.replay()
         return self._static_loss
 
     def step(self, batch_map, idx2word=None, train=True, compute_loss=True, sync_result=True):

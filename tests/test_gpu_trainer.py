@@ -81,3 +81,27 @@ def test_train_step_losses_vs_cpu_oracle_step():
     assert rel_err(net.embed.mat.grad, cpu.mat.grad) < 2e-4
     assert rel_err(net.img_encoder.fc.weight.grad, cpu.enc['fc.weight'].grad) < 2e-4
     assert rel_err(net.diora.inside_compose_func.h_fcs[2].weight.grad, cpu.P['inside_compose_func.h_fcs.2.weight'].grad) < 2e-4
+
+
+def test_split_graph_path_used_for_data_parallel():
+    """With a grad_sync hook the step is two graphs around an eager all-reduce; same losses as eager."""
+    batches = [_batch(seed=i) for i in range(3)]
+    eager, graphed = _trainer(), _trainer()
+    calls = []
+    graphed.grad_sync = lambda: calls.append(1)
+    for tr in (eager, graphed):
+        tr.net.diora.atten_head.dropout.p = 0.0
+    sd = {k: v.clone() for k, v in eager.net.state_dict().items()}
+    graphed.capture(batches[0], warmup=1)
+    assert graphed._graph_opt is not None
+    graphed.net.load_state_dict(sd)
+    for st in graphed.optimizer.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    n0 = len(calls)
+    la = [eager.step(x, train=True, sync_result=False)['total_loss'].item() for x in batches]
+    lb = [graphed.step_graphed(x).item() for x in batches]
+    assert len(calls) - n0 == len(batches)
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-4 * abs(x), (la, lb)
