@@ -266,15 +266,26 @@ def main():
                                  gbs=v['bytes'] / v['ms'] / 1e6 if v['ms'] else 0, avg_launch_us=per * 1e3)
         top = max(prof.items(), key=lambda kv: kv[1]['ms'])
         name, v = top
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')
+        if os.path.exists(tpath):      # dram__bytes_read+write of one ncu --set full capture of this kernel class
+            t = json.load(open(tpath)).get(name)
+            if t:
+                traffic, traffic_note = t['dram_bytes'], 'ncu capture of: ' + t['launch']
         if name.startswith('gemm') or name.startswith('atten_max'):
             ach = v['flops'] / v['ms'] / 1e9
+            tcg = name.startswith('tc_')
             roof = dict(kernel=name, bound='tensor', achieved=ach, peak=pk['tensor'], unit='TFLOP/s',
-                        frac=ach / pk['tensor'], traffic=None, peak_source=pk['src'] + ' bf16 sustained',
-                        note='fp32-accurate path; algorithmic flops = 2*M*N*K per launch')
+                        frac=ach / pk['tensor'], traffic=traffic, traffic_note=traffic_note,
+                        peak_source=pk['src'] + ' bf16 sustained',
+                        note=('algorithmic flops = 2*M*N*K per launch; fp32-accurate 3xTF32 on tcgen05: the tensor '
+                              'pipe executes 3 tf32 UMMAs per algorithmic MAC, tf32 peak = half the bf16 peak, so '
+                              'frac 1/6 would be the speed of light of this scheme') if tcg else
+                        'algorithmic flops = 2*M*N*K per launch; fp32 FMA (SIMT) kernel')
         else:
             ach = v['bytes'] / v['ms'] / 1e6
             roof = dict(kernel=name, bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
-                        traffic=None, peak_source=pk['src'])
+                        traffic=traffic, traffic_note=traffic_note, peak_source=pk['src'])
 
     if dist is not None:
         dist.barrier()
