@@ -4,6 +4,7 @@
 
 #include "align_kernels.cuh"
 #include "chart_kernels.cuh"
+#include "cell_warp_kernels.cuh"
 #include "cky_kernels.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -13,7 +14,7 @@ namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
 long long g_launch_count = 0;
 Profiler g_prof;
-int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide)
+int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = 1: block-per-cell VL kernels
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -78,8 +79,11 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   if ((t = 64 * PI * D) > sk) sk = t;
   if ((t = tc::tn_tc_scratch_floats((int)L.rows_in, (int)D, (int)D)) > sk) sk = t;
   if ((t = tc::tn_tc_scratch_floats((int)L.rows_out, (int)D, (int)D)) > sk) sk = t;
+  if ((t = tc::tn_tc_scratch_floats((int)(B * C), (int)D, (int)D)) > sk) sk = t;
   L.splitk = take(sk);
   L.gu = take(B * n * D);
+  L.GPp = take(2 * B * C * PI * D);   // split pairs of the projection-gradient accumulators (tensor-core wgrad)
+  L.Hp = take(2 * B * C * D);         // split pair of the chart vectors
   L.bws_floats = o;
   return CLIORA_OK;
 }
@@ -261,26 +265,79 @@ static int prepare_w2_pairs(const Ctx& c, const float* W2, float* pair, float* p
   return CLIORA_OK;
 }
 
+// dW_k[D, D] (+)= GP[:, k*D:(k+1)*D]^T H  for the nblk column blocks of a projection-gradient accumulator GP [B*C, nblk*D]
+// (dst[k], ldc[k], acc[k] say where block k goes).  Tensor-core path: GP and H are first re-written as split pairs.
+static int cell_wgrad(const Ctx& c, const float* GP, int nblk, const float* H, float* const* dst, const int64_t* ldc,
+                      const int* acc, float* bws) {
+  const int D = c.d.D;
+  const int64_t BC = (int64_t)c.d.B * c.C;
+  float* scratch = bws + c.L.splitk;
+  if (c.use_tc) {
+    float* GPp = bws + c.L.GPp;
+    float* Hp = bws + c.L.Hp;
+    const int64_t n4 = BC * nblk * D / 4;
+    tc::split_tf32_rows_kernel<<<ceil_div(n4, 256) < 2368 ? ceil_div(n4, 256) : 2368, 256, 0, c.st>>>(
+        GP, BC, nblk * D, nblk * D, GPp);
+    CL_CHECK_LAUNCH("split_tf32_rows_kernel");
+    tc::split_tf32_rows_kernel<<<ceil_div(BC * D / 4, 256) < 2368 ? ceil_div(BC * D / 4, 256) : 2368, 256, 0, c.st>>>(
+        H, BC, D, D, Hp);
+    CL_CHECK_LAUNCH("split_tf32_rows_kernel");
+    tc::PairRef Bp{Hp, BC, D, BC * D};
+    for (int k = 0; k < nblk; ++k) {
+      if (!dst[k]) continue;
+      tc::PairRef Ap{GPp + (int64_t)k * D, BC, (int64_t)nblk * D, BC * nblk * D};
+      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)BC, D, D, dst[k], ldc[k], acc[k], scratch, "tc_gemm_wgrad_cell"));
+    }
+    return CLIORA_OK;
+  }
+  for (int k = 0; k < nblk; ++k) {
+    if (!dst[k]) continue;
+    CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GP + (int64_t)k * D, (int64_t)nblk * D, H, D, dst[k], ldc[k], acc[k], scratch));
+  }
+  return CLIORA_OK;
+}
+
 template <bool VL>
 static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
-  const size_t smem = (size_t)(a.D + a.N + 2 * a.R + 64) * sizeof(float);
-  {
-    const double rows = (double)a.B * a.L * a.N;
-    ProfScope prof(c.st, "cell_aggregate", 2.0 * rows * a.D, 4.0 * (rows * (a.D + 2) + 2.0 * a.B * a.L * a.D));
-    cell_aggregate_kernel<VL><<<a.B * a.L, 128, smem, c.st>>>(a);
+  const double rows = (double)a.B * a.L * a.N;
+  ProfScope prof(c.st, "cell_aggregate", 2.0 * rows * a.D, 4.0 * (rows * (a.D + 2) + 2.0 * a.B * a.L * a.D));
+  if (VL && a.D <= 128 * kColT && g_debug[3] == 0) {
+    // warp per cell, 8 cells of one sentence per CTA, the image's regions staged once in shared memory
+    const size_t smem = ((size_t)a.R * a.D + (size_t)kCellsPerCta * a.N) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      CL_CUDA(cudaFuncSetAttribute(cell_fwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const int chunks = ceil_div(a.L, kCellsPerCta);
+    cell_fwd_warp_kernel<true><<<a.B * chunks, 256, smem, c.st>>>(a);
+    CL_CHECK_LAUNCH("cell_fwd_warp_kernel");
+    return CLIORA_OK;
   }
+  const size_t smem = (size_t)(a.D + a.N + 2 * a.R + 64) * sizeof(float);
+  cell_aggregate_kernel<VL><<<a.B * a.L, 128, smem, c.st>>>(a);
   CL_CHECK_LAUNCH("cell_aggregate_kernel");
   return CLIORA_OK;
 }
 
 template <bool VL>
 static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
-  const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64) * sizeof(float);
-  {
-    const double rows = (double)g.c.B * g.c.L * g.c.N;
-    ProfScope prof(c.st, "cell_bwd", 4.0 * rows * g.c.D, 4.0 * (2.0 * rows * (g.c.D + 2) + 3.0 * g.c.B * g.c.L * g.c.D));
-    cell_bwd_kernel<VL><<<g.c.B * g.c.L, 256, smem, c.st>>>(g);
+  const double rows = (double)g.c.B * g.c.L * g.c.N;
+  ProfScope prof(c.st, "cell_bwd", 4.0 * rows * g.c.D, 4.0 * (2.0 * rows * (g.c.D + 2) + 3.0 * g.c.B * g.c.L * g.c.D));
+  if (VL && g.c.D <= 128 * kColT && g_debug[3] == 0) {
+    const size_t smem = ((size_t)g.c.R * g.c.D + (size_t)kCellsPerCta * g.c.D + 32) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      CL_CUDA(cudaFuncSetAttribute(cell_bwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const int chunks = ceil_div(g.c.L, kCellsPerCta);
+    cell_bwd_warp_kernel<true><<<g.c.B * chunks, 256, smem, c.st>>>(g);
+    CL_CHECK_LAUNCH("cell_bwd_warp_kernel");
+    return CLIORA_OK;
   }
+  const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64) * sizeof(float);
+  cell_bwd_kernel<VL><<<g.c.B * g.c.L, 256, smem, c.st>>>(g);
   CL_CHECK_LAUNCH("cell_bwd_kernel");
   return CLIORA_OK;
 }
@@ -566,11 +623,15 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
     CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
     if (lo_out) CL_TRY(colsum(c.st, GY + lo_out, D, c.L.rows_out, D, db2, 1, scratch));
   }
-  if (dW1) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPo, 2 * D, outside_h, D, dW1 + D, 2 * D, 0, scratch));
-  if (dWb) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPo + D, 2 * D, outside_h, D, dWb, D, 0, scratch));
+  {
+    float* dst[2] = {dW1 ? dW1 + D : nullptr, dWb};
+    const int64_t ldc[2] = {2 * D, D};
+    const int accs[2] = {0, 0};
+    CL_TRY(cell_wgrad(c, GPo, 2, outside_h, dst, ldc, accs, bws));
+  }
   if (!sh) {
     const float* GPi = bws + c.L.GP_in;
-    if (grads->oW1)
+    if (grads->oW1)   // first-argument projection of the outside compose (column block 3 of GP_in)
       CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + 3 * D, 4 * D, inside_h, D, grads->oW1, 2 * D, 0, scratch));
     if (grads->ob1) CL_TRY(colsum(c.st, GPi + 3 * D, 4 * D, BC, D, grads->ob1, 0, scratch));
   }
@@ -629,11 +690,12 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
     CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
     if (lo_in) CL_TRY(colsum(c.st, GY + lo_in, D, c.L.rows_in, D, grads->b2, 1, scratch));
   }
-  if (grads->W1) {
-    CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi, ldp, inside_h, D, grads->W1, 2 * D, 0, scratch));
-    CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + D, ldp, inside_h, D, grads->W1 + D, 2 * D, acc, scratch));
+  {
+    float* dst[4] = {grads->W1, grads->W1 ? grads->W1 + D : nullptr, grads->Wb, nullptr};
+    const int64_t ldc[4] = {2 * D, 2 * D, D, D};
+    const int accs[4] = {0, acc, acc, 0};
+    CL_TRY(cell_wgrad(c, GPi, PI, inside_h, dst, ldc, accs, bws));
   }
-  if (grads->Wb) CL_TRY(launch_gemm_tn(c.st, (int)BC, D, D, GPi + 2 * D, ldp, inside_h, D, grads->Wb, D, acc, scratch));
   if (grads->b1) CL_TRY(colsum(c.st, GPi, ldp, BC, D, grads->b1, 0, scratch));
   if (vl && grad_obj) {
     dim3 grid(ceil_div(D, 32), B);

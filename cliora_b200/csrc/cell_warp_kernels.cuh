@@ -1,0 +1,341 @@
+// Vision-language cell kernels, warp-per-cell variant.
+//
+// The block-per-cell kernels in chart_kernels.cuh make every cell re-read its image's R region vectors
+// (R*D*4 = 57.6 KB at R=36, D=400) from L2 twice; at 640 cells per level that is ~74 MB of L2 traffic per
+// level and ~22 us.  Here one CTA owns up to 8 cells of the SAME sentence: the image's regions are staged
+// once in shared memory and each warp then does everything for one cell with warp shuffles only (no block
+// barrier after the staging).  Lane l owns columns j = 4*l + 128*t, t < 4, so D <= 512.
+#pragma once
+#include "chart_kernels.cuh"
+
+namespace cliora {
+
+constexpr int kCellsPerCta = 8;
+constexpr int kColT = 4;   // float4 column groups per lane
+
+CL_D float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+CL_D void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+}
+
+// forward: softmax over splits, weighted sum, normalise, region attention, second normalise
+// dynamic smem: (VL ? R*D : 0) + 8*N floats
+template <bool VL>
+__global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_obj = sm;
+  float* s_pbase = sm + (VL ? a.R * a.D : 0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunks = (a.L + kCellsPerCta - 1) / kCellsPerCta;
+  const int b = blockIdx.x / chunks;
+  const int p = (blockIdx.x % chunks) * kCellsPerCta + warp;
+  if (VL) {
+    const float* obj = a.obj + (int64_t)b * a.R * a.D;
+    for (int i = tid * 4; i < a.R * a.D; i += 1024) st4(s_obj + i, ld4(obj + i));
+    __syncthreads();
+  }
+  if (p >= a.L) return;
+  float* s_p = s_pbase + warp * a.N;
+  const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + p;
+  const int64_t row0 = (int64_t)b * a.L * a.N + (int64_t)p * a.sp;
+
+  // 1. softmax over the N splits (lanes over k)
+  float sbar = 0.f;
+  if (a.E == nullptr) {
+    if (lane == 0) s_p[0] = 1.f;
+  } else {
+    float mx = -INFINITY;
+    for (int k = lane; k < a.N; k += 32) mx = fmaxf(mx, a.E[row0 + (int64_t)k * a.sk]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < a.N; k += 32) {
+      const float ex = expf(a.E[row0 + (int64_t)k * a.sk] - mx);
+      s_p[k] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int k = lane; k < a.N; k += 32) {
+      const float pk = s_p[k] * inv;
+      s_p[k] = pk;
+      a.Pr[row0 + (int64_t)k * a.sk] = pk;
+      sbar = fmaf(pk, a.E[row0 + (int64_t)k * a.sk], sbar);
+    }
+    sbar = warp_sum(sbar);
+  }
+  if (lane == 0) a.chart_s[cell] = sbar;
+  __syncwarp();
+
+  // 2. a = sum_k p_k y_k   (two rows in flight)
+  float4 acc[kColT];
+#pragma unroll
+  for (int t = 0; t < kColT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < a.N; k += 2) {
+    const bool two = k + 1 < a.N;
+    const float p0 = s_p[k], p1 = two ? s_p[k + 1] : 0.f;
+    const float* y0 = a.Y + (row0 + (int64_t)k * a.sk) * a.D;
+    const float* y1 = two ? a.Y + (row0 + (int64_t)(k + 1) * a.sk) * a.D : y0;
+    float4 v0[kColT], v1[kColT];
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < a.D) {
+        v0[t] = ld4(y0 + j);
+        v1[t] = ld4(y1 + j);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < a.D) {
+        fma4(acc[t], p0, v0[t]);
+        fma4(acc[t], p1, v1[t]);
+      }
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int t = 0; t < kColT; ++t)
+    if (lane * 4 + t * 128 < a.D) ss += dot4(acc[t], acc[t]);
+  ss = warp_sum(ss);
+  const float nrm = fmaxf(sqrtf(ss), kTiny);
+  const float inv_nrm = 1.f / nrm;
+  float4 q[kColT];
+#pragma unroll
+  for (int t = 0; t < kColT; ++t) {
+    const int j = lane * 4 + t * 128;
+    q[t] = make_float4(acc[t].x * inv_nrm, acc[t].y * inv_nrm, acc[t].z * inv_nrm, acc[t].w * inv_nrm);
+    if (j < a.D) st4((VL ? a.q : a.chart_h) + cell * a.D + j, q[t]);
+  }
+  if (lane == 0) a.nrm[cell] = nrm;
+  if (!VL) return;
+
+  // 3. attention against the staged regions: logits owned by lane r % 32 (R <= 64)
+  float lg0 = -INFINITY, lg1 = -INFINITY;
+  for (int r = 0; r < a.R; ++r) {
+    float d = 0.f;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < a.D) d += dot4(q[t], ld4(s_obj + r * a.D + j));
+    }
+    d = warp_sum(d);
+    if ((r & 31) == lane) {
+      if (r < 32) lg0 = d;
+      else lg1 = d;
+    }
+  }
+  const float mx = warp_max(fmaxf(lg0, lg1));
+  const float e0 = (lane < a.R) ? expf(lg0 - mx) : 0.f;
+  const float e1 = (lane + 32 < a.R) ? expf(lg1 - mx) : 0.f;
+  const float inv = 1.f / warp_sum(e0 + e1);
+  const float at0 = e0 * inv, at1 = e1 * inv;
+  float pa0 = at0, pa1 = at1;
+  if (lane < a.R) {
+    a.att[cell * a.R + lane] = at0;
+    if (a.keep != nullptr) pa0 = a.keep[cell * a.R + lane] ? at0 * kKeepScale : 0.f;
+  }
+  if (lane + 32 < a.R) {
+    a.att[cell * a.R + lane + 32] = at1;
+    if (a.keep != nullptr) pa1 = a.keep[cell * a.R + lane + 32] ? at1 * kKeepScale : 0.f;
+  }
+  // a2 = q + sum_r patt_r obj_r
+  for (int r = 0; r < a.R; ++r) {
+    const float w = __shfl_sync(0xffffffffu, r < 32 ? pa0 : pa1, r & 31);
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < a.D) fma4(q[t], w, ld4(s_obj + r * a.D + j));
+    }
+  }
+  float ss2 = 0.f;
+#pragma unroll
+  for (int t = 0; t < kColT; ++t)
+    if (lane * 4 + t * 128 < a.D) ss2 += dot4(q[t], q[t]);
+  ss2 = warp_sum(ss2);
+  const float nrm2 = fmaxf(sqrtf(ss2), kTiny);
+  const float inv2 = 1.f / nrm2;
+#pragma unroll
+  for (int t = 0; t < kColT; ++t) {
+    const int j = lane * 4 + t * 128;
+    if (j < a.D)
+      st4(a.chart_h + cell * a.D + j, make_float4(q[t].x * inv2, q[t].y * inv2, q[t].z * inv2, q[t].w * inv2));
+  }
+  if (lane == 0) a.nrm2[cell] = nrm2;
+}
+
+// backward of the above + per-split gradients (same maths as cell_bwd_kernel)
+// phase 1: warp per cell (attention / normalise backward against the staged regions) -> ga in shared memory
+// phase 2: all (cell, split) items of the CTA spread over the 8 warps
+// dynamic smem: (VL ? R*D : 0) + 8*D + 32 floats
+template <bool VL>
+__global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g) {
+  const CellArgs& a = g.c;
+  extern __shared__ __align__(16) float sm[];
+  float* s_obj = sm;
+  float* s_ga = sm + (VL ? a.R * a.D : 0);            // [8][D]
+  float* s_sc = s_ga + kCellsPerCta * a.D;             // [8][2]: gs, cm
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunks = (a.L + kCellsPerCta - 1) / kCellsPerCta;
+  const int b = blockIdx.x / chunks;
+  const int p0 = (blockIdx.x % chunks) * kCellsPerCta;
+  const int p = p0 + warp;
+  const bool active = p < a.L;
+  if (VL) {
+    const float* obj = a.obj + (int64_t)b * a.R * a.D;
+    for (int i = tid * 4; i < a.R * a.D; i += 1024) st4(s_obj + i, ld4(obj + i));
+    __syncthreads();
+  }
+  if (active) {
+    const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + p;
+    const float nrm = a.nrm[cell];
+    float4 gv[kColT], hv[kColT], qv[kColT];
+    float hd = 0.f;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      gv[t] = hv[t] = qv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < a.D) {
+        gv[t] = ld4(g.Gh + cell * a.D + j);
+        hv[t] = ld4(a.chart_h + cell * a.D + j);
+        qv[t] = VL ? ld4(a.q + cell * a.D + j) : hv[t];
+        hd += dot4(hv[t], gv[t]);
+      }
+    }
+    hd = warp_sum(hd);
+    if (VL) {
+      const float nrm2 = a.nrm2[cell];
+      const float coef = unit_bwd_coef(nrm2, hd);
+      const float inv2 = 1.f / nrm2;
+#pragma unroll
+      for (int t = 0; t < kColT; ++t) {
+        const int j = lane * 4 + t * 128;
+        gv[t] = make_float4((gv[t].x - hv[t].x * coef) * inv2, (gv[t].y - hv[t].y * coef) * inv2,
+                            (gv[t].z - hv[t].z * coef) * inv2, (gv[t].w - hv[t].w * coef) * inv2);   // ga2
+        if (j < a.D) st4(g.GA2 + cell * a.D + j, gv[t]);
+      }
+      float ga0 = 0.f, ga1 = 0.f;   // g_att_r = (ga2 . obj_r) * scale_r, owned by lane r % 32
+      for (int r = 0; r < a.R; ++r) {
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (j < a.D) d += dot4(gv[t], ld4(s_obj + r * a.D + j));
+        }
+        d = warp_sum(d);
+        if ((r & 31) == lane) {
+          if (r < 32) ga0 = d;
+          else ga1 = d;
+        }
+      }
+      float at0 = 0.f, at1 = 0.f, sc0 = 1.f, sc1 = 1.f;
+      if (lane < a.R) {
+        at0 = a.att[cell * a.R + lane];
+        if (a.keep != nullptr) sc0 = a.keep[cell * a.R + lane] ? kKeepScale : 0.f;
+      }
+      if (lane + 32 < a.R) {
+        at1 = a.att[cell * a.R + lane + 32];
+        if (a.keep != nullptr) sc1 = a.keep[cell * a.R + lane + 32] ? kKeepScale : 0.f;
+      }
+      ga0 *= sc0;
+      ga1 *= sc1;
+      const float dsum = warp_sum(at0 * ga0 + at1 * ga1);
+      const float gl0 = at0 * (ga0 - dsum), gl1 = at1 * (ga1 - dsum);
+      if (lane < a.R) {
+        g.coef[(cell * 2) * a.R + lane] = at0 * sc0;
+        g.coef[(cell * 2 + 1) * a.R + lane] = gl0;
+      }
+      if (lane + 32 < a.R) {
+        g.coef[(cell * 2) * a.R + lane + 32] = at1 * sc1;
+        g.coef[(cell * 2 + 1) * a.R + lane + 32] = gl1;
+      }
+      for (int r = 0; r < a.R; ++r) {   // gq = ga2 + sum_r g_logit_r obj_r
+        const float w = __shfl_sync(0xffffffffu, r < 32 ? gl0 : gl1, r & 31);
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (j < a.D) fma4(gv[t], w, ld4(s_obj + r * a.D + j));
+        }
+      }
+      hd = 0.f;
+#pragma unroll
+      for (int t = 0; t < kColT; ++t)
+        if (lane * 4 + t * 128 < a.D) hd += dot4(qv[t], gv[t]);
+      hd = warp_sum(hd);
+    }
+    // ga = unit_bwd(gq, q, nrm)
+    const float coef = unit_bwd_coef(nrm, hd);
+    const float inv = 1.f / nrm;
+    float ad = 0.f;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      gv[t] = make_float4((gv[t].x - qv[t].x * coef) * inv, (gv[t].y - qv[t].y * coef) * inv,
+                          (gv[t].z - qv[t].z * coef) * inv, (gv[t].w - qv[t].w * coef) * inv);
+      if (lane * 4 + t * 128 < a.D) ad += dot4(qv[t], gv[t]);
+    }
+    ad = warp_sum(ad);
+    if (a.E == nullptr) {   // leaf: gu = ga * (1 - t^2)
+      const int64_t row = (int64_t)b * a.L + p;
+#pragma unroll
+      for (int t = 0; t < kColT; ++t) {
+        const int j = lane * 4 + t * 128;
+        if (j < a.D) {
+          const float4 tv = ld4(g.leaf_t + row * a.D + j);
+          st4(g.gu + row * a.D + j, make_float4(gv[t].x * (1.f - tv.x * tv.x), gv[t].y * (1.f - tv.y * tv.y),
+                                                 gv[t].z * (1.f - tv.z * tv.z), gv[t].w * (1.f - tv.w * tv.w)));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < kColT; ++t) {
+        const int j = lane * 4 + t * 128;
+        if (j < a.D) st4(s_ga + warp * a.D + j, gv[t]);
+      }
+      if (lane == 0) {
+        const float gs = g.Gs[cell];
+        s_sc[warp * 2] = gs;
+        s_sc[warp * 2 + 1] = nrm * ad + a.chart_s[cell] * gs;   // sum_m p_m gp_m
+      }
+    }
+  }
+  if (a.E == nullptr) return;   // uniform over the CTA
+  __syncthreads();
+  const int ncell = min(kCellsPerCta, a.L - p0);
+  for (int it = warp; it < ncell * a.N; it += kCellsPerCta) {
+    const int cw = it / a.N, k = it % a.N;
+    const int64_t row = (int64_t)b * a.L * a.N + (int64_t)(p0 + cw) * a.sp + (int64_t)k * a.sk;
+    float* y = a.Y + row * a.D;
+    const float pk = a.Pr[row];
+    const float gs = s_sc[cw * 2], cm = s_sc[cw * 2 + 1];
+    float d = 0.f;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < a.D) {
+        const float4 yv = ld4(y + j);
+        const float4 gg = ld4(s_ga + cw * a.D + j);
+        d += dot4(yv, gg);
+        float4 o;
+        o.x = yv.x > 0.f ? pk * gg.x : 0.f;
+        o.y = yv.y > 0.f ? pk * gg.y : 0.f;
+        o.z = yv.z > 0.f ? pk * gg.z : 0.f;
+        o.w = yv.w > 0.f ? pk * gg.w : 0.f;
+        if (a.y_lo_off != 0) {
+          float4 hi, lo;
+          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+          st4(y + j, hi);
+          st4(y + a.y_lo_off + j, lo);
+        } else {
+          st4(y + j, o);
+        }
+      }
+    }
+    d = warp_sum(d);
+    if (lane == 0) {
+      const float gp = d + a.E[row] * gs;
+      g.GE[row] = pk * (gs + gp - cm);
+    }
+  }
+}
+
+}  // namespace cliora

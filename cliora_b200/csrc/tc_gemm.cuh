@@ -493,6 +493,22 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float*
     out[n + i] = v - hi;
   }
 }
+// src[rows, cols] (row pitch ld) -> dense split pair [2, rows, cols]
+__global__ void split_tf32_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld,
+                                      float* __restrict__ out) {
+  const int64_t n4 = rows * (cols / 4);
+  const int64_t part = rows * (int64_t)cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (cols / 4);
+    const int c = (int)(i % (cols / 4)) * 4;
+    const float4 v = ld4(src + r * ld + c);
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+    st4(out + r * cols + c, hi);
+    st4(out + part + r * cols + c, lo);
+  }
+}
+
 // W[rows, cols] -> split pair of W^T ([2, cols, rows])
 __global__ void split_tf32_transpose_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
                                             float* __restrict__ out) {
@@ -567,7 +583,7 @@ struct PairRef {            // a split-pair operand in global memory
 // Two tile configurations.  Wide (256 columns, 2 stages): 21.8 MAC per shared-memory byte read by the UMMAs, main +
 // cross accumulators fill the 512 TMEM columns -- used whenever the narrow grid would exceed one wave.  Narrow (80
 // columns, 4 stages): 5 CTAs per 128 rows at N = 400, more SMs busy on the small chart levels.
-constexpr int kTcNarrowN = 80, kTcNarrowStages = 4;
+constexpr int kTcNarrowN = 80, kTcNarrowStages = 4;   // (2 stages / 2 CTAs per SM was tried: the tile is smem-bound, no gain)
 constexpr int kTcWideN = 256, kTcWideStages = 2;
 
 inline bool tc_supported(int N, int K, const PairRef& A, const PairRef& W) {

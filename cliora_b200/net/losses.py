@@ -62,8 +62,19 @@ class VGLossFn(torch.autograd.Function):
         return g * g_w, None
 
 
+def _pair(t):
+    """Split pair [2, rows, cols] (tf32-rounded part, exact remainder) of a contiguous fp32 matrix."""
+    out = torch.empty((2,) + tuple(t.shape), device=t.device, dtype=torch.float32)
+    check(_lib.lib().cliora_split_tf32(ptr(t), t.numel(), ptr(out), _lib.stream()), 'cliora_split_tf32')
+    return out
+
+
+_TC_MIN_FLOP = 2e8     # below this the fp32 SIMT kernel is as fast (launch-bound)
+
+
 class LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b) on the library's fp32 GEMM (Embed / ImageEncoder / reconstruction projections)."""
+    """y = x W^T + b (Embed / ImageEncoder / reconstruction projections, trainer.py:219-224, utils.py:52-55).
+    Large problems run on the tcgen05 3xTF32 kernels (fp32-grade accuracy), small ones on the fp32 SIMT kernel."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -72,21 +83,32 @@ class LinearFn(torch.autograd.Function):
         b = None if bias is None else bias.contiguous().float()
         M, K = x2.shape
         N = w.shape[0]
+        L = _lib.lib()
         out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        use_tc = (2.0 * M * N * K >= _TC_MIN_FLOP) and K % 4 == 0 and N % 4 == 0 and K >= 32
+        xp = None
         with torch.cuda.device(x.device):
-            check(_lib.lib().cliora_linear(M, N, K, ptr(x2), ptr(w), ptr(b), 0, ptr(out), _lib.stream()),
-                  'cliora_linear')
-        ctx.save_for_backward(x2, w)
+            if use_tc:
+                xp, wp = _pair(x2), _pair(w)
+                check(L.cliora_tc_linear(M, N, K, ptr(xp), ptr(wp), ptr(b), 0, ptr(out), _lib.stream()),
+                      'cliora_tc_linear')
+            else:
+                check(L.cliora_linear(M, N, K, ptr(x2), ptr(w), ptr(b), 0, ptr(out), _lib.stream()), 'cliora_linear')
+        ctx.use_tc = use_tc
+        if use_tc:
+            ctx.save_for_backward(xp, w)     # the input pair is reused by the weight-gradient GEMM
+        else:
+            ctx.save_for_backward(x2, w)
         ctx.has_bias = bias is not None
         ctx.in_shape = x.shape
         return out.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, g):
-        x2, w = ctx.saved_tensors
+        xs, w = ctx.saved_tensors
         L = _lib.lib()
-        M, K = x2.shape
-        N = w.shape[0]
+        N, K = w.shape
+        M = xs.shape[-2]
         g2 = g.reshape(M, N).contiguous().float()
         gx = gw = gb = None
         with torch.cuda.device(g.device):
@@ -97,9 +119,17 @@ class LinearFn(torch.autograd.Function):
                 gx = gx.view(ctx.in_shape)
             if ctx.needs_input_grad[1]:
                 gw = torch.empty(N, K, device=g.device, dtype=torch.float32)
-                scratch = torch.empty(int(L.cliora_matmul_tn_scratch_floats(M, N, K)) + 8, device=g.device,
-                                      dtype=torch.float32)
-                check(L.cliora_matmul_tn(M, N, K, ptr(g2), ptr(x2), ptr(gw), 0, ptr(scratch), st), 'cliora_matmul_tn')
+                if ctx.use_tc:
+                    gp = _pair(g2)
+                    scratch = torch.empty(int(L.cliora_tc_matmul_tn_scratch_floats(M, N, K)) + 8, device=g.device,
+                                          dtype=torch.float32)
+                    check(L.cliora_tc_matmul_tn(M, N, K, ptr(gp), ptr(xs), ptr(gw), 0, ptr(scratch), st),
+                          'cliora_tc_matmul_tn')
+                else:
+                    scratch = torch.empty(int(L.cliora_matmul_tn_scratch_floats(M, N, K)) + 8, device=g.device,
+                                          dtype=torch.float32)
+                    check(L.cliora_matmul_tn(M, N, K, ptr(g2), ptr(xs), ptr(gw), 0, ptr(scratch), st),
+                          'cliora_matmul_tn')
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 gb = g2.sum(0)
         return gx, gw, gb

@@ -26,8 +26,11 @@ class ImageEncoder(nn.Module):
                 p.data.zero_()
 
     def forward(self, obj_feats):
+        # one N = 2D GEMM for both heads (the input pair and its weight-gradient GEMM are shared)
         f = obj_feats.float()
-        return linear(f, self.fc.weight, self.fc.bias), linear(f, self.fc_vis.weight, self.fc_vis.bias)
+        D = self.fc.weight.shape[0]
+        both = linear(f, torch.cat([self.fc.weight, self.fc_vis.weight], 0), torch.cat([self.fc.bias, self.fc_vis.bias], 0))
+        return both[..., :D].contiguous(), both[..., D:].contiguous()
 
 
 class Embed(nn.Module):
@@ -49,7 +52,9 @@ class Embed(nn.Module):
     def forward(self, x):
         B, n = x.shape
         emb = self.embeddings(x.view(-1))
-        return linear(emb, self.mat).view(B, n, -1), linear(emb, self.mat1).view(B, n, -1)
+        D = self.mat.shape[0]
+        both = linear(emb, torch.cat([self.mat, self.mat1], 0))      # one N = 2D GEMM for span and word projections
+        return both[:, :D].contiguous().view(B, n, -1), both[:, D:].contiguous().view(B, n, -1)
 
 
 class ReconstructionSoftmaxLoss(nn.Module):

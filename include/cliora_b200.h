@@ -120,6 +120,8 @@ typedef struct cliora_layout {
   int64_t GE, GZ, splitk, gu; /* per-level split scratch, split-K partials, leaf pre-activation grads */
   /* forward workspace, tensor-core operands: split pairs [2, D, D] of W2 and W2^T (o* alias when share) */
   int64_t W2p, W2Tp, oW2p, oW2Tp;
+  /* backward scratch, tensor-core weight gradients: split pairs of GP [2,B*C,PI*D] and of the chart vectors [2,B*C,D] */
+  int64_t GPp, Hp;
 } cliora_layout;
 
 int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);

@@ -206,3 +206,14 @@ def test_simt_fallback_gemm_path_matches_too():
         test_chart_vs_oracle_live(3, 9, 400, 36, True)
     finally:
         _lib.lib().cliora_debug_set(1, 0)
+
+
+def test_block_per_cell_vl_kernels_match_too(golden):
+    """The original block-per-cell attention kernels (used when D > 512) stay parity-green."""
+    from cliora_b200 import _lib
+    _lib.lib().cliora_debug_set(3, 1)
+    try:
+        test_cliora_chart_vs_golden(golden, 'cliora_b4_n9_d48_r36_train.pt')
+        test_chart_vs_oracle_live(4, 10, 400, 36, True)
+    finally:
+        _lib.lib().cliora_debug_set(3, 0)
