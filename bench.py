@@ -131,6 +131,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chains', type=int, default=None, help='concurrent sentence sub-batches (default: auto)')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32'],
+                    help="fp32 = fp32-accurate 3xTF32 tensor-core GEMMs (headline); tf32 = single-pass TF32, tolerance 1e-2")
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     cfg = dict(CFG, B=args.batch, n=args.length)
@@ -174,6 +176,7 @@ def main():
     trainer = build_trainer(cfg)
     if args.chains is not None:
         trainer.net.diora.chains = args.chains
+    trainer.net.diora.precision = args.precision
     if world > 1:
         from cliora_b200.parallel import GradSync
         trainer.grad_sync = GradSync([p for p in trainer.net.parameters() if p.requires_grad], world)
@@ -299,7 +302,7 @@ def main():
         out = {
             'metric': METRIC, 'value': value, 'unit': 'sentences/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'tf32', 'data': 'synthetic',
             'config': {'workload': workload, 'global_batch': cfg['B'] * world, 'parallelism': 'dp%d' % world,
                        'launch': 'cuda-graph replay' if use_graph else 'eager',
                        'l2': 'per-step working set (~0.6 GB of per-split buffers) exceeds the 126 MB L2; 4 distinct batches cycled'},

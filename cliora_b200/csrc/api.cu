@@ -94,6 +94,7 @@ struct Ctx {
   int64_t C;
   cudaStream_t st;
   bool use_tc;   // compose GEMMs on tcgen05 (3xTF32 split pairs) instead of the SIMT fp32 kernel
+  int tc_mode;   // UMMA accumulation scheme: 2 = fp32-accurate 3xTF32 (default), 1 = single-pass TF32 (CLIORA_FLAG_TF32_1PASS)
 };
 
 static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
@@ -103,6 +104,7 @@ static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
   c.C = num_cells(dims->n);
   c.st = (cudaStream_t)stream;
   c.use_tc = (dims->D >= 32) && (g_debug[1] == 0);
+  c.tc_mode = (dims->flags & CLIORA_FLAG_TF32_1PASS) ? 1 : g_debug[0];
   return CLIORA_OK;
 }
 
@@ -224,7 +226,7 @@ static int compose_gemm(const Ctx& c, bool outside, int64_t r0, int64_t rows, co
     tc::TcEpilogue ep{};
     ep.C = Yb + r0 * D; ep.ldc = D; ep.cmap = dense_rows();
     ep.bias = b2; ep.act = 1;
-    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2", g_debug[0], g_debug[2]);
+    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2", c.tc_mode, g_debug[2]);
   }
   return dense_linear(c.st, (int)rows, D, D, Zb + r0 * D, W2, b2, 1, Yb + r0 * D, "gemm_compose_w2");
 }
@@ -242,7 +244,7 @@ static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows
     tc::TcEpilogue ep{};
     ep.C = GZ; ep.ldc = D; ep.cmap = dense_rows();
     ep.mask = Zb + r0 * D; ep.ldm = D; ep.mask_lo_off = total * D;
-    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", g_debug[0], g_debug[2]);
+    return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", c.tc_mode, g_debug[2]);
   }
   GemmParams p{};
   p.A = Yb + r0 * D; p.lda = D; p.amap = dense_rows();
@@ -286,7 +288,7 @@ static int cell_wgrad(const Ctx& c, const float* GP, int nblk, const float* H, f
     for (int k = 0; k < nblk; ++k) {
       if (!dst[k]) continue;
       tc::PairRef Ap{GPp + (int64_t)k * D, BC, (int64_t)nblk * D, BC * nblk * D};
-      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)BC, D, D, dst[k], ldc[k], acc[k], scratch, "tc_gemm_wgrad_cell"));
+      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)BC, D, D, dst[k], ldc[k], acc[k], scratch, "tc_gemm_wgrad_cell", c.tc_mode));
     }
     return CLIORA_OK;
   }
@@ -614,7 +616,7 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
   if (dW2) {
     if (c.use_tc) {
       tc::PairRef Ap{GY, c.L.rows_out, D, lo_out}, Bp{Z, c.L.rows_out, D, lo_out};
-      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)c.L.rows_out, D, D, dW2, D, 0, scratch, "tc_gemm_wgrad_w2"));
+      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)c.L.rows_out, D, D, dW2, D, 0, scratch, "tc_gemm_wgrad_w2", c.tc_mode));
     } else {
       CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch, "gemm_wgrad", 0, 0));
     }
@@ -681,7 +683,7 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   if (grads->W2) {
     if (c.use_tc) {
       tc::PairRef Ap{GY, c.L.rows_in, D, lo_in}, Bp{Z, c.L.rows_in, D, lo_in};
-      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)c.L.rows_in, D, D, grads->W2, D, acc, scratch, "tc_gemm_wgrad_w2"));
+      CL_TRY(tc::launch_tc_gemm_tn(c.st, Ap, Bp, (int)c.L.rows_in, D, D, grads->W2, D, acc, scratch, "tc_gemm_wgrad_w2", c.tc_mode));
     } else {
       CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch, "gemm_wgrad", 0, 0));
     }

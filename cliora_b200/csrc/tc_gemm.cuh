@@ -181,12 +181,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int stage = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        mbar_expect_tx(&full[stage], mode == 1 ? S::A_BYTES + S::B_BYTES : S::STAGE_BYTES);
         uint8_t* s = smem + stage * S::STAGE_BYTES;
         tma_load_3d(s, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 0);
-        tma_load_3d(s + S::A_BYTES, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 1);
         tma_load_3d(s + 2 * S::A_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 0);
-        tma_load_3d(s + 2 * S::A_BYTES + S::B_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 1);
+        if (mode != 1) {   // single-pass TF32 never touches the remainder parts
+          tma_load_3d(s + S::A_BYTES, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 1);
+          tma_load_3d(s + 2 * S::A_BYTES + S::B_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 1);
+        }
       }
     }
   } else if (warp == 1) {
@@ -358,7 +360,7 @@ struct TnSmem {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  float* __restrict__ partial, int rows, int Ka, int Kb, int rows_per_split) {
+                  float* __restrict__ partial, int rows, int Ka, int Kb, int rows_per_split, int mode) {
   using S = TnSmem<BLOCK_N, STAGES>;
   static_assert(BLOCK_N % 32 == 0 && 2 * BLOCK_N <= 512, "BLOCK_N");
   extern __shared__ uint8_t smem_raw[];
@@ -405,11 +407,12 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int stage = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        mbar_expect_tx(&full[stage], mode == 1 ? S::A_BYTES + S::B_BYTES : S::STAGE_BYTES);
         uint8_t* s = smem + stage * S::STAGE_BYTES;
         const int r = r_begin + kb * kTnBlockK;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
+          if (part == 1 && mode == 1) break;
 #pragma unroll
           for (int g = 0; g < kBlockM / 32; ++g)
             tma_load_3d(s + part * S::A_BYTES + g * S::CHUNK, &tmA, &full[stage], i0 + g * 32, r, part);
@@ -435,8 +438,10 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint64_t b_lo = umma_desc_mn_sw128(sa + 2 * S::A_BYTES + S::B_BYTES, S::CHUNK);
 #pragma unroll
         for (int k = 0; k < kTnBlockK / 8; ++k) {   // one 8-row K group = 1024 B = 64 x 16 B
-          umma_tf32(tmem_base + BLOCK_N, a_lo + 64 * k, b_hi + 64 * k, idesc, acc);
-          umma_tf32(tmem_base + BLOCK_N, a_hi + 64 * k, b_lo + 64 * k, idesc, 1);
+          if (mode != 1) {
+            umma_tf32(tmem_base + BLOCK_N, a_lo + 64 * k, b_hi + 64 * k, idesc, acc);
+            umma_tf32(tmem_base + BLOCK_N, a_hi + 64 * k, b_lo + 64 * k, idesc, 1);
+          }
           umma_tf32(tmem_base, a_hi + 64 * k, b_hi + 64 * k, idesc, acc);
           acc = 1;
         }
@@ -456,11 +461,13 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int c = 0; c < BLOCK_N; c += 16) {
       float v[16];
       if (num_kb > 0) {
-        float x[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), x);
+        if (mode != 1) {
+          float x[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), x);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] += x[t];
+          for (int t = 0; t < 16; ++t) v[t] += x[t];
+        }
       } else {
 #pragma unroll
         for (int t = 0; t < 16; ++t) v[t] = 0.f;
@@ -645,7 +652,7 @@ inline int64_t tn_tc_scratch_floats(int rows, int Ka, int Kb) { return (int64_t)
 
 // C[Ka,Kb] (+)= A[rows,Ka]^T B[rows,Kb], operands as split pairs
 inline int launch_tc_gemm_tn(cudaStream_t st, const PairRef& A, const PairRef& B, int rows, int Ka, int Kb, float* C,
-                             int64_t ldc, int accumulate, float* scratch, const char* tag) {
+                             int64_t ldc, int accumulate, float* scratch, const char* tag, int mode = 2) {
   if (Ka <= 0 || Kb <= 0) return CLIORA_OK;
   using S = TnSmem<kTnBlockN, kTnStages>;
   CUtensorMap tmA, tmB;
@@ -662,7 +669,7 @@ inline int launch_tc_gemm_tn(cudaStream_t st, const PairRef& A, const PairRef& B
   if (per < kTnBlockK) per = kTnBlockK;
   dim3 grid(ceil_div(Kb, kTnBlockN), ceil_div(Ka, kBlockM), splits);
   ProfScope prof(st, tag, 2.0 * rows * Ka * Kb, 4.0 * ((double)rows * (Ka + Kb) * 2 + (double)Ka * Kb));
-  tc_gemm_tn_kernel<kTnBlockN, kTnStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, scratch, rows, Ka, Kb, per);
+  tc_gemm_tn_kernel<kTnBlockN, kTnStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, scratch, rows, Ka, Kb, per, mode);
   CL_CHECK_LAUNCH("tc_gemm_tn_kernel");
   const int64_t total = (int64_t)Ka * Kb;
   splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(scratch, splits, total, Ka, Kb, C, ldc, accumulate);

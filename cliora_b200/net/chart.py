@@ -141,7 +141,7 @@ class ChartFunction(torch.autograd.Function):
     (fork/join around the calls; under CUDA-graph capture they become parallel branches)."""
 
     @staticmethod
-    def forward(ctx, run, share, outside, chains, x, obj, keep, *weights):
+    def forward(ctx, run, share, outside, chains, flags, x, obj, keep, *weights):
         L = _lib.lib()
         if not x.is_cuda:
             raise _lib.ClioraError('cliora_b200: the chart runs on CUDA only (input is on %s); no CPU fallback'
@@ -174,7 +174,7 @@ class ChartFunction(torch.autograd.Function):
             for (b0, b1, ws, lay), st in zip(parts, streams):
                 if st is not cur:
                     st.wait_stream(cur)
-                dims = Dims(b1 - b0, n, D, R, 1 if share else 0, 0)
+                dims = Dims(b1 - b0, n, D, R, 1 if share else 0, flags)
                 with torch.cuda.stream(st):
                     h = st.cuda_stream
                     check(L.cliora_inside_fwd(ctypes.byref(dims), ctypes.byref(W), _off(x, b0 * n * D),
@@ -189,7 +189,7 @@ class ChartFunction(torch.autograd.Function):
                 if st is not cur:
                     cur.wait_stream(st)
         run.parts, run.B, run.n, run.D, run.R = parts, B, n, D, R
-        ctx.run, ctx.share, ctx.outside, ctx.dims_t = run, share, outside, (B, n, D, R)
+        ctx.run, ctx.share, ctx.outside, ctx.dims_t, ctx.flags = run, share, outside, (B, n, D, R), flags
         ctx.has_obj, ctx.has_keep = obj is not None, keep is not None
         saved = [x, inside_h, inside_s, outside_h, outside_s]
         if obj is not None:
@@ -238,7 +238,7 @@ class ChartFunction(torch.autograd.Function):
             for (b0, b1, _, lay), ws, st, bws, grads in zip(parts, wss, streams, all_bws, all_grads):
                 if st is not cur:
                     st.wait_stream(cur)
-                dims = Dims(b1 - b0, n, D, R, 1 if share else 0, 0)
+                dims = Dims(b1 - b0, n, D, R, 1 if share else 0, ctx.flags)
                 with torch.cuda.stream(st):
                     h = st.cuda_stream
                     G = _weights_struct(WeightGrads, grads, share)
@@ -263,4 +263,4 @@ class ChartFunction(torch.autograd.Function):
             for other in all_grads[1:]:
                 torch._foreach_add_(grads, other)
         ctx.run.consumed = True
-        return (None, None, None, None, gx, gobj, None) + tuple(grads)
+        return (None, None, None, None, None, gx, gobj, None) + tuple(grads)

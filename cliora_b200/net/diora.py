@@ -58,6 +58,9 @@ class DioraBase(nn.Module):
         self._pending = None
         self._keep_override = None
         self.chains = None     # concurrent sentence sub-batches (None: pick from the batch size)
+        # 'fp32': tensor-core GEMMs are fp32-accurate (3xTF32, default, <= 1e-4 vs the reference);
+        # 'tf32': single TF32 pass, stated tolerance 1e-2 of max, trees not guaranteed identical
+        self.precision = 'fp32'
         self.init_parameters()
         self.reset_parameters()
         self.reset()
@@ -166,7 +169,10 @@ class DioraBase(nn.Module):
         self._keep_override = None
         run = ChartRun()
         chains = self.chains if self.chains is not None else max(1, min(4, B // 8))
-        outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, x_span, obj, keep,
+        if self.precision not in ('fp32', 'tf32'):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        flags = 2 if self.precision == 'tf32' else 0
+        outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, flags, x_span, obj, keep,
                                    *self._weight_list())
         self._run = run
         self._pending = outs

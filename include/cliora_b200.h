@@ -95,6 +95,9 @@ typedef struct cliora_dims {
 } cliora_dims;
 
 #define CLIORA_FLAG_DETERMINISTIC 1 /* reserved */
+/* Reduced-precision mode: the tensor-core GEMMs issue one TF32 pass instead of the fp32-accurate three.
+ * Stated tolerance 1e-2 of max on chart vectors (measured ~3e-3); CKY trees are NOT guaranteed identical. */
+#define CLIORA_FLAG_TF32_1PASS 2
 
 /* Float offsets of every sub-buffer inside the single forward workspace `ws`
  * (saved for backward) and the backward scratch `bws`.  -1 = not present. */

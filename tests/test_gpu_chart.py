@@ -217,3 +217,22 @@ def test_block_per_cell_vl_kernels_match_too(golden):
         test_chart_vs_oracle_live(4, 10, 400, 36, True)
     finally:
         _lib.lib().cliora_debug_set(3, 0)
+
+
+def test_tf32_single_pass_mode_has_its_own_tolerance():
+    """precision='tf32' (CLIORA_FLAG_TF32_1PASS): stated tolerance 1e-2 of max on chart tensors (fp32 mode: 1e-4)."""
+    from cliora_b200.net.cliora import DioraMLP
+    B, n, D, R = 4, 12, 400, 36
+    P0, x, obj, keep, ct, ref64 = _oracle_run(torch.float64, B, n, D, R, True)
+    errs = {}
+    for prec in ('fp32', 'tf32'):
+        m = DioraMLP(D).cuda()
+        _fill(m, P0)
+        m.precision = prec
+        m.train()
+        m.set_dropout_mask(keep.cuda())
+        with torch.no_grad():
+            m(x.cuda(), x.cuda(), obj.cuda(), obj.cuda())
+        errs[prec] = max(rel_err(getattr(m, k), ref64[k]) for k in ct)
+    assert errs['fp32'] < 1e-4, errs
+    assert 1e-5 < errs['tf32'] < 1e-2, errs     # really a different arithmetic, within its stated tolerance
