@@ -592,6 +592,7 @@ struct PairRef {            // a split-pair operand in global memory
 // columns, 4 stages): 5 CTAs per 128 rows at N = 400, more SMs busy on the small chart levels.
 constexpr int kTcNarrowN = 80, kTcNarrowStages = 4;   // (2 stages / 2 CTAs per SM was tried: the tile is smem-bound, no gain)
 constexpr int kTcWideN = 256, kTcWideStages = 2;
+constexpr int kTcMidN = 160, kTcMidStages = 3;       // 216 KB: A tile reused over 2x the columns of narrow, 3 stages
 
 inline bool tc_supported(int N, int K, const PairRef& A, const PairRef& W) {
   return (N % 4 == 0) && (K % 4 == 0) && (A.ld % 4 == 0) && (W.ld % 4 == 0) && (A.part_stride % 4 == 0) &&
@@ -622,12 +623,18 @@ inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, 
 inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, const PairRef& W, int M, int N, int K,
                              const TcEpilogue& ep, const char* tag, int mode = 2, int force_cfg = 0) {
   if (M <= 0 || N <= 0) return CLIORA_OK;
-  const int64_t narrow_ctas = (int64_t)ceil_div(M, kBlockM) * ceil_div(N, kTcNarrowN);
-  const bool wide = force_cfg == 2 || (force_cfg == 0 && narrow_ctas > 148);
-  if (wide) {
-    if (mode == 3) mode = 2;   // the wide tile has no room for rotating accumulator sets
-    return launch_tc_gemm_nt_cfg<kTcWideN, kTcWideStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
+  // pick the tile by estimated time = waves x (measured time of one CTA of that shape at K = 400, scaled by K)
+  int cfg = force_cfg;
+  if (cfg == 0) {
+    const int mt = ceil_div(M, kBlockM);
+    const double kscale = 0.5 + 0.5 * (double)K / 400.0;
+    auto cost = [&](int bn, double t_cta) { return ceil_div((int64_t)mt * ceil_div(N, bn), 148) * t_cta * kscale; };
+    const double cn = cost(kTcNarrowN, 16.5), cm = cost(kTcMidN, 22.0), cw = cost(kTcWideN, 32.0);
+    cfg = (cn <= cm && cn <= cw) ? 1 : (cm <= cw ? 3 : 2);
   }
+  if (cfg != 1 && mode == 3) mode = 2;   // only the narrow tile has room for rotating accumulator sets
+  if (cfg == 3) return launch_tc_gemm_nt_cfg<kTcMidN, kTcMidStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
+  if (cfg == 2) return launch_tc_gemm_nt_cfg<kTcWideN, kTcWideStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
   return launch_tc_gemm_nt_cfg<kTcNarrowN, kTcNarrowStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
 }
 

@@ -7,10 +7,10 @@ N = K = 400
 W = torch.randn(N, K).cuda(); b = torch.randn(N).cuda()
 Wp = torch.empty(2, N, K, device='cuda')
 L.check(lib.cliora_split_tf32(L.ptr(W), W.numel(), L.ptr(Wp), L.stream()), 's')
-for cfg in (1, 2):
+for cfg in (1, 3, 2):
   lib.cliora_debug_set(2, cfg)
-  print('tile config', {1: 'narrow 80x4', 2: 'wide 256x2'}[cfg])
-  for M in (608, 3200, 12160, 48640):
+  print('tile config', {1: 'narrow 80x4', 2: 'wide 256x2', 3: 'mid 160x3'}[cfg])
+  for M in (608, 3200, 6720, 12160, 48640):
       A = torch.randn(M, K).cuda(); Ap = torch.empty(2, M, K, device='cuda')
       L.check(lib.cliora_split_tf32(L.ptr(A), A.numel(), L.ptr(Ap), L.stream()), 's')
       C = torch.empty(M, N, device='cuda')

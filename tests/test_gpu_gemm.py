@@ -105,7 +105,7 @@ def test_tc_matmul_tn_3xtf32(M, Ka, Kb):
     assert err < 1e-5, err   # 42k rows: 5.7e-6 (truncating TMEM accumulation over ~300 k-steps per split)
 
 
-@pytest.mark.parametrize('cfg', [1, 2])
+@pytest.mark.parametrize('cfg', [1, 2, 3])
 @pytest.mark.parametrize('M,N,K', [(300, 400, 400), (1000, 1200, 400), (129, 144, 64)])
 def test_tc_linear_both_tile_configs(cfg, M, N, K):
     """Narrow (80-column) and wide (256-column, runtime UMMA N on the ragged tile) configurations agree with fp64."""
