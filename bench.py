@@ -133,6 +133,8 @@ def main():
     ap.add_argument('--chains', type=int, default=None, help='concurrent sentence sub-batches (default: auto)')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32'],
                     help="fp32 = fp32-accurate 3xTF32 tensor-core GEMMs (headline); tf32 = single-pass TF32, tolerance 1e-2")
+    ap.add_argument('--pdl', type=int, default=None, help='programmatic dependent launch on (1) / off (0)')
+    ap.add_argument('--debug-set', default='', help='dev knobs: comma list of key=value passed to cliora_debug_set')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     cfg = dict(CFG, B=args.batch, n=args.length)
@@ -172,6 +174,11 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
         dist.barrier()
     _lib.lib()
+    if args.pdl is not None:
+        _lib.lib().cliora_debug_set(100, args.pdl)
+    for kv in filter(None, args.debug_set.split(',')):
+        k, v = kv.split('=')
+        _lib.lib().cliora_debug_set(int(k), int(v))
 
     trainer = build_trainer(cfg)
     if args.chains is not None:

@@ -13,6 +13,7 @@ namespace cliora {
 __global__ __launch_bounds__(256) void atten_max_kernel(int B, int ncell, int D, int R, const float* __restrict__ h,
                                                         int64_t h_bstride, const float* __restrict__ obj,
                                                         float* __restrict__ smax, int32_t* __restrict__ amax) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][16][68];
   __shared__ __align__(16) float Bs[2][16][68];
   const int tid = threadIdx.x;
@@ -100,6 +101,7 @@ __global__ __launch_bounds__(128) void atten_max_bwd_h_kernel(int B, int ncell, 
                                                               const float* __restrict__ g,
                                                               const int32_t* __restrict__ amax,
                                                               float* __restrict__ g_h, int64_t gh_bstride) {
+  pdl_prologue();
   const int a = blockIdx.x / ncell, cell = blockIdx.x % ncell;
   float* dst = g_h + ((int64_t)a * gh_bstride + cell) * D;
   for (int j = threadIdx.x * 4; j < D; j += blockDim.x * 4) {
@@ -129,6 +131,7 @@ __global__ __launch_bounds__(128) void atten_max_bwd_obj_kernel(int B, int ncell
                                                                 const float* __restrict__ g,
                                                                 const int32_t* __restrict__ amax,
                                                                 float* __restrict__ g_obj) {
+  pdl_prologue();
   extern __shared__ __align__(16) float s_part[];   // [4][D]
   __shared__ int s_row[128];
   __shared__ float s_gv[128];
@@ -230,6 +233,7 @@ __global__ __launch_bounds__(128) void contrastive_cell_kernel(int B, int64_t C,
                                                                float* __restrict__ g_S, float* __restrict__ g_is,
                                                                float* __restrict__ g_os,
                                                                float* __restrict__ g_root_part) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* s_diag = sm;          // [B]
   float* s_gvl = sm + B;       // [B]  d loss / d vl[b]  (already divided by B for the mean over negatives)
@@ -287,6 +291,7 @@ __global__ __launch_bounds__(128) void contrastive_cell_kernel(int B, int64_t C,
 __global__ void contrastive_finish_kernel(int B, int64_t C, int ncell, const float* __restrict__ partial, float scale,
                                           float* __restrict__ loss, const float* __restrict__ g_root_part,
                                           float* __restrict__ g_is) {
+  pdl_prologue();
   __shared__ float red[64];
   float t = 0.f;
   for (int i = threadIdx.x; i < ncell; i += blockDim.x) t += partial[i];
@@ -308,6 +313,7 @@ __global__ void contrastive_finish_kernel(int B, int64_t C, int ncell, const flo
 // ------------------------------------------------------------------------------------------
 __global__ __launch_bounds__(128) void vg_loss_kernel(int B, int n, const float* __restrict__ wmax, float alpha,
                                                       float* __restrict__ rowloss, float* __restrict__ g_wmax) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* s_logit = sm;
   float* s_red = sm + B;
@@ -341,6 +347,7 @@ __global__ __launch_bounds__(128) void vg_loss_kernel(int B, int n, const float*
 }
 
 __global__ void sum_small_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[64];
   float t = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) t += v[i];

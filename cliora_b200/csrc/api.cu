@@ -1,5 +1,6 @@
 // extern "C" entry points of libcliora_b200.so (declared in include/cliora_b200.h).
 // Host-side orchestration only: level loops, buffer carving, kernel launches on the caller's stream.
+#include <stdlib.h>
 #include <string.h>
 
 #include "align_kernels.cuh"
@@ -14,6 +15,11 @@ namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
 long long g_launch_count = 0;
 Profiler g_prof;
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+int g_pdl = env_int("CLIORA_PDL", 0);
 int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = 1: block-per-cell VL kernels
 
 static int validate(const cliora_dims* d) {
@@ -155,9 +161,9 @@ static int colsum(cudaStream_t st, const float* src, int64_t ld, int64_t rows, i
   if (S < 1) S = 1;
   if (S > 64) S = 64;
   dim3 grid(ceil_div(cols, 32), S);
-  colsum_stage1_kernel<<<grid, dim3(32, 8), 0, st>>>(src, ld, rows, cols, scratch);
+  launch_k(colsum_stage1_kernel, grid, dim3(32, 8), 0, st, src, ld, rows, cols, scratch);
   CL_CHECK_LAUNCH("colsum_stage1_kernel");
-  colsum_stage2_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(scratch, S, cols, dst, accumulate);
+  launch_k(colsum_stage2_kernel, ceil_div(cols, 128), 128, 0, st, scratch, S, cols, dst, accumulate);
   CL_CHECK_LAUNCH("colsum_stage2_kernel");
   return CLIORA_OK;
 }
@@ -259,10 +265,10 @@ static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows
 static int prepare_w2_pairs(const Ctx& c, const float* W2, float* pair, float* pairT) {
   const int D = c.d.D;
   const int64_t n = (int64_t)D * D;
-  tc::split_tf32_kernel<<<ceil_div(n, 256), 256, 0, c.st>>>(W2, n, pair);
+  launch_k(tc::split_tf32_kernel, ceil_div(n, 256), 256, 0, c.st, W2, n, pair);
   CL_CHECK_LAUNCH("split_tf32_kernel");
   dim3 grid(ceil_div(D, 32), ceil_div(D, 32));
-  tc::split_tf32_transpose_kernel<<<grid, dim3(32, 8), 0, c.st>>>(W2, D, D, D, pairT);
+  launch_k(tc::split_tf32_transpose_kernel, grid, dim3(32, 8), 0, c.st, W2, D, D, D, pairT);
   CL_CHECK_LAUNCH("split_tf32_transpose_kernel");
   return CLIORA_OK;
 }
@@ -278,11 +284,9 @@ static int cell_wgrad(const Ctx& c, const float* GP, int nblk, const float* H, f
     float* GPp = bws + c.L.GPp;
     float* Hp = bws + c.L.Hp;
     const int64_t n4 = BC * nblk * D / 4;
-    tc::split_tf32_rows_kernel<<<ceil_div(n4, 256) < 2368 ? ceil_div(n4, 256) : 2368, 256, 0, c.st>>>(
-        GP, BC, nblk * D, nblk * D, GPp);
+    launch_k(tc::split_tf32_rows_kernel, ceil_div(n4, 256) < 2368 ? ceil_div(n4, 256) : 2368, 256, 0, c.st, GP, BC, nblk * D, nblk * D, GPp);
     CL_CHECK_LAUNCH("split_tf32_rows_kernel");
-    tc::split_tf32_rows_kernel<<<ceil_div(BC * D / 4, 256) < 2368 ? ceil_div(BC * D / 4, 256) : 2368, 256, 0, c.st>>>(
-        H, BC, D, D, Hp);
+    launch_k(tc::split_tf32_rows_kernel, ceil_div(BC * D / 4, 256) < 2368 ? ceil_div(BC * D / 4, 256) : 2368, 256, 0, c.st, H, BC, D, D, Hp);
     CL_CHECK_LAUNCH("split_tf32_rows_kernel");
     tc::PairRef Bp{Hp, BC, D, BC * D};
     for (int k = 0; k < nblk; ++k) {
@@ -312,12 +316,12 @@ static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
       configured = smem;
     }
     const int chunks = ceil_div(a.L, kCellsPerCta);
-    cell_fwd_warp_kernel<true><<<a.B * chunks, 256, smem, c.st>>>(a);
+    launch_k(cell_fwd_warp_kernel<true>, a.B * chunks, 256, smem, c.st, a);
     CL_CHECK_LAUNCH("cell_fwd_warp_kernel");
     return CLIORA_OK;
   }
   const size_t smem = (size_t)(a.D + a.N + 2 * a.R + 64) * sizeof(float);
-  cell_aggregate_kernel<VL><<<a.B * a.L, 128, smem, c.st>>>(a);
+  launch_k(cell_aggregate_kernel<VL>, a.B * a.L, 128, smem, c.st, a);
   CL_CHECK_LAUNCH("cell_aggregate_kernel");
   return CLIORA_OK;
 }
@@ -334,12 +338,12 @@ static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
       configured = smem;
     }
     const int chunks = ceil_div(g.c.L, kCellsPerCta);
-    cell_bwd_warp_kernel<true><<<g.c.B * chunks, 256, smem, c.st>>>(g);
+    launch_k(cell_bwd_warp_kernel<true>, g.c.B * chunks, 256, smem, c.st, g);
     CL_CHECK_LAUNCH("cell_bwd_warp_kernel");
     return CLIORA_OK;
   }
   const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64) * sizeof(float);
-  cell_bwd_kernel<VL><<<g.c.B * g.c.L, 256, smem, c.st>>>(g);
+  launch_k(cell_bwd_kernel<VL>, g.c.B * g.c.L, 256, smem, c.st, g);
   CL_CHECK_LAUNCH("cell_bwd_kernel");
   return CLIORA_OK;
 }
@@ -379,7 +383,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   sc.Gs_out = bws + c.L.Gs_out; sc.GP_out = bws + c.L.GP_out;
   {
     ProfScope prof(c.st, "split_scatter", 2.0 * rows * D, 4.0 * rows * (7.0 * D + 3));
-    split_scatter_kernel<OUTSIDE><<<ceil_div(rows, 8), 256, 0, c.st>>>(sc);
+    launch_k(split_scatter_kernel<OUTSIDE>, ceil_div(rows, 8), 256, 0, c.st, sc);
   }
   CL_CHECK_LAUNCH("split_scatter_kernel");
   (void)n;
@@ -496,7 +500,7 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
   float* Wcat_in = ws + c.L.Wcat_in;
 
   CL_CUDA(cudaMemsetAsync(ws + c.L.Pin, 0, (size_t)B * c.C * PI * D * sizeof(float), c.st));
-  pack_weights_kernel<<<296, 256, 0, c.st>>>(D, PI, w->W1, w->Wb, oW1, oWb, Wcat_in, ws + c.L.Wcat_out);
+  launch_k(pack_weights_kernel, 296, 256, 0, c.st, D, PI, w->W1, w->Wb, oW1, oWb, Wcat_in, ws + c.L.Wcat_out);
   CL_CHECK_LAUNCH("pack_weights_kernel");
   if (c.use_tc) {
     CL_TRY(prepare_w2_pairs(c, w->W2, ws + c.L.W2p, ws + c.L.W2Tp));
@@ -511,7 +515,7 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
       const int64_t rows = (int64_t)B * s.L * s.N;
       {
         ProfScope prof(c.st, "split_build", 2.0 * rows * D, 4.0 * rows * (5.0 * D + 3));
-        split_build_kernel<false><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+        launch_k(split_build_kernel<false>, ceil_div(rows, 8), 256, 0, c.st, s);
       }
       CL_CHECK_LAUNCH("split_build_kernel<inside>");
       const int64_t r0 = B * inside_rows_before(n, level);
@@ -539,7 +543,7 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
   float* Wcat_out = ws + c.L.Wcat_out;
 
   CL_CUDA(cudaMemsetAsync(ws + c.L.Pout, 0, (size_t)B * c.C * 2 * D * sizeof(float), c.st));
-  outside_root_kernel<<<B, 128, 0, c.st>>>(B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out);
+  launch_k(outside_root_kernel, B, 128, 0, c.st, B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out);
   CL_CHECK_LAUNCH("outside_root_kernel");
   if (n > 1) CL_TRY(project_level(c, n - 1, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
   for (int level = n - 2; level >= 0; --level) {
@@ -547,7 +551,7 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
     const int64_t rows = (int64_t)B * s.L * s.N;
     {
       ProfScope prof(c.st, "split_build", 2.0 * rows * D, 4.0 * rows * (5.0 * D + 3));
-      split_build_kernel<true><<<ceil_div(rows, 8), 256, 0, c.st>>>(s);
+      launch_k(split_build_kernel<true>, ceil_div(rows, 8), 256, 0, c.st, s);
     }
     CL_CHECK_LAUNCH("split_build_kernel<outside>");
     const int64_t r0 = B * outside_rows_before(n, level);
@@ -599,8 +603,7 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
   }
   if (n > 1) CL_TRY(cellgrad_level(c, n - 1, bws + c.L.GP_out, 2 * D, Wcat_out, bws + c.L.Gh_out));
   if (grads->root) {
-    outside_root_bwd_kernel<<<1, 128, 0, c.st>>>(B, D, c.C, bws + c.L.Gh_out, outside_h, ws + c.L.nrm_out,
-                                                 grads->root);
+    launch_k(outside_root_bwd_kernel, 1, 128, 0, c.st, B, D, c.C, bws + c.L.Gh_out, outside_h, ws + c.L.nrm_out, grads->root);
     CL_CHECK_LAUNCH("outside_root_bwd_kernel");
   }
   // weight gradients contributed by the outside pass
@@ -701,7 +704,7 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   if (grads->b1) CL_TRY(colsum(c.st, GPi, ldp, BC, D, grads->b1, 0, scratch));
   if (vl && grad_obj) {
     dim3 grid(ceil_div(D, 32), B);
-    obj_grad_kernel<64><<<grid, dim3(32, 4), 0, c.st>>>(D, R, c.C, bws + c.L.GA2, ws + c.L.q_in, bws + c.L.coef, grad_obj, 0);
+    launch_k(obj_grad_kernel<64>, grid, dim3(32, 4), 0, c.st, D, R, c.C, bws + c.L.GA2, ws + c.L.q_in, bws + c.L.coef, grad_obj, 0);
     CL_CHECK_LAUNCH("obj_grad_kernel");
   }
   if (!had_outside) {
@@ -744,7 +747,7 @@ int cliora_atten_max_fwd(int B, int ncell, int D, int R, const float* h, int64_t
   {
     ProfScope prof((cudaStream_t)stream, "atten_max", 2.0 * B * ncell * (double)B * R * D,
                    4.0 * ((double)B * ncell * D + (double)B * R * D + 2.0 * B * B * ncell));
-    atten_max_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, ncell, D, R, h, h_batch_stride, obj, smax, amax);
+    launch_k(atten_max_kernel, grid, 256, 0, (cudaStream_t)stream, B, ncell, D, R, h, h_batch_stride, obj, smax, amax);
   }
   CL_CHECK_LAUNCH("atten_max_kernel");
   return CLIORA_OK;
@@ -759,11 +762,11 @@ int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(st, "atten_max_bwd", 4.0 * B * ncell * (double)B * D, 4.0 * 2.0 * B * ncell * (double)B * D);
   if (g_h) {
-    atten_max_bwd_h_kernel<<<B * ncell, 128, 0, st>>>(B, ncell, D, R, obj, g_smax, amax, g_h, gh_batch_stride);
+    launch_k(atten_max_bwd_h_kernel, B * ncell, 128, 0, st, B, ncell, D, R, obj, g_smax, amax, g_h, gh_batch_stride);
     CL_CHECK_LAUNCH("atten_max_bwd_h_kernel");
   }
   if (g_obj) {
-    atten_max_bwd_obj_kernel<<<B * R, 128, 4 * 512 * sizeof(float), st>>>(B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
+    launch_k(atten_max_bwd_obj_kernel, B * R, 128, 4 * 512 * sizeof(float), st, B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
     CL_CHECK_LAUNCH("atten_max_bwd_obj_kernel");
   }
   return CLIORA_OK;
@@ -782,13 +785,10 @@ int cliora_contrastive_loss(int B, int cells, int ncell, const float* smax, cons
   const float scale = alpha / (float)B;
   if (ncell > 0) {
     const size_t smem = (size_t)(2 * B + 64) * sizeof(float);
-    contrastive_cell_kernel<<<ncell, 128, smem, st>>>(B, cells, ncell, smax, inside_s, outside_s, margin, scale,
-                                                      partial, g_smax, g_inside_s, g_outside_s,
-                                                      g_smax ? root_part : nullptr);
+    launch_k(contrastive_cell_kernel, ncell, 128, smem, st, B, cells, ncell, smax, inside_s, outside_s, margin, scale, partial, g_smax, g_inside_s, g_outside_s, g_smax ? root_part : nullptr);
     CL_CHECK_LAUNCH("contrastive_cell_kernel");
   }
-  contrastive_finish_kernel<<<1, 128, 0, st>>>(B, cells, ncell, partial, scale, loss_out,
-                                               g_smax ? root_part : nullptr, g_inside_s);
+  launch_k(contrastive_finish_kernel, 1, 128, 0, st, B, cells, ncell, partial, scale, loss_out, g_smax ? root_part : nullptr, g_inside_s);
   CL_CHECK_LAUNCH("contrastive_finish_kernel");
   return CLIORA_OK;
 }
@@ -799,9 +799,9 @@ int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out
   if (B < 1 || n < 1) return CLIORA_ERR_BAD_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)(B + 64) * sizeof(float);
-  vg_loss_kernel<<<B, 128, smem, st>>>(B, n, wmax, alpha, scratch, g_wmax);
+  launch_k(vg_loss_kernel, B, 128, smem, st, B, n, wmax, alpha, scratch, g_wmax);
   CL_CHECK_LAUNCH("vg_loss_kernel");
-  sum_small_kernel<<<1, 128, 0, st>>>(scratch, B, loss_out);
+  launch_k(sum_small_kernel, 1, 128, 0, st, scratch, B, loss_out);
   CL_CHECK_LAUNCH("sum_small_kernel");
   return CLIORA_OK;
 }
@@ -813,7 +813,7 @@ int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float*
   const size_t smem = (size_t)num_cells(n) * sizeof(float);
   if (smem > 48 * 1024)
     CL_CUDA(cudaFuncSetAttribute(cky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cky_kernel<<<B, 64, smem, (cudaStream_t)stream>>>(B, n, split_scores, backptr, best);
+  launch_k(cky_kernel, B, 64, smem, (cudaStream_t)stream, B, n, split_scores, backptr, best);
   CL_CHECK_LAUNCH("cky_kernel");
   return CLIORA_OK;
 }
@@ -840,14 +840,14 @@ int cliora_matmul_nn(int M, int N, int K, const float* A, const float* Bm, float
 }
 
 void cliora_debug_set(int key, int value) {
+  if (key == 100) { g_pdl = value ? 1 : 0; return; }   // programmatic dependent launch on/off
   if (key >= 0 && key < 8) g_debug[key] = value;
 }
 
 int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_t stream) {
   if (!x || !out_pair) return CLIORA_ERR_NULL_POINTER;
   if (n <= 0) return CLIORA_OK;
-  tc::split_tf32_kernel<<<ceil_div(n, 256 * 4) < 1184 ? ceil_div(n, 256 * 4) : 1184, 256, 0, (cudaStream_t)stream>>>(
-      x, n, out_pair);
+  launch_k(tc::split_tf32_kernel, ceil_div(n, 256 * 4) < 1184 ? ceil_div(n, 256 * 4) : 1184, 256, 0, (cudaStream_t)stream, x, n, out_pair);
   CL_CHECK_LAUNCH("split_tf32_kernel");
   return CLIORA_OK;
 }

@@ -22,6 +22,7 @@ CL_D void fma4(float4& acc, float w, const float4& v) {
 // dynamic smem: (VL ? R*D : 0) + 8*N floats
 template <bool VL>
 __global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* s_obj = sm;
   float* s_pbase = sm + (VL ? a.R * a.D : 0);
@@ -170,6 +171,7 @@ __global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
 // dynamic smem: (VL ? R*D : 0) + 8*D + 32 floats
 template <bool VL>
 __global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g) {
+  pdl_prologue();
   const CellArgs& a = g.c;
   extern __shared__ __align__(16) float sm[];
   float* s_obj = sm;

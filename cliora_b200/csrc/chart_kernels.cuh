@@ -12,6 +12,7 @@ namespace cliora {
 __global__ void pack_weights_kernel(int D, int PI, const float* __restrict__ W1, const float* __restrict__ Wb,
                                     const float* __restrict__ oW1, const float* __restrict__ oWb,
                                     float* __restrict__ Wcat_in, float* __restrict__ Wcat_out) {
+  pdl_prologue();
   const int64_t total = (int64_t)(PI + 2) * D * D;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -68,6 +69,7 @@ CL_D void decode_row(const SplitArgs& a, int64_t m, int& b, int& first, int& sec
 
 template <bool OUTSIDE>
 __global__ __launch_bounds__(256) void split_build_kernel(const SplitArgs a) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t rows = (int64_t)a.B * a.L * a.N;
@@ -136,6 +138,7 @@ struct CellArgs {
 
 template <bool VL>
 __global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* s_a = sm;                 // [D]
   float* s_p = s_a + a.D;          // [N]
@@ -266,6 +269,7 @@ __global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
 // outside root: outside_h[:, root] = unit(root_vector), outside_s[:, root] = 0   (diora.py:337-356)
 __global__ void outside_root_kernel(int B, int D, int64_t C, const float* __restrict__ root,
                                     float* __restrict__ oh, float* __restrict__ os_, float* __restrict__ nrm_out) {
+  pdl_prologue();
   __shared__ float red[64];
   float ss = 0.f;
   for (int j = threadIdx.x; j < D; j += blockDim.x) ss += root[j] * root[j];
@@ -300,6 +304,7 @@ struct CellBwdArgs {
 // One block per cell.  Dynamic shared memory: (2D + 3R + 64) floats.
 template <bool VL>
 __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
+  pdl_prologue();
   const CellArgs& a = g.c;
   extern __shared__ __align__(16) float sm[];
   float* s_g = sm;                  // [D] working gradient
@@ -441,6 +446,7 @@ struct ScatterArgs {
 
 template <bool OUTSIDE>
 __global__ __launch_bounds__(256) void split_scatter_kernel(const ScatterArgs g) {
+  pdl_prologue();
   const SplitArgs& a = g.s;
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -475,6 +481,7 @@ __global__ __launch_bounds__(256) void split_scatter_kernel(const ScatterArgs g)
 __global__ void outside_root_bwd_kernel(int B, int D, int64_t C, const float* __restrict__ Gh_out,
                                         const float* __restrict__ oh, const float* __restrict__ nrm_out,
                                         float* __restrict__ g_root) {
+  pdl_prologue();
   __shared__ float red[64];
   const float nrm = nrm_out[C - 1];
   for (int j = threadIdx.x; j < D; j += blockDim.x) g_root[j] = 0.f;
@@ -496,6 +503,7 @@ template <int RMAX>
 __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, const float* __restrict__ GA2,
                                                        const float* __restrict__ q, const float* __restrict__ coef,
                                                        float* __restrict__ g_obj, int accumulate) {
+  pdl_prologue();
   constexpr int RQ = (RMAX + 3) / 4;   // regions per threadIdx.y
   constexpr int CH = 16;               // cells per chunk
   const int b = blockIdx.y;
@@ -548,6 +556,7 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
 // column sums: dst[j] (+)= sum_r src[r*ld + j].  Two deterministic stages through `part` [S, cols].
 __global__ void colsum_stage1_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols,
                                      float* __restrict__ part) {
+  pdl_prologue();
   __shared__ float s[8][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int64_t chunk = (rows + gridDim.y - 1) / gridDim.y;
@@ -566,6 +575,7 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ src, int64_t ld, 
 }
 __global__ void colsum_stage2_kernel(const float* __restrict__ part, int S, int cols, float* __restrict__ dst,
                                      int accumulate) {
+  pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   float t = 0.f;

@@ -11,6 +11,7 @@ namespace cliora {
 // Dynamic smem: cells floats.
 __global__ __launch_bounds__(64) void cky_kernel(int B, int n, const float* __restrict__ E,
                                                  int32_t* __restrict__ backptr, float* __restrict__ best_out) {
+  pdl_prologue();
   extern __shared__ float s_best[];
   const int b = blockIdx.x;
   const int C = (int)num_cells(n);

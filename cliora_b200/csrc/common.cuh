@@ -103,6 +103,15 @@ CL_D void red_add4(float* p, float4 v) {
                : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// First statement of every kernel: let the next kernel in the stream get scheduled while this one runs, then
+// wait until the previous kernel has completed and flushed its memory.  All global accesses come after the
+// wait, so semantics equal plain stream order; what overlaps is launch latency / block scheduling.
+CL_D void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- host-side error plumbing ----
 struct LaunchCtx {
   cudaStream_t stream;
@@ -110,6 +119,7 @@ struct LaunchCtx {
 };
 extern thread_local char g_last_cuda_error[256];
 extern long long g_launch_count;
+extern int g_pdl;   // 1: launch kernels with the programmatic-stream-serialization attribute
 
 inline int record_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
@@ -139,6 +149,22 @@ inline int record_cuda_error(cudaError_t e, const char* what) {
   } while (0)
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// kernel launch with the optional PDL attribute (replaces the triple-chevron syntax everywhere)
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // errors are picked up by CL_CHECK_LAUNCH
+}
 
 // ---- optional per-launch CUDA-event profiler (bench.py's roofline pass) ----
 struct ProfEntry {

@@ -38,6 +38,7 @@ constexpr int kBK = 16;
 
 template <int TM, bool A_KMAJOR, bool B_KMAJOR>
 __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
+  pdl_prologue();
   constexpr int BM = 16 * TM;
   constexpr int A_LD = BM + 4;
   constexpr int B_LD = kBN + 4;
@@ -305,6 +306,7 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
 // C[i*ldc + j] (+)= sum_z part[z][i][j]
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int Mo,
                                      int No, float* __restrict__ C, int64_t ldc, int accumulate) {
+  pdl_prologue();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)Mo * No) return;
   const int i = (int)(idx / No), j = (int)(idx % No);
@@ -344,11 +346,11 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = 
     }
   }
   if (nt) {
-    if (big) gemm_simt_kernel<8, false, false><<<grid, 256, 0, st>>>(p);
-    else gemm_simt_kernel<4, false, false><<<grid, 256, 0, st>>>(p);
+    if (big) launch_k(gemm_simt_kernel<8, false, false>, grid, 256, 0, st, p);
+    else launch_k(gemm_simt_kernel<4, false, false>, grid, 256, 0, st, p);
   } else {
-    if (big) gemm_simt_kernel<8, false, true><<<grid, 256, 0, st>>>(p);
-    else gemm_simt_kernel<4, false, true><<<grid, 256, 0, st>>>(p);
+    if (big) launch_k(gemm_simt_kernel<8, false, true>, grid, 256, 0, st, p);
+    else launch_k(gemm_simt_kernel<4, false, true>, grid, 256, 0, st, p);
   }
   CL_CHECK_LAUNCH("gemm_simt_kernel");
   return CLIORA_OK;
@@ -391,11 +393,10 @@ inline int launch_gemm_tn(cudaStream_t st, int rows, int Ka, int Kb, const float
   p.vec_w = aligned16(B) && (ldb % 4 == 0);
   p.vec_c = (Kb % 4 == 0) && aligned16(scratch);
   dim3 grid(ceil_div(Kb, kBN), ceil_div(Ka, 64), splits);
-  gemm_simt_kernel<4, true, true><<<grid, 256, 0, st>>>(p);
+  launch_k(gemm_simt_kernel<4, true, true>, grid, 256, 0, st, p);
   CL_CHECK_LAUNCH("gemm_simt_kernel<tn>");
   const int64_t total = (int64_t)Ka * Kb;
-  splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(scratch, splits, p.split_stride, Ka, Kb, C, ldc,
-                                                              accumulate);
+  launch_k(splitk_reduce_kernel, ceil_div(total, 256), 256, 0, st, scratch, splits, p.split_stride, Ka, Kb, C, ldc, accumulate);
   CL_CHECK_LAUNCH("splitk_reduce_kernel");
   return CLIORA_OK;
 }

@@ -133,6 +133,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcEpilogue ep, int a_row0, int M, int N, int K, int mode) {
+  pdl_prologue();
   using S = TcSmem<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -361,6 +362,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   float* __restrict__ partial, int rows, int Ka, int Kb, int rows_per_split, int mode) {
+  pdl_prologue();
   using S = TnSmem<BLOCK_N, STAGES>;
   static_assert(BLOCK_N % 32 == 0 && 2 * BLOCK_N <= 512, "BLOCK_N");
   extern __shared__ uint8_t smem_raw[];
@@ -491,6 +493,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // x -> split pair (hi at out, lo at out + n)
 __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     uint32_t h;
@@ -503,6 +506,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float*
 // src[rows, cols] (row pitch ld) -> dense split pair [2, rows, cols]
 __global__ void split_tf32_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld,
                                       float* __restrict__ out) {
+  pdl_prologue();
   const int64_t n4 = rows * (cols / 4);
   const int64_t part = rows * (int64_t)cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -519,6 +523,7 @@ __global__ void split_tf32_rows_kernel(const float* __restrict__ src, int64_t ro
 // W[rows, cols] -> split pair of W^T ([2, cols, rows])
 __global__ void split_tf32_transpose_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
                                             float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -614,7 +619,7 @@ inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, 
   }
   dim3 grid(ceil_div(N, BLOCK_N), ceil_div(M, kBlockM));
   ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
-  tc_gemm_nt_kernel<BLOCK_N, STAGES><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, ep, a_row0, M, N, K, mode);
+  launch_k(tc_gemm_nt_kernel<BLOCK_N, STAGES>, grid, kThreads, S::TOTAL, st, tmA, tmB, ep, a_row0, M, N, K, mode);
   CL_CHECK_LAUNCH("tc_gemm_nt_kernel");
   return CLIORA_OK;
 }
@@ -676,10 +681,10 @@ inline int launch_tc_gemm_tn(cudaStream_t st, const PairRef& A, const PairRef& B
   if (per < kTnBlockK) per = kTnBlockK;
   dim3 grid(ceil_div(Kb, kTnBlockN), ceil_div(Ka, kBlockM), splits);
   ProfScope prof(st, tag, 2.0 * rows * Ka * Kb, 4.0 * ((double)rows * (Ka + Kb) * 2 + (double)Ka * Kb));
-  tc_gemm_tn_kernel<kTnBlockN, kTnStages><<<grid, kThreads, S::TOTAL, st>>>(tmA, tmB, scratch, rows, Ka, Kb, per, mode);
+  launch_k(tc_gemm_tn_kernel<kTnBlockN, kTnStages>, grid, kThreads, S::TOTAL, st, tmA, tmB, scratch, rows, Ka, Kb, per, mode);
   CL_CHECK_LAUNCH("tc_gemm_tn_kernel");
   const int64_t total = (int64_t)Ka * Kb;
-  splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(scratch, splits, total, Ka, Kb, C, ldc, accumulate);
+  launch_k(splitk_reduce_kernel, ceil_div(total, 256), 256, 0, st, scratch, splits, total, Ka, Kb, C, ldc, accumulate);
   CL_CHECK_LAUNCH("splitk_reduce_kernel");
   return CLIORA_OK;
 }
