@@ -20,7 +20,7 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 int g_pdl = env_int("CLIORA_PDL", 0);
-int g_debug[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = 1: block-per-cell VL kernels
+int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -307,7 +307,7 @@ template <bool VL>
 static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
   const double rows = (double)a.B * a.L * a.N;
   ProfScope prof(c.st, "cell_aggregate", 2.0 * rows * a.D, 4.0 * (rows * (a.D + 2) + 2.0 * a.B * a.L * a.D));
-  if (VL && a.D <= 128 * kColT && g_debug[3] == 0) {
+  if (VL && a.D <= 128 * kColT && (g_debug[3] & 1) == 0) {
     // warp per cell, 8 cells of one sentence per CTA, the image's regions staged once in shared memory
     const size_t smem = ((size_t)a.R * a.D + (size_t)kCellsPerCta * a.N) * sizeof(float);
     static size_t configured = 0;
@@ -330,7 +330,7 @@ template <bool VL>
 static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
   const double rows = (double)g.c.B * g.c.L * g.c.N;
   ProfScope prof(c.st, "cell_bwd", 4.0 * rows * g.c.D, 4.0 * (2.0 * rows * (g.c.D + 2) + 3.0 * g.c.B * g.c.L * g.c.D));
-  if (VL && g.c.D <= 128 * kColT && g_debug[3] == 0) {
+  if (VL && g.c.D <= 128 * kColT && (g_debug[3] & 2) == 0) {
     const size_t smem = ((size_t)g.c.R * g.c.D + (size_t)kCellsPerCta * g.c.D + 32) * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {

@@ -208,15 +208,17 @@ def test_simt_fallback_gemm_path_matches_too():
         _lib.lib().cliora_debug_set(1, 0)
 
 
-def test_block_per_cell_vl_kernels_match_too(golden):
-    """The original block-per-cell attention kernels (used when D > 512) stay parity-green."""
+@pytest.mark.parametrize('variant', [0, 3])
+def test_all_vl_cell_kernel_variants_match(golden, variant):
+    """Default = warp-per-cell forward + block-per-cell backward (fastest measured); the all-warp (0) and
+    all-block (3, also the D > 512 fallback) variants stay parity-green too."""
     from cliora_b200 import _lib
-    _lib.lib().cliora_debug_set(3, 1)
+    _lib.lib().cliora_debug_set(3, variant)
     try:
         test_cliora_chart_vs_golden(golden, 'cliora_b4_n9_d48_r36_train.pt')
         test_chart_vs_oracle_live(4, 10, 400, 36, True)
     finally:
-        _lib.lib().cliora_debug_set(3, 0)
+        _lib.lib().cliora_debug_set(3, 2)
 
 
 def test_tf32_single_pass_mode_has_its_own_tolerance():
