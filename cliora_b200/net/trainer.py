@@ -264,11 +264,42 @@ class Trainer(object):
                 self._optimizer_update()
         return self
 
+    def prefetch(self, batch_map):
+        """Start the host->device copy of a (pinned) batch on a side stream into one of two staging slots and
+        return a handle for ``step_graphed``; the copy overlaps the step that is currently running."""
+        dev = next(self.net.parameters()).device
+        if not hasattr(self, '_stage'):
+            self._stage = [{k: torch.empty_like(v) for k, v in self._static.items() if torch.is_tensor(v)}
+                           for _ in range(2)]
+            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._slot = 0
+            for e in self._stage_free:
+                e.record(torch.cuda.current_stream(dev))
+        slot = self._slot
+        self._slot ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[slot])     # the step that last read this slot is done
+            for k, dst in self._stage[slot].items():
+                dst.copy_(batch_map[k], non_blocking=True)
+            self._stage_ev[slot].record(self._copy_stream)
+        return ('staged', slot)
+
     def step_graphed(self, batch_map):
-        """Replay the captured step on a new batch of the captured shape; returns the (device) total loss."""
-        for k, v in batch_map.items():
-            if torch.is_tensor(v):
-                self._static[k].copy_(v, non_blocking=True)
+        """Replay the captured step on a new batch of the captured shape; returns the (device) total loss.
+        ``batch_map`` is a dict of tensors (host or device) or a handle from ``prefetch``."""
+        if isinstance(batch_map, tuple) and batch_map[0] == 'staged':
+            slot = batch_map[1]
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._stage_ev[slot])
+            for k, src in self._stage[slot].items():
+                self._static[k].copy_(src, non_blocking=True)        # device->device, a few microseconds
+            self._stage_free[slot].record(cur)
+        else:
+            for k, v in batch_map.items():
+                if torch.is_tensor(v):
+                    self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
         if self._graph_opt is not None:
             self.grad_sync()          # one flat fp32 all-reduce over NVLink (NCCL), then 1/N

@@ -105,3 +105,28 @@ def test_split_graph_path_used_for_data_parallel():
     assert len(calls) - n0 == len(batches)
     for x, y in zip(la, lb):
         assert abs(x - y) <= 2e-4 * abs(x), (la, lb)
+
+
+def test_prefetched_batches_give_same_losses():
+    """Trainer.prefetch (side-stream H2D into staging slots) feeds step_graphed the right batch every time."""
+    batches = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in _batch(seed=i).items()} for i in range(5)]
+    a, b = _trainer(), _trainer()
+    for tr in (a, b):
+        tr.net.diora.atten_head.dropout.p = 0.0
+    sd = {k: v.clone() for k, v in a.net.state_dict().items()}
+    for tr in (a, b):
+        tr.capture(batches[0], warmup=1)
+        tr.net.load_state_dict(sd)
+        for st in tr.optimizer.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+    la = [a.step_graphed(x).item() for x in batches]
+    h = b.prefetch(batches[0])
+    lb = []
+    for i in range(len(batches)):
+        nxt = b.prefetch(batches[(i + 1) % len(batches)])
+        lb.append(b.step_graphed(h).item())
+        h = nxt
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-4 * abs(x), (la, lb)
