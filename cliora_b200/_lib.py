@@ -122,6 +122,8 @@ def _declare(lib):
     lib.cliora_tc_matmul_tn_scratch_floats.argtypes = [c_int, c_int, c_int]
     lib.cliora_tc_matmul_tn.argtypes = [c_int, c_int, c_int, vp, vp, vp, c_int, vp, st]
     lib.cliora_tc_matmul_tn.restype = c_int
+    lib.cliora_tc_atten_max_fwd.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, st]
+    lib.cliora_tc_atten_max_fwd.restype = c_int
     lib.cliora_debug_set.argtypes = [c_int, c_int]
     lib.cliora_debug_set.restype = None
     lib.cliora_profile_start.restype = None
@@ -142,7 +144,7 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_atten_max_bwd', 'cliora_contrastive_loss', 'cliora_vg_loss', 'cliora_cky', 'cliora_linear',
            'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
            'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set',
-           'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn']
+           'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn', 'cliora_tc_atten_max_fwd']
 
 
 def lib():

@@ -865,6 +865,23 @@ int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pa
   return tc::launch_tc_gemm_nt((cudaStream_t)stream, A, 0, W, M, N, K, ep, "tc_gemm_linear", g_debug[0], g_debug[2]);
 }
 
+int cliora_tc_atten_max_fwd(int B, int ncell, int D, int R, const float* h_pair, const float* obj_pair, float* smax,
+                            int32_t* amax, cliora_stream_t stream) {
+  if (!h_pair || !obj_pair || !smax || !amax) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || ncell < 0 || D < 32 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
+  if (ncell == 0) return CLIORA_OK;
+  const int64_t M = (int64_t)B * ncell, N = (int64_t)B * R;
+  tc::PairRef A{h_pair, M, D, M * D};
+  tc::PairRef W{obj_pair, N, D, N * D};
+  tc::TcEpilogue ep{};
+  ep.cmap = dense_rows();
+  ep.gmax = smax; ep.gargmax = amax;
+  ep.R = R; ep.ncell = ncell; ep.B_img = B;
+  ep.n_stride = (tc::kTcNarrowN / R) * R;     // whole images per 80-column tile
+  return tc::launch_tc_gemm_nt_cfg<tc::kTcNarrowN, tc::kTcNarrowStages>((cudaStream_t)stream, A, 0, W, (int)M, (int)N, D,
+                                                                        ep, "tc_atten_max", 2);
+}
+
 int64_t cliora_tc_matmul_tn_scratch_floats(int M, int Ka, int Kb) { return tc::tn_tc_scratch_floats(M, Ka, Kb); }
 
 int cliora_tc_matmul_tn(int M, int Ka, int Kb, const float* A_pair, const float* B_pair, float* C, int accumulate,

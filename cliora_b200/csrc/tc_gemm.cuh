@@ -115,6 +115,13 @@ struct TcEpilogue {
   float* C_lo;          // optional: also emit the split pair of the result (C gets hi, C_lo gets lo); or null
   int act;              // 0 none, 1 relu, 2 tanh
   int accumulate;       // C += result
+  // --- group-max mode (span-region alignment, cliora.py:457 + trainer.py:101): columns are B_img images x R
+  // regions; instead of storing C the epilogue writes, per row (a, cell) and image c, the max over that
+  // image's R columns and its argmax (first max).  Tiles advance by whole images (n_stride = imgs * R).
+  float* gmax;          // [B_sent, B_img, ncell] or null
+  int32_t* gargmax;
+  int R, ncell, B_img;
+  int n_stride;         // columns advanced per blockIdx.x (0: BLOCK_N)
 };
 
 CL_HD constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -143,7 +150,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kBlockM, n0 = blockIdx.x * BLOCK_N;
+  const int m0 = blockIdx.y * kBlockM, n0 = blockIdx.x * (ep.n_stride > 0 ? ep.n_stride : BLOCK_N);
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   // columns this CTA really owns, rounded up to the UMMA granularity (N % 16 == 0 for M = 128)
   const int n_cur = min(BLOCK_N, ((N - n0 + 15) / 16) * 16);
@@ -246,6 +253,40 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* crow = row_ok ? ep.C + map_row(ep.cmap, r) * ep.ldc : nullptr;
     float* clo = (row_ok && ep.C_lo) ? ep.C_lo + map_row(ep.cmap, r) * ep.ldc : nullptr;
     const float* mrow = (row_ok && ep.mask) ? ep.mask + (int64_t)r * ep.ldm : nullptr;
+    if (ep.gmax != nullptr) {
+      // running max / argmax over each image's R columns; this thread owns the whole row of the tile
+      const int imgs = ep.n_stride / ep.R;
+      const int img0 = n0 / ep.R;
+      float best = -INFINITY;
+      int bi = 0, gi = 0;   // argmax within the group, current group index
+      const int a = row_ok ? r / ep.ncell : 0, cell = row_ok ? r % ep.ncell : 0;
+#pragma unroll 1
+      for (int c = 0; c < n_cur; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if (mode == 2) {
+          float x[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), x);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += x[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = c + i;              // column within the tile
+          const int g = col / ep.R;           // image within the tile
+          if (g >= imgs) break;
+          if (g != gi) { best = -INFINITY; bi = 0; gi = g; }
+          const int rr = col - g * ep.R;
+          if (v[i] > best) { best = v[i]; bi = rr; }
+          if (rr == ep.R - 1 && row_ok && img0 + g < ep.B_img) {
+            const int64_t o = ((int64_t)a * ep.B_img + img0 + g) * ep.ncell + cell;
+            ep.gmax[o] = best;
+            ep.gargmax[o] = bi;
+          }
+        }
+      }
+      tcgen05_fence_before();
+    } else
 #pragma unroll 1
     for (int c = 0; c < n_cur; c += 16) {
       float v[16];
@@ -617,7 +658,7 @@ inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, 
                                  S::TOTAL));
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, BLOCK_N), ceil_div(M, kBlockM));
+  dim3 grid(ceil_div(N, ep.n_stride > 0 ? ep.n_stride : BLOCK_N), ceil_div(M, kBlockM));
   ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
   launch_k(tc_gemm_nt_kernel<BLOCK_N, STAGES>, grid, kThreads, S::TOTAL, st, tmA, tmB, ep, a_row0, M, N, K, mode);
   CL_CHECK_LAUNCH("tc_gemm_nt_kernel");

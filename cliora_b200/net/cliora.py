@@ -68,9 +68,19 @@ class AttenMax(torch.autograd.Function):
         R = obj.shape[1]
         smax = torch.empty(B, B, ncell, device=h.device, dtype=torch.float32)
         amax = torch.empty(B, B, ncell, device=h.device, dtype=torch.int32)
+        L = _lib.lib()
         with torch.cuda.device(h.device):
-            check(_lib.lib().cliora_atten_max_fwd(B, ncell, D, R, ptr(h), ncell, ptr(obj), ptr(smax), ptr(amax),
-                                                  _lib.stream()), 'cliora_atten_max_fwd')
+            if D >= 32 and D % 4 == 0 and 2.0 * B * ncell * B * R * D >= 2e8:
+                # tcgen05 3xTF32 GEMM with the max-over-regions epilogue (operands re-written as split pairs)
+                hp = torch.empty(2, B * ncell, D, device=h.device, dtype=torch.float32)
+                op = torch.empty(2, B * R, D, device=h.device, dtype=torch.float32)
+                check(L.cliora_split_tf32(ptr(h), h.numel(), ptr(hp), _lib.stream()), 'cliora_split_tf32')
+                check(L.cliora_split_tf32(ptr(obj), obj.numel(), ptr(op), _lib.stream()), 'cliora_split_tf32')
+                check(L.cliora_tc_atten_max_fwd(B, ncell, D, R, ptr(hp), ptr(op), ptr(smax), ptr(amax), _lib.stream()),
+                      'cliora_tc_atten_max_fwd')
+            else:
+                check(L.cliora_atten_max_fwd(B, ncell, D, R, ptr(h), ncell, ptr(obj), ptr(smax), ptr(amax),
+                                             _lib.stream()), 'cliora_atten_max_fwd')
         ctx.save_for_backward(h, obj, amax)
         ctx.mark_non_differentiable(amax)
         return smax, amax

@@ -249,6 +249,11 @@ void cliora_debug_set(int key, int value);
 int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pair, const float* bias, int act,
                      float* C, cliora_stream_t stream);
 
+/* cliora_atten_max_fwd on tensor cores: the [B*ncell, D] x [B*R, D]^T alignment GEMM with the max-over-regions
+ * (+ argmax) epilogue, operands as split pairs [2, B*ncell, D] and [2, B*R, D].  D >= 32, R <= 64. */
+int cliora_tc_atten_max_fwd(int B, int ncell, int D, int R, const float* h_pair, const float* obj_pair, float* smax,
+                            int32_t* amax, cliora_stream_t stream);
+
 /* C[Ka,Kb] (+)= A[M,Ka]^T B[M,Kb] on tensor cores (MN-major UMMA, split-K); Ka, Kb multiples of 4. */
 int64_t cliora_tc_matmul_tn_scratch_floats(int M, int Ka, int Kb);
 int cliora_tc_matmul_tn(int M, int Ka, int Kb, const float* A_pair, const float* B_pair, float* C, int accumulate,

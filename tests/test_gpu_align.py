@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-@pytest.mark.parametrize('B,ncell,D,R', [(3, 7, 32, 5), (8, 105, 400, 36), (5, 20, 48, 64)])
+@pytest.mark.parametrize('B,ncell,D,R', [(3, 7, 32, 5), (8, 105, 400, 36), (5, 20, 48, 64), (32, 105, 400, 36),
+                                         (9, 50, 400, 17)])   # the last two take the tcgen05 path
 def test_atten_max_fwd_bwd(B, ncell, D, R):
     from cliora_b200.net.cliora import AttenMax, AttenScores
     g = torch.Generator().manual_seed(B * ncell)
