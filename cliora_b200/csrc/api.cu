@@ -7,6 +7,7 @@
 #include "chart_kernels.cuh"
 #include "cell_warp_kernels.cuh"
 #include "cky_kernels.cuh"
+#include "recon_kernels.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "tc_gemm.cuh"
@@ -603,7 +604,8 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
   }
   if (n > 1) CL_TRY(cellgrad_level(c, n - 1, bws + c.L.GP_out, 2 * D, Wcat_out, bws + c.L.Gh_out));
   if (grads->root) {
-    launch_k(outside_root_bwd_kernel, 1, 128, 0, c.st, B, D, c.C, bws + c.L.Gh_out, outside_h, ws + c.L.nrm_out, grads->root);
+    CL_CUDA(cudaMemsetAsync(grads->root, 0, D * sizeof(float), c.st));
+    launch_k(outside_root_bwd_kernel, B, 128, 0, c.st, B, D, c.C, bws + c.L.Gh_out, outside_h, ws + c.L.nrm_out, grads->root);
     CL_CHECK_LAUNCH("outside_root_bwd_kernel");
   }
   // weight gradients contributed by the outside pass
@@ -803,6 +805,27 @@ int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out
   CL_CHECK_LAUNCH("vg_loss_kernel");
   launch_k(sum_small_kernel, 1, 128, 0, st, scratch, B, loss_out);
   CL_CHECK_LAUNCH("sum_small_kernel");
+  return CLIORA_OK;
+}
+
+int cliora_recon_ce_fwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg, float* rowloss,
+                        float* probs, cliora_stream_t stream) {
+  if (!cell || !pos || !neg || !rowloss || !probs) return CLIORA_ERR_NULL_POINTER;
+  if (rows < 1 || D < 4 || D % 4 || D > 128 * kColT || K < 1 || K > 127) return CLIORA_ERR_BAD_SHAPE;
+  launch_k(recon_ce_fwd_kernel, ceil_div(rows, 8), 256, (size_t)kNegChunk * D * sizeof(float), (cudaStream_t)stream, rows,
+           D, K, cell, pos, neg, rowloss, probs);
+  CL_CHECK_LAUNCH("recon_ce_fwd_kernel");
+  return CLIORA_OK;
+}
+
+int cliora_recon_ce_bwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg,
+                        const float* probs, const float* g_loss, float* g_scores, float* g_cell, float* g_pos,
+                        cliora_stream_t stream) {
+  if (!cell || !pos || !neg || !probs || !g_loss || !g_scores || !g_cell || !g_pos) return CLIORA_ERR_NULL_POINTER;
+  if (rows < 1 || D < 4 || D % 4 || D > 128 * kColT || K < 1 || K > 127) return CLIORA_ERR_BAD_SHAPE;
+  launch_k(recon_ce_bwd_kernel, ceil_div(rows, 8), 256, (size_t)kNegChunk * D * sizeof(float), (cudaStream_t)stream, rows,
+           D, K, cell, pos, neg, probs, g_loss, 1.f / (float)rows, g_scores, g_cell, g_pos);
+  CL_CHECK_LAUNCH("recon_ce_bwd_kernel");
   return CLIORA_OK;
 }
 

@@ -477,23 +477,21 @@ __global__ __launch_bounds__(256) void split_scatter_kernel(const ScatterArgs g)
   }
 }
 
-// g_root = sum_b unit_bwd(Gh_out[b, root], h_root, nrm_root)
+// g_root += unit_bwd(Gh_out[b, root], h_root, nrm_root)   one block per sentence b; g_root zero-filled by the caller
 __global__ void outside_root_bwd_kernel(int B, int D, int64_t C, const float* __restrict__ Gh_out,
                                         const float* __restrict__ oh, const float* __restrict__ nrm_out,
                                         float* __restrict__ g_root) {
   pdl_prologue();
   __shared__ float red[64];
-  const float nrm = nrm_out[C - 1];
-  for (int j = threadIdx.x; j < D; j += blockDim.x) g_root[j] = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float* gh = Gh_out + ((int64_t)b * C + C - 1) * D;
-    const float* h = oh + ((int64_t)b * C + C - 1) * D;
-    float d = 0.f;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) d = fmaf(h[j], gh[j], d);
-    d = block_sum(d, red);
-    const float coef = unit_bwd_coef(nrm, d);
-    for (int j = threadIdx.x; j < D; j += blockDim.x) g_root[j] += (gh[j] - h[j] * coef) / nrm;
-  }
+  const int b = blockIdx.x;
+  const float nrm = nrm_out[(int64_t)b * C + C - 1];
+  const float* gh = Gh_out + ((int64_t)b * C + C - 1) * D;
+  const float* h = oh + ((int64_t)b * C + C - 1) * D;
+  float d = 0.f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) d = fmaf(h[j], gh[j], d);
+  d = block_sum(d, red);
+  const float coef = unit_bwd_coef(nrm, d);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) atomicAdd(g_root + j, (gh[j] - h[j] * coef) / nrm);
 }
 
 // g_obj[b,r,:] = sum_c patt[b,c,r] ga2[b,c,:] + g_logit[b,c,r] q[b,c,:]     grid (ceil(D/32), B), block (32, 4)

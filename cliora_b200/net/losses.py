@@ -62,6 +62,46 @@ class VGLossFn(torch.autograd.Function):
         return g * g_w, None
 
 
+class ReconCEFn(torch.autograd.Function):
+    """mean over words of CE([pos.cell, neg_1.cell, ..., neg_K.cell], target 0)  (trainer.py:46-78), fused."""
+
+    @staticmethod
+    def forward(ctx, cell, pos, neg):
+        cell = cell.reshape(-1, cell.shape[-1]).contiguous().float()
+        pos = pos.reshape(-1, pos.shape[-1]).contiguous().float()
+        neg = neg.reshape(-1, neg.shape[-1]).contiguous().float()
+        rows, D = cell.shape
+        K = neg.shape[0]
+        rowloss = torch.empty(rows, device=cell.device, dtype=torch.float32)
+        probs = torch.empty(rows, K + 1, device=cell.device, dtype=torch.float32)
+        with torch.cuda.device(cell.device):
+            check(_lib.lib().cliora_recon_ce_fwd(rows, D, K, ptr(cell), ptr(pos), ptr(neg), ptr(rowloss), ptr(probs),
+                                                 _lib.stream()), 'cliora_recon_ce_fwd')
+        ctx.save_for_backward(cell, pos, neg, probs)
+        return rowloss.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        cell, pos, neg, probs = ctx.saved_tensors
+        L = _lib.lib()
+        rows, D = cell.shape
+        K = neg.shape[0]
+        g = g.reshape(1).contiguous().float()
+        gs = torch.empty(rows, K + 1, device=cell.device, dtype=torch.float32)
+        g_cell, g_pos = torch.empty_like(cell), torch.empty_like(pos)
+        g_all = torch.empty(K + 1, D, device=cell.device, dtype=torch.float32)
+        scratch = torch.empty(int(L.cliora_matmul_tn_scratch_floats(rows, K + 1, D)) + 8, device=cell.device,
+                              dtype=torch.float32)
+        with torch.cuda.device(cell.device):
+            st = _lib.stream()
+            check(L.cliora_recon_ce_bwd(rows, D, K, ptr(cell), ptr(pos), ptr(neg), ptr(probs), ptr(g), ptr(gs),
+                                        ptr(g_cell), ptr(g_pos), st), 'cliora_recon_ce_bwd')
+            # gradient wrt the negatives: rows 1..K of g_scores^T cell (row 0 belongs to the per-word positives)
+            check(L.cliora_matmul_tn(rows, K + 1, D, ptr(gs), ptr(cell), ptr(g_all), 0, ptr(scratch), st),
+                  'cliora_matmul_tn')
+        return g_cell, g_pos, g_all[1:]
+
+
 def _pair(t):
     """Split pair [2, rows, cols] (tf32-rounded part, exact remainder) of a contiguous fp32 matrix."""
     out = torch.empty((2,) + tuple(t.shape), device=t.device, dtype=torch.float32)

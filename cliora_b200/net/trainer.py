@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
-from .losses import ContrastiveFn, VGLossFn, linear
+from .losses import ContrastiveFn, ReconCEFn, VGLossFn, linear
 
 
 class ImageEncoder(nn.Module):
@@ -79,11 +79,14 @@ class ReconstructionSoftmaxLoss(nn.Module):
         cell = diora.outside_h[:, :n]                                   # [B,n,D]
         pos = linear(self.embeddings(sentences), self.mat)             # [B,n,D]
         neg = linear(self.embeddings(neg_samples), self.mat)           # [K,D]
-        xp = (pos * cell).sum(-1, keepdim=True)
-        xn = linear(cell, neg)                                         # [B,n,K]
-        score = torch.cat([xp, xn], 2).view(B * n, -1)
-        target = torch.zeros(B * n, dtype=torch.int64, device=score.device)
-        loss = nn.functional.cross_entropy(score, target)
+        D, K = cell.shape[-1], neg.shape[0]
+        if D % 4 == 0 and D <= 512 and K <= 127:
+            loss = ReconCEFn.apply(cell.reshape(B * n, D), pos.reshape(B * n, D), neg.reshape(K, D))   # fused kernel
+        else:   # shapes outside the fused kernel's range: same maths on the library GEMM + torch CE
+            xp = (pos * cell).sum(-1, keepdim=True)
+            xn = linear(cell, neg.reshape(K, D))
+            score = torch.cat([xp, xn], 2).view(B * n, -1)
+            loss = nn.functional.cross_entropy(score, torch.zeros(B * n, dtype=torch.int64, device=score.device))
         return loss, dict(reconstruction_softmax_loss=loss)
 
 

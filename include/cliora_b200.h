@@ -214,6 +214,18 @@ int cliora_contrastive_loss(int B, int cells, int ncell, const float* smax, cons
 int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out, float* g_wmax,
                    float* scratch, cliora_stream_t stream);
 
+/* ReconstructionSoftmaxLoss.forward (trainer.py:46-78), the 1+K-way scoring and cross-entropy fused:
+ *   rows = B*n words; cell [rows, D] = outside_h leaves; pos [rows, D], neg [K, D] = projected embeddings
+ *   rowloss[row] = logsumexp(s) - s_0 with s_0 = pos.cell, s_{1+e} = neg[e].cell; probs [rows, K+1] = softmax(s)
+ * The loss is mean(rowloss).  Backward: g_scores [rows, K+1] = (probs - onehot_0) g_loss / rows,
+ * g_cell / g_pos [rows, D]; the gradient wrt neg is g_scores[:, 1:]^T cell (cliora_matmul_tn).
+ * D <= 512, K <= 127. */
+int cliora_recon_ce_fwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg, float* rowloss,
+                        float* probs, cliora_stream_t stream);
+int cliora_recon_ce_bwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg,
+                        const float* probs, const float* g_loss, float* g_scores, float* g_cell, float* g_pos,
+                        cliora_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * CKY decode (replaces ParsePredictor.batched_cky, cliora/analysis/cky.py:31-99,
  * fed by the hook of cliora/analysis/utils.py:78-95).

@@ -102,3 +102,30 @@ def test_cliora_losses_and_grads_vs_golden(golden, name):
     mine = _grads(m)
     for k, gref in blob['grads'].items():
         assert rel_err(mine[k], gref) < TOL, k
+
+
+@pytest.mark.parametrize('B,n,D,K', [(3, 5, 32, 7), (32, 20, 400, 100), (2, 1, 48, 33)])
+def test_fused_reconstruction_ce(B, n, D, K):
+    """recon_ce kernels == the oracle's reconstruction_loss (trainer.py:46-78), loss and all three gradients."""
+    from oracle import cliora_oracle as O
+    from cliora_b200.net.losses import ReconCEFn
+    g = torch.Generator().manual_seed(B * n + K)
+    V, E = 50 + K, 24
+    emb = torch.randn(V, E, generator=g)
+    mat = (0.2 * torch.randn(D, E, generator=g)).requires_grad_()
+    sent = torch.randint(0, V, (B, n), generator=g)
+    neg = torch.randperm(V, generator=g)[:K]
+    C = n * (n + 1) // 2
+    oh = torch.randn(B, C, D, generator=g).requires_grad_()
+    ref = O.reconstruction_loss(emb, mat, sent, neg, oh)
+    ref.backward()
+    cell = oh.detach()[:, :n].cuda().requires_grad_()
+    pos = (emb[sent] @ mat.detach().t()).cuda().requires_grad_()
+    ngv = (emb[neg] @ mat.detach().t()).cuda().requires_grad_()
+    loss = ReconCEFn.apply(cell.reshape(B * n, D), pos.reshape(B * n, D), ngv)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    (loss * 1.7).backward()
+    assert rel_err(cell.grad, 1.7 * oh.grad[:, :n]) < 1e-5
+    # chain the pos / neg grads back to `mat` to compare with the oracle's gradient of the projection matrix
+    gmat = pos.grad.reshape(B * n, D).cpu().t() @ emb[sent].reshape(B * n, E) + ngv.grad.cpu().t() @ emb[neg]
+    assert rel_err(gmat, 1.7 * mat.grad) < 1e-5
