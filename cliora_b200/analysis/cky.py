@@ -40,6 +40,20 @@ def tree_from_backpointers(row, n):
     return rec(n - 1, 0)
 
 
+def spans(diora):
+    """int32 [B, n-1, 2]: (start, end) inclusive spans of every constituent of the decoded trees, computed on
+    the device from the backpointer table (the reference goes tree -> str -> actions -> spans on the host)."""
+    bp, _ = backpointers(diora)
+    B, n = diora._run.B, diora._run.n
+    if n < 2:
+        return torch.empty(B, 0, 2, device=bp.device, dtype=torch.int32)
+    out = torch.empty(B, n - 1, 2, device=bp.device, dtype=torch.int32)
+    scratch = torch.empty(3 * B * n, device=bp.device, dtype=torch.int32)
+    with torch.cuda.device(bp.device):
+        check(_lib.lib().cliora_tree_spans(B, n, ptr(bp), ptr(out), ptr(scratch), _lib.stream()), 'cliora_tree_spans')
+    return out
+
+
 class ParsePredictor(object):
     def __init__(self, net):
         self.net = net
@@ -49,3 +63,7 @@ class ParsePredictor(object):
         bp, _ = backpointers(self.net)
         rows = bp.cpu().tolist()           # the single device->host transfer
         return [tree_from_backpointers(r, n) for r in rows]
+
+    def parse_spans(self, batch_map=None):
+        """Predicted constituent spans as a device tensor [B, n-1, 2] (no host tree building)."""
+        return spans(self.net)

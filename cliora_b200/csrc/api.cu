@@ -808,6 +808,14 @@ int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out
   return CLIORA_OK;
 }
 
+int cliora_tree_spans(int B, int n, const int32_t* backptr, int32_t* spans, int32_t* scratch, cliora_stream_t stream) {
+  if (!backptr || !spans || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || n < 2 || n > 512) return CLIORA_ERR_BAD_SHAPE;
+  launch_k(tree_spans_kernel, ceil_div(B, 64), 64, 0, (cudaStream_t)stream, B, n, backptr, spans, scratch);
+  CL_CHECK_LAUNCH("tree_spans_kernel");
+  return CLIORA_OK;
+}
+
 int cliora_recon_ce_fwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg, float* rowloss,
                         float* probs, cliora_stream_t stream) {
   if (!cell || !pos || !neg || !rowloss || !probs) return CLIORA_ERR_NULL_POINTER;

@@ -46,4 +46,41 @@ __global__ __launch_bounds__(64) void cky_kernel(int B, int n, const float* __re
     for (int i = threadIdx.x; i < C; i += blockDim.x) best_out[(int64_t)b * C + i] = s_best[i];
 }
 
+// Spans of the CKY tree straight from the backpointer table (replaces the host round trip
+// tree -> str -> get_actions -> get_spans of cliora/analysis/utils.py:3-48 used by scripts/parse.py:215-219).
+// One thread per sentence, explicit stack, post-order like get_spans: spans[b, i] = (start, end) inclusive word
+// positions of the i-th reduced constituent, i < n-1 (the last one is the whole sentence).
+__global__ void tree_spans_kernel(int B, int n, const int32_t* __restrict__ backptr, int32_t* __restrict__ spans,
+                                  int32_t* __restrict__ stack_mem) {
+  pdl_prologue();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int C = (int)num_cells(n);
+  const int32_t* bp = backptr + (int64_t)b * C;
+  int32_t* out = spans + (int64_t)b * (n - 1) * 2;
+  int32_t* st = stack_mem + (int64_t)b * 3 * n;   // (level, pos, state) triples, depth <= n
+  int sp = 0, emitted = 0;
+  st[0] = n - 1; st[1] = 0; st[2] = 0; sp = 1;
+  while (sp > 0) {
+    int32_t* top = st + 3 * (sp - 1);
+    const int level = top[0], pos = top[1], state = top[2];
+    if (level == 0) { --sp; continue; }
+    const int k = bp[lvl_off(n, level) + pos];
+    if (state == 0) {          // visit left child (k, pos)
+      top[2] = 1;
+      int32_t* nx = st + 3 * sp++;
+      nx[0] = k; nx[1] = pos; nx[2] = 0;
+    } else if (state == 1) {   // visit right child (level-1-k, pos+k+1)
+      top[2] = 2;
+      int32_t* nx = st + 3 * sp++;
+      nx[0] = level - 1 - k; nx[1] = pos + k + 1; nx[2] = 0;
+    } else {                   // both children done: emit this constituent
+      out[2 * emitted] = pos;
+      out[2 * emitted + 1] = pos + level;
+      ++emitted;
+      --sp;
+    }
+  }
+}
+
 }  // namespace cliora

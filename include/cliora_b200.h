@@ -235,6 +235,11 @@ int cliora_recon_ce_bwd(int rows, int D, int K, const float* cell, const float* 
  * ---------------------------------------------------------------------- */
 int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float* best, cliora_stream_t stream);
 
+/* Constituent spans of the decoded trees, on the device (replaces tree -> str -> get_actions -> get_spans,
+ * cliora/analysis/utils.py:3-48, scripts/parse.py:215-219).  spans [B, n-1, 2] int32: (start, end) inclusive
+ * word positions in post-order (the last entry is the whole sentence); scratch: 3*B*n int32. */
+int cliora_tree_spans(int B, int n, const int32_t* backptr, int32_t* spans, int32_t* scratch, cliora_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Dense helper used on both sides of the chart (Embed, ImageEncoder,
  * reconstruction loss; trainer.py:219-224, utils.py:52-55):

@@ -54,3 +54,24 @@ def test_cky_vs_oracle_live(B, n, D):
             # any disagreement must be a near-tie in the oracle's own candidate scores
             assert (o_best - best.cpu()).abs().max() < 1e-3
             assert same.float().mean() > 0.99
+
+
+@pytest.mark.parametrize('B,n', [(7, 9), (64, 30), (3, 2)])
+def test_device_spans_match_host_tree_spans(B, n):
+    """tree_spans_kernel == spans read off the nested-tuple trees (reference: get_actions/get_spans on str(tree))."""
+    from oracle import cliora_oracle as O
+    from cliora_b200.net.diora import DioraMLP
+    from cliora_b200.analysis.cky import ParsePredictor
+    from cliora_b200.analysis.utils import get_spans_from_tree
+    from test_gpu_chart import _fill
+    m = DioraMLP(32).cuda()
+    _fill(m, O.init_params(32, seed=2))
+    x = torch.randn(B, n, 32, generator=torch.Generator().manual_seed(n)).cuda()
+    with torch.no_grad():
+        m(x, x)
+    pp = ParsePredictor(m)
+    trees = pp.parse_batch({'sentences': torch.zeros(B, n, dtype=torch.int64)})
+    sp = pp.parse_spans().cpu().tolist()
+    for b in range(B):
+        assert [tuple(s) for s in sp[b]] == get_spans_from_tree(trees[b])   # same post-order, same spans
+        assert sp[b][-1] == [0, n - 1]
