@@ -139,17 +139,21 @@ __global__ __launch_bounds__(128) void atten_max_bwd_obj_kernel(int B, int ncell
   const int c = blockIdx.x / R, r = blockIdx.x % R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int E = B * ncell;
+  // blockIdx.y splits the (a,cell) scan: a dominant region can own most cells of an image, so one block per
+  // (c,r) would walk thousands of rows serially; partial sums are red.add'ed into g_obj (caller zero-fills)
+  const int e_chunk = ((E + gridDim.y - 1) / gridDim.y + 127) / 128 * 128;
+  const int e_lo = blockIdx.y * e_chunk, e_hi = min(E, e_lo + e_chunk);
   // lane owns columns j = lane*4 + t*128, t < 4 (D <= 512), looping beyond for larger D
   for (int jbase = 0; jbase < D; jbase += 512) {
     float4 acc[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = 0; e0 < E; e0 += 128) {
+    for (int e0 = e_lo; e0 < e_hi; e0 += 128) {
       const int e = e0 + tid;
       bool hit = false;
       float gv = 0.f;
       int a = 0, cell = 0;
-      if (e < E) {
+      if (e < e_hi) {
         a = e / ncell;
         cell = e % ncell;
         const int64_t o = ((int64_t)a * B + c) * ncell + cell;
@@ -206,13 +210,13 @@ __global__ __launch_bounds__(128) void atten_max_bwd_obj_kernel(int B, int ncell
     __syncthreads();
     float* dst = g_obj + ((int64_t)c * R + r) * D + jbase;
     for (int j = tid * 4; j < Dc; j += 512) {
-      float4 o = ld4(dst + j);
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int w2 = 0; w2 < 4; ++w2) {
         const float4 pv = ld4(s_part + w2 * 512 + j);
         o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
       }
-      st4(dst + j, o);
+      if (o.x != 0.f || o.y != 0.f || o.z != 0.f || o.w != 0.f) red_add4(dst + j, o);
     }
   }
 }

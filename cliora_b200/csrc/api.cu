@@ -768,7 +768,7 @@ int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t
     CL_CHECK_LAUNCH("atten_max_bwd_h_kernel");
   }
   if (g_obj) {
-    launch_k(atten_max_bwd_obj_kernel, B * R, 128, 4 * 512 * sizeof(float), st, B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
+    launch_k(atten_max_bwd_obj_kernel, dim3(B * R, 8), 128, 4 * 512 * sizeof(float), st, B, ncell, D, R, h, h_batch_stride, g_smax, amax, g_obj);
     CL_CHECK_LAUNCH("atten_max_bwd_obj_kernel");
   }
   return CLIORA_OK;
