@@ -64,6 +64,8 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   L.W2Tp = take(2 * D * D);
   L.oW2p = d.share ? L.W2p : take(2 * D * D);
   L.oW2Tp = d.share ? L.W2Tp : take(2 * D * D);
+  L.Mbin = D <= 512 ? take(L.rows_in * 16) : -1;    // ReLU bitmasks of Z (16 x uint32 per split row)
+  L.Mbout = D <= 512 ? take(L.rows_out * 16) : -1;
   L.ws_floats = o;
 
   const int64_t max_rows = B * n * (n - 1) > 0 ? B * n * (n - 1) : 4;
@@ -217,6 +219,8 @@ static SplitArgs split_args(const Ctx& c, int level, bool outside, const float* 
   s.Z = ws + (outside ? c.L.Zout : c.L.Zin) + r0 * c.d.D;
   s.E = ws + (outside ? c.L.Eout : c.L.Ein) + r0;
   s.z_lo_off = c.use_tc ? (outside ? c.L.rows_out : c.L.rows_in) * c.d.D : 0;
+  const int64_t mb = outside ? c.L.Mbout : c.L.Mbin;
+  s.zmask = (c.use_tc && mb >= 0) ? reinterpret_cast<uint32_t*>(ws + mb) + r0 * 16 : nullptr;
   return s;
 }
 
@@ -251,6 +255,8 @@ static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows
     tc::TcEpilogue ep{};
     ep.C = GZ; ep.ldc = D; ep.cmap = dense_rows();
     ep.mask = Zb + r0 * D; ep.ldm = D; ep.mask_lo_off = total * D;
+    const int64_t mb = outside ? c.L.Mbout : c.L.Mbin;
+    if (mb >= 0) ep.maskbits = reinterpret_cast<const uint32_t*>(ws + mb) + r0 * 16;
     return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", c.tc_mode, g_debug[2]);
   }
   GemmParams p{};

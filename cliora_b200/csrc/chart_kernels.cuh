@@ -51,6 +51,7 @@ struct SplitArgs {
   float* Z;           // level block [B*L*N, D] (hi part of the split pair when z_lo_off != 0)
   float* E;           // level block [B*L*N]
   int64_t z_lo_off;   // floats from Z to the lo part of the pair (0: store plain fp32)
+  uint32_t* zmask;    // level block [B*L*N, 16]: ReLU bits, word t*4+comp bit l <-> column 128t + 4l + comp; or null
 };
 
 template <bool OUTSIDE>
@@ -83,26 +84,35 @@ __global__ __launch_bounds__(256) void split_build_kernel(const SplitArgs a) {
   const float* h1 = a.ih + g1 * a.D;
   float* z = a.Z + m * a.D;
   float dot = 0.f;
-  for (int j = lane * 4; j < a.D; j += 128) {
-    const float4 x = ld4(Al + j), y = ld4(Ar + j), bb = ld4(a.b1 + j);
-    float4 o;
-    o.x = fmaxf(x.x + y.x + bb.x, 0.f);
-    o.y = fmaxf(x.y + y.y + bb.y, 0.f);
-    o.z = fmaxf(x.z + y.z + bb.z, 0.f);
-    o.w = fmaxf(x.w + y.w + bb.w, 0.f);
-    if (a.z_lo_off != 0) {
-      float4 hi, lo;
-      split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
-      st4(z + j, hi);
-      st4(z + a.z_lo_off + j, lo);
-    } else {
-      st4(z + j, o);
+  for (int t = 0; t * 128 < a.D; ++t) {          // warp-uniform trip count: the ballots below need every lane
+    const int j = lane * 4 + t * 128;
+    const bool valid = j < a.D;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float4 x = ld4(Al + j), y = ld4(Ar + j), bb = ld4(a.b1 + j);
+      o.x = fmaxf(x.x + y.x + bb.x, 0.f);
+      o.y = fmaxf(x.y + y.y + bb.y, 0.f);
+      o.z = fmaxf(x.z + y.z + bb.z, 0.f);
+      o.w = fmaxf(x.w + y.w + bb.w, 0.f);
+      if (a.z_lo_off != 0) {
+        float4 hi, lo;
+        split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+        st4(z + j, hi);
+        st4(z + a.z_lo_off + j, lo);
+      } else {
+        st4(z + j, o);
+      }
+      const float4 hv = ld4(h1 + j), vv = ld4(V + j);
+      dot = fmaf(hv.x, vv.x, dot);
+      dot = fmaf(hv.y, vv.y, dot);
+      dot = fmaf(hv.z, vv.z, dot);
+      dot = fmaf(hv.w, vv.w, dot);
     }
-    const float4 hv = ld4(h1 + j), vv = ld4(V + j);
-    dot = fmaf(hv.x, vv.x, dot);
-    dot = fmaf(hv.y, vv.y, dot);
-    dot = fmaf(hv.z, vv.z, dot);
-    dot = fmaf(hv.w, vv.w, dot);
+    if (a.zmask != nullptr) {   // ReLU bits for the backward GEMM epilogue (invalid lanes contribute zeros)
+      const unsigned b0 = __ballot_sync(0xffffffffu, o.x > 0.f), b1 = __ballot_sync(0xffffffffu, o.y > 0.f);
+      const unsigned b2 = __ballot_sync(0xffffffffu, o.z > 0.f), b3 = __ballot_sync(0xffffffffu, o.w > 0.f);
+      if (lane == 0 && t < 4) *reinterpret_cast<uint4*>(a.zmask + m * 16 + t * 4) = make_uint4(b0, b1, b2, b3);
+    }
   }
   dot = warp_sum(dot);
   if (lane == 0) {

@@ -112,6 +112,7 @@ struct TcEpilogue {
   const float* mask;    // dense [M, ldm]: result zeroed where mask <= 0; or null
   int64_t ldm;
   int64_t mask_lo_off;  // mask stored as a split pair: value = mask[i] + mask[i + mask_lo_off] (0: plain)
+  const uint32_t* maskbits;  // [M, 16] ReLU bitmask written by split_build (word t*4+comp, bit l <-> col 128t+4l+comp); or null
   float* C_lo;          // optional: also emit the split pair of the result (C gets hi, C_lo gets lo); or null
   int act;              // 0 none, 1 relu, 2 tanh
   int accumulate;       // C += result
@@ -253,6 +254,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* crow = row_ok ? ep.C + map_row(ep.cmap, r) * ep.ldc : nullptr;
     float* clo = (row_ok && ep.C_lo) ? ep.C_lo + map_row(ep.cmap, r) * ep.ldc : nullptr;
     const float* mrow = (row_ok && ep.mask) ? ep.mask + (int64_t)r * ep.ldm : nullptr;
+    const uint32_t* brow = (row_ok && ep.maskbits) ? ep.maskbits + (int64_t)r * 16 : nullptr;
     if (ep.gmax != nullptr) {
       // running max / argmax over each image's R columns; this thread owns the whole row of the tile
       const int imgs = ep.n_stride / ep.R;
@@ -333,7 +335,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int t = 0; t < 4; ++t) o[t] = tanhf(o[t]);
         }
-        if (mrow) {
+        if (brow) {
+          const uint4 w = *reinterpret_cast<const uint4*>(brow + (col >> 7) * 4);
+          const int l = (col & 127) >> 2;
+          if (!((w.x >> l) & 1u)) o[0] = 0.f;
+          if (!((w.y >> l) & 1u)) o[1] = 0.f;
+          if (!((w.z >> l) & 1u)) o[2] = 0.f;
+          if (!((w.w >> l) & 1u)) o[3] = 0.f;
+        } else if (mrow) {
           float4 mv = ld4(mrow + col);
           if (ep.mask_lo_off != 0) {
             const float4 ml = ld4(mrow + col + ep.mask_lo_off);

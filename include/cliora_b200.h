@@ -125,6 +125,8 @@ typedef struct cliora_layout {
   int64_t W2p, W2Tp, oW2p, oW2Tp;
   /* backward scratch, tensor-core weight gradients: split pairs of GP [2,B*C,PI*D] and of the chart vectors [2,B*C,D] */
   int64_t GPp, Hp;
+  /* forward workspace: ReLU bitmasks of the hidden activations, 16 x uint32 per split row (D <= 512), else -1 */
+  int64_t Mbin, Mbout;
 } cliora_layout;
 
 int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);
