@@ -164,9 +164,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; cliora_b200 has no CPU path (use --impl reference for the CPU arm)')
     from cliora_b200 import _lib
-    if _lib.needs_build():
-        if rank == 0:
-            _lib.build()
+    if not os.path.exists(_lib.LIB_PATH):      # normally shipped prebuilt (python -c 'import __graft_entry__ as g; g.build()')
+        if world > 1:
+            raise SystemExit('bench.py: build cliora_b200/libcliora_b200.so before a multi-rank run')
+        _lib.build()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:

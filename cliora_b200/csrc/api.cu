@@ -8,6 +8,7 @@
 #include "cell_warp_kernels.cuh"
 #include "cky_kernels.cuh"
 #include "recon_kernels.cuh"
+#include "optim_kernels.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "tc_gemm.cuh"
@@ -811,6 +812,43 @@ int cliora_vg_loss(int B, int n, const float* wmax, float alpha, float* loss_out
   CL_CHECK_LAUNCH("vg_loss_kernel");
   launch_k(sum_small_kernel, 1, 128, 0, st, scratch, B, loss_out);
   CL_CHECK_LAUNCH("sum_small_kernel");
+  return CLIORA_OK;
+}
+
+int64_t cliora_adam_table_bytes(int ntensors) { return (int64_t)ntensors * sizeof(AdamTensor); }
+
+int cliora_adam_table_fill(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                           void* const* exp_avg_sq, const int64_t* numel, void* host_table, int64_t* total_blocks) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !host_table || !total_blocks)
+    return CLIORA_ERR_NULL_POINTER;
+  AdamTensor* t = static_cast<AdamTensor*>(host_table);
+  int64_t blk = 0;
+  for (int i = 0; i < ntensors; ++i) {
+    t[i].p = static_cast<float*>(params[i]);
+    t[i].g = static_cast<const float*>(grads[i]);
+    t[i].m = static_cast<float*>(exp_avg[i]);
+    t[i].v = static_cast<float*>(exp_avg_sq[i]);
+    t[i].n = numel[i];
+    t[i].block0 = blk;
+    blk += (numel[i] + kAdamChunk - 1) / kAdamChunk;
+  }
+  *total_blocks = blk;
+  return CLIORA_OK;
+}
+
+int cliora_adam_step(const void* device_table, int ntensors, int64_t total_blocks, float lr, float beta1, float beta2,
+                     float eps, float max_norm, float* state, float* scratch, cliora_stream_t stream) {
+  if (!device_table || !state || !scratch) return CLIORA_ERR_NULL_POINTER;
+  if (ntensors < 1 || total_blocks < 1) return CLIORA_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdamTensor* tab = static_cast<const AdamTensor*>(device_table);
+  launch_k(adam_gradnorm_kernel, (unsigned)total_blocks, kAdamBlock, 0, st, tab, ntensors, scratch);
+  CL_CHECK_LAUNCH("adam_gradnorm_kernel");
+  launch_k(adam_norm_finish_kernel, 1, 256, 0, st, (const float*)scratch, (int)total_blocks, max_norm, state);
+  CL_CHECK_LAUNCH("adam_norm_finish_kernel");
+  launch_k(adam_update_kernel, (unsigned)total_blocks, kAdamBlock, 0, st, tab, ntensors, lr, beta1, beta2, eps,
+           (const float*)state);
+  CL_CHECK_LAUNCH("adam_update_kernel");
   return CLIORA_OK;
 }
 

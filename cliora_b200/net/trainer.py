@@ -196,11 +196,21 @@ class Trainer(object):
         self.ngpus = ngpus
         self.grad_sync = None     # set by cliora_b200.parallel for data-parallel runs
 
-    def init_optimizer(self, optimizer_cls=optim.Adam, optimizer_kwargs=None):
+    def init_optimizer(self, optimizer_cls=optim.Adam, optimizer_kwargs=None, fused=None):
+        """Adam(lr, betas, eps) like the reference (trainer.py:580).  On CUDA the default is the library's fused
+        clip(5.0)+Adam (three launches for all tensors, cliora_b200/optim.py); ``fused=False`` keeps torch's."""
         kw = dict(optimizer_kwargs or dict(lr=2e-3, betas=(0.9, 0.999), eps=1e-8))
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        if fused is None:
+            fused = bool(self.cuda) and optimizer_cls is optim.Adam
+        self.fused_optimizer = fused
+        if fused:
+            from ..optim import FusedClipAdam
+            self.optimizer = FusedClipAdam(params, lr=kw.get('lr', 2e-3), betas=kw.get('betas', (0.9, 0.999)),
+                                           eps=kw.get('eps', 1e-8), max_norm=5.0)
+            return
         if self.cuda and optimizer_cls is optim.Adam:
             kw.setdefault('capturable', True)   # lets Trainer.capture() put the Adam step inside a CUDA graph
-        params = [p for p in self.net.parameters() if p.requires_grad]
         self.optimizer = optimizer_cls(params, **kw)
 
     def run_net(self, batch_map, idx2word=None, compute_loss=True):
@@ -211,16 +221,17 @@ class Trainer(object):
                         batch_parse=batch_map.get('GT'))
 
     def gradient_update(self, loss):
-        self.optimizer.zero_grad()
+        self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync()
-        params = [p for p in self.net.parameters() if p.requires_grad]
-        torch.nn.utils.clip_grad_norm_(params, 5.0)
-        self.optimizer.step()
+        self._optimizer_update()
 
     # ---- CUDA-graph replay of the whole training step (forward, losses, backward, clip, Adam) ----
     def _optimizer_update(self):
+        if getattr(self, 'fused_optimizer', False):
+            self.optimizer.step()          # clip_grad_norm_(5.0) and Adam in one pass
+            return
         params = [p for p in self.net.parameters() if p.requires_grad]
         torch.nn.utils.clip_grad_norm_(params, 5.0)
         self.optimizer.step()

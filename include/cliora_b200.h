@@ -237,6 +237,21 @@ int cliora_recon_ce_bwd(int rows, int D, int K, const float* cell, const float* 
  * ---------------------------------------------------------------------- */
 int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float* best, cliora_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Fused optimiser step (replaces Trainer.gradient_update's clip_grad_norm_(params, 5.0) + Adam.step,
+ * cliora/net/trainer.py:450-455): global-norm clip and Adam over a table of tensors in three launches.
+ *   cliora_adam_table_fill  fills a HOST staging table (cliora_adam_table_bytes(n) bytes) from pointer arrays;
+ *                           the caller copies it to the device once.  Pointers must stay valid (graph-safe:
+ *                           gradients are written in place every step).
+ *   cliora_adam_step        state [3] floats on the device: out ||g||, out clip coefficient, in/out step count
+ *                           (incremented on the device); scratch: total_blocks floats.
+ * ---------------------------------------------------------------------- */
+int64_t cliora_adam_table_bytes(int ntensors);
+int cliora_adam_table_fill(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                           void* const* exp_avg_sq, const int64_t* numel, void* host_table, int64_t* total_blocks);
+int cliora_adam_step(const void* device_table, int ntensors, int64_t total_blocks, float lr, float beta1, float beta2,
+                     float eps, float max_norm, float* state, float* scratch, cliora_stream_t stream);
+
 /* Constituent spans of the decoded trees, on the device (replaces tree -> str -> get_actions -> get_spans,
  * cliora/analysis/utils.py:3-48, scripts/parse.py:215-219).  spans [B, n-1, 2] int32: (start, end) inclusive
  * word positions in post-order (the last entry is the whole sentence); scratch: 3*B*n int32. */

@@ -20,6 +20,16 @@ def _trainer(D=64, V=200, E=32, k_neg=10, seed=5):
     return tr
 
 
+def _reset_optimizer(tr):
+    if hasattr(tr.optimizer, 'reset_state'):
+        tr.optimizer.reset_state()
+        return
+    for st in tr.optimizer.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+
+
 def _batch(B=6, n=7, V=200, R=9, F=2048, k_neg=10, seed=0):
     g = torch.Generator().manual_seed(seed)
     return dict(sentences=torch.randint(0, V, (B, n), generator=g).cuda(),
@@ -36,10 +46,7 @@ def test_graphed_step_matches_eager_step():
     sd = {k: v.clone() for k, v in eager.net.state_dict().items()}
     graphed.capture(batches[0], warmup=2)          # warm-up steps update the weights and Adam state ...
     graphed.net.load_state_dict(sd)                # ... so reset both before comparing
-    for st in graphed.optimizer.state.values():
-        for v in st.values():
-            if torch.is_tensor(v):
-                v.zero_()
+    _reset_optimizer(graphed)
     la = [eager.step(x, train=True, sync_result=False)['total_loss'].item() for x in batches]
     lb = [graphed.step_graphed(x).item() for x in batches]
     for x, y in zip(la, lb):
@@ -95,10 +102,7 @@ def test_split_graph_path_used_for_data_parallel():
     graphed.capture(batches[0], warmup=1)
     assert graphed._graph_opt is not None
     graphed.net.load_state_dict(sd)
-    for st in graphed.optimizer.state.values():
-        for v in st.values():
-            if torch.is_tensor(v):
-                v.zero_()
+    _reset_optimizer(graphed)
     n0 = len(calls)
     la = [eager.step(x, train=True, sync_result=False)['total_loss'].item() for x in batches]
     lb = [graphed.step_graphed(x).item() for x in batches]
@@ -117,10 +121,7 @@ def test_prefetched_batches_give_same_losses():
     for tr in (a, b):
         tr.capture(batches[0], warmup=1)
         tr.net.load_state_dict(sd)
-        for st in tr.optimizer.state.values():
-            for v in st.values():
-                if torch.is_tensor(v):
-                    v.zero_()
+        _reset_optimizer(tr)
     la = [a.step_graphed(x).item() for x in batches]
     h = b.prefetch(batches[0])
     lb = []
@@ -130,3 +131,39 @@ def test_prefetched_batches_give_same_losses():
         h = nxt
     for x, y in zip(la, lb):
         assert abs(x - y) <= 2e-4 * abs(x), (la, lb)
+
+
+def test_fused_clip_adam_matches_torch():
+    """FusedClipAdam == clip_grad_norm_(5.0) + torch Adam (trainer.py:450-455,580) over several steps."""
+    from cliora_b200.optim import FusedClipAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(400, 800), (400,), (400, 400), (7,), (1025, 3)]
+    pa = [torch.randn(*s, generator=g).cuda().requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    fa = FusedClipAdam(pa, lr=2e-3)
+    fb = torch.optim.Adam(pb, lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(4):
+        scale = 10.0 if step % 2 == 0 else 0.01          # exercise both the clipping and the no-clip branch
+        grads = [scale * torch.randn(*s, generator=g).cuda() for s in shapes]
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_(pb, 5.0)
+        fb.step()
+        fa.step()
+        assert abs(fa.grad_norm.item() - norm.item()) <= 1e-5 * norm.item()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+
+
+def test_torch_adam_path_still_works():
+    """fused=False keeps torch's capturable Adam + clip_grad_norm_ (also inside the step graph)."""
+    import torch.optim as optim
+    tr = _trainer()
+    tr.init_optimizer(optim.Adam, dict(lr=2e-3, betas=(0.9, 0.999), eps=1e-8), fused=False)
+    tr.net.diora.atten_head.dropout.p = 0.0
+    b = _batch(seed=1)
+    tr.capture(b, warmup=1)
+    l1 = tr.step_graphed(b).item()
+    l2 = tr.step_graphed(b).item()
+    assert l2 < l1          # same batch twice: the update must reduce its loss
