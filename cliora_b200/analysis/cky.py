@@ -54,6 +54,29 @@ def spans(diora):
     return out
 
 
+def span_f1(diora, gold_spans):
+    """Per-sentence (tp, fp, fn, F1) of the decoded trees against gold spans, on the device.
+
+    ``gold_spans``: list (one per sentence) of lists of (start, end) like ``batch_map['GT']`` (scripts/parse.py:216;
+    the last entry of each list is dropped, as there).  Returns a float tensor [B, 4]; corpus F1 follows from the
+    column sums exactly as parse.py:283-287."""
+    sp = spans(diora)
+    B, n = diora._run.B, diora._run.n
+    G = max(1, max(len(g) for g in gold_spans))
+    gold = torch.zeros(B, G, 2, dtype=torch.int32)
+    glen = torch.zeros(B, dtype=torch.int32)
+    for b, g in enumerate(gold_spans):
+        glen[b] = len(g)
+        if len(g):
+            gold[b, :len(g)] = torch.tensor([list(x) for x in g], dtype=torch.int32)
+    gold, glen = gold.to(sp.device), glen.to(sp.device)
+    out = torch.empty(B, 4, device=sp.device, dtype=torch.float32)
+    with torch.cuda.device(sp.device):
+        check(_lib.lib().cliora_span_f1(B, n, G, ptr(sp), ptr(gold), ptr(glen), ptr(out), _lib.stream()),
+              'cliora_span_f1')
+    return out
+
+
 class ParsePredictor(object):
     def __init__(self, net):
         self.net = net

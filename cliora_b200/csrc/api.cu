@@ -860,6 +860,15 @@ int cliora_tree_spans(int B, int n, const int32_t* backptr, int32_t* spans, int3
   return CLIORA_OK;
 }
 
+int cliora_span_f1(int B, int n, int G, const int32_t* spans, const int32_t* gold, const int32_t* gold_len, float* out,
+                   cliora_stream_t stream) {
+  if (!spans || !gold || !gold_len || !out) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || n < 2 || G < 0) return CLIORA_ERR_BAD_SHAPE;
+  launch_k(span_f1_kernel, ceil_div(B, 64), 64, 0, (cudaStream_t)stream, B, n, G, spans, gold, gold_len, out);
+  CL_CHECK_LAUNCH("span_f1_kernel");
+  return CLIORA_OK;
+}
+
 int cliora_recon_ce_fwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg, float* rowloss,
                         float* probs, cliora_stream_t stream) {
   if (!cell || !pos || !neg || !rowloss || !probs) return CLIORA_ERR_NULL_POINTER;

@@ -83,4 +83,45 @@ __global__ void tree_spans_kernel(int B, int n, const int32_t* __restrict__ back
   }
 }
 
+// Bracketing scores of predicted vs gold spans with the reference's set semantics (scripts/parse.py:216-233:
+// gold = set(GT[:-1]), pred = set(get_spans(...)[:-1]), get_stats -> tp/fp/fn, sentence F1 with the 1e-8 guards).
+// pred [B, n-1, 2] from tree_spans_kernel (last entry = whole sentence, dropped); gold [B, G, 2] padded,
+// gold_len[b] entries valid of which the LAST is dropped like the reference's [:-1].  One thread per sentence.
+// out [B, 4]: tp, fp, fn, sentence F1.
+__global__ void span_f1_kernel(int B, int n, int G, const int32_t* __restrict__ pred, const int32_t* __restrict__ gold,
+                               const int32_t* __restrict__ gold_len, float* __restrict__ out) {
+  pdl_prologue();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int32_t* p = pred + (int64_t)b * (n - 1) * 2;
+  const int32_t* g = gold + (int64_t)b * G * 2;
+  const int np = n - 2;                              // predicted spans without the whole-sentence one
+  const int ng = max(0, min(G, gold_len[b]) - 1);    // gold[:-1]
+  int tp = 0, fn = 0, ngold = 0;
+  for (int i = 0; i < np; ++i) {
+    bool hit = false;
+    for (int j = 0; j < ng && !hit; ++j) hit = (g[2 * j] == p[2 * i]) && (g[2 * j + 1] == p[2 * i + 1]);
+    tp += hit;
+  }
+  for (int j = 0; j < ng; ++j) {
+    bool dup = false;
+    for (int k = 0; k < j && !dup; ++k) dup = (g[2 * k] == g[2 * j]) && (g[2 * k + 1] == g[2 * j + 1]);
+    if (dup) continue;                               // set(): duplicates in the gold list count once
+    ++ngold;
+    bool hit = false;
+    for (int i = 0; i < np && !hit; ++i) hit = (g[2 * j] == p[2 * i]) && (g[2 * j + 1] == p[2 * i + 1]);
+    fn += !hit;
+  }
+  const int fp = np - tp;
+  float prec = (float)tp / ((float)np + 1e-8f);
+  float reca = (float)tp / ((float)ngold + 1e-8f);
+  if (ngold == 0) {
+    reca = 1.f;
+    if (np == 0) prec = 1.f;
+  }
+  float* o = out + (int64_t)b * 4;
+  o[0] = (float)tp; o[1] = (float)fp; o[2] = (float)fn;
+  o[3] = 2.f * prec * reca / (prec + reca + 1e-8f);
+}
+
 }  // namespace cliora

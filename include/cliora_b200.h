@@ -257,6 +257,12 @@ int cliora_adam_step(const void* device_table, int ntensors, int64_t total_block
  * word positions in post-order (the last entry is the whole sentence); scratch: 3*B*n int32. */
 int cliora_tree_spans(int B, int n, const int32_t* backptr, int32_t* spans, int32_t* scratch, cliora_stream_t stream);
 
+/* Bracketing scores on the device (replaces get_stats + the sentence-F1 arithmetic of scripts/parse.py:216-233):
+ * spans from cliora_tree_spans, gold [B, G, 2] padded with gold_len[b] valid entries (the last one is dropped like
+ * the reference's GT[:-1]); out [B, 4] = tp, fp, fn, sentence F1. */
+int cliora_span_f1(int B, int n, int G, const int32_t* spans, const int32_t* gold, const int32_t* gold_len, float* out,
+                   cliora_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Dense helper used on both sides of the chart (Embed, ImageEncoder,
  * reconstruction loss; trainer.py:219-224, utils.py:52-55):

@@ -75,3 +75,43 @@ def test_device_spans_match_host_tree_spans(B, n):
     for b in range(B):
         assert [tuple(s) for s in sp[b]] == get_spans_from_tree(trees[b])   # same post-order, same spans
         assert sp[b][-1] == [0, n - 1]
+
+
+def test_device_span_f1_matches_reference_set_arithmetic():
+    """span_f1_kernel == get_stats + the sentence-F1 arithmetic of scripts/parse.py:216-233 (set semantics)."""
+    import random
+    from oracle import cliora_oracle as O
+    from cliora_b200.net.diora import DioraMLP
+    from cliora_b200.analysis.cky import ParsePredictor, span_f1
+    from cliora_b200.analysis.utils import get_spans_from_tree
+    from test_gpu_chart import _fill
+    B, n = 12, 11
+    m = DioraMLP(32).cuda()
+    _fill(m, O.init_params(32, seed=4))
+    x = torch.randn(B, n, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        m(x, x)
+    trees = ParsePredictor(m).parse_batch({'sentences': torch.zeros(B, n, dtype=torch.int64)})
+    rnd = random.Random(0)
+    gold = []
+    for b in range(B):
+        own = get_spans_from_tree(trees[b])
+        g = [s for s in own if rnd.random() < 0.5]                       # some right ones
+        g += [(rnd.randrange(0, n - 2), rnd.randrange(2, n)) for _ in range(3)]   # some arbitrary ones
+        g += g[:1]                                                          # a duplicate (set semantics)
+        g.append((0, n - 1))                                                # the last entry is dropped
+        gold.append(g if b != 5 else [(0, n - 1)])                          # one sentence with an empty gold set
+    got = span_f1(m, gold).cpu()
+    for b in range(B):
+        gs = set(tuple(s) for s in gold[b][:-1])
+        ps = set(get_spans_from_tree(trees[b])[:-1])
+        tp = len(ps & gs); fp = len(ps - gs); fn = len(gs - ps)
+        prec = float(tp) / (len(ps) + 1e-8)
+        reca = float(tp) / (len(gs) + 1e-8)
+        if len(gs) == 0:
+            reca = 1.
+            if len(ps) == 0:
+                prec = 1.
+        f1 = 2 * prec * reca / (prec + reca + 1e-8)
+        assert got[b, :3].tolist() == [tp, fp, fn], (b, got[b], tp, fp, fn)
+        assert abs(got[b, 3].item() - f1) < 1e-5
