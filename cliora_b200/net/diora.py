@@ -168,7 +168,8 @@ class DioraBase(nn.Module):
                 keep = torch.rand(B, n * (n + 1) // 2, obj.shape[1], device=x_span.device) >= p_drop
         self._keep_override = None
         run = ChartRun()
-        chains = self.chains if self.chains is not None else max(1, min(4, B // 8))
+        # measured on B200 (n=20, D=400): 2 chains are best at batch 32 (5034 vs 4910 sent/s with 4), 4 at batch 128
+        chains = self.chains if self.chains is not None else max(1, min(2 if B < 64 else 4, B // 8))
         if self.precision not in ('fp32', 'tf32'):
             raise ValueError("precision must be 'fp32' or 'tf32'")
         flags = 2 if self.precision == 'tf32' else 0
