@@ -99,9 +99,9 @@ def _declare(lib):
     lib.cliora_outside_fwd.argtypes = [POINTER(Dims), POINTER(Weights), vp, vp, vp, vp, vp, st]
     lib.cliora_chart_bwd_begin.argtypes = [POINTER(Dims), vp, vp, vp, vp, vp, st]
     lib.cliora_outside_bwd.argtypes = [POINTER(Dims), POINTER(Weights), vp, vp, vp, vp, vp, vp,
-                                       POINTER(WeightGrads), st]
+                                       POINTER(WeightGrads), c_int, st]
     lib.cliora_inside_bwd.argtypes = [POINTER(Dims), POINTER(Weights), vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp,
-                                      vp, POINTER(WeightGrads), st]
+                                      vp, POINTER(WeightGrads), c_int, st]
     lib.cliora_atten_scores.argtypes = [c_int, c_int, c_int, c_int, vp, c_int64, vp, vp, st]
     lib.cliora_atten_max_fwd.argtypes = [c_int, c_int, c_int, c_int, vp, c_int64, vp, vp, vp, st]
     lib.cliora_atten_max_bwd.argtypes = [c_int, c_int, c_int, c_int, vp, c_int64, vp, vp, vp, vp, c_int64, vp, st]

@@ -595,15 +595,17 @@ int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, con
 
 int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* inside_h,
                        const float* inside_s, const float* outside_h, const float* outside_s, float* ws,
-                       float* bws, cliora_weight_grads* grads, cliora_stream_t stream) {
+                       float* bws, cliora_weight_grads* grads, int phase, cliora_stream_t stream) {
   Ctx c;
   CL_TRY(make_ctx(dims, stream, c));
   if (!w || !inside_h || !inside_s || !outside_h || !outside_s || !ws || !bws || !grads)
     return CLIORA_ERR_NULL_POINTER;
+  if ((phase & 3) == 0) return CLIORA_ERR_BAD_SHAPE;
   const int B = c.d.B, n = c.d.n, D = c.d.D;
   const int64_t BC = (int64_t)B * c.C;
   float* Wcat_out = ws + c.L.Wcat_out;
   float* scratch = bws + c.L.splitk;
+  if (phase & CLIORA_PHASE_LEVELS) {
   for (int level = 0; level <= n - 2; ++level) {
     if (level > 0) CL_TRY(cellgrad_level(c, level, bws + c.L.GP_out, 2 * D, Wcat_out, bws + c.L.Gh_out));
     CL_TRY((level_bwd<true, false>(c, level, w, inside_h, inside_s, outside_s, const_cast<float*>(outside_h),
@@ -615,7 +617,9 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
     launch_k(outside_root_bwd_kernel, B, 128, 0, c.st, B, D, c.C, bws + c.L.Gh_out, outside_h, ws + c.L.nrm_out, grads->root);
     CL_CHECK_LAUNCH("outside_root_bwd_kernel");
   }
-  // weight gradients contributed by the outside pass
+  }   // CLIORA_PHASE_LEVELS
+  if (!(phase & CLIORA_PHASE_WEIGHTS)) return CLIORA_OK;
+  // weight gradients contributed by the outside pass (independent of the inside backward's level chain)
   const bool sh = c.d.share != 0;
   float* dW1 = sh ? grads->W1 : grads->oW1;
   float* dW2 = sh ? grads->W2 : grads->oW2;
@@ -655,10 +659,11 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
 int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* x, const float* obj,
                       const uint8_t* keep, const float* inside_h, const float* inside_s,
                       const float* outside_h, float* ws, float* bws, int had_outside, float* grad_x,
-                      float* grad_obj, cliora_weight_grads* grads, cliora_stream_t stream) {
+                      float* grad_obj, cliora_weight_grads* grads, int phase, cliora_stream_t stream) {
   Ctx c;
   CL_TRY(make_ctx(dims, stream, c));
   if (!w || !x || !inside_h || !inside_s || !ws || !bws || !grads) return CLIORA_ERR_NULL_POINTER;
+  if ((phase & 3) == 0) return CLIORA_ERR_BAD_SHAPE;
   (void)outside_h;
   const int B = c.d.B, n = c.d.n, D = c.d.D, R = c.d.R, PI = (int)c.L.PI;
   const int64_t BC = (int64_t)B * c.C;
@@ -668,11 +673,14 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   float* scratch = bws + c.L.splitk;
   float* ih = const_cast<float*>(inside_h);
   float* is_ = const_cast<float*>(inside_s);
+  if (phase & CLIORA_PHASE_LEVELS) {
   for (int level = n - 1; level >= 0; --level) {
     if (level < n - 1) CL_TRY(cellgrad_level(c, level, bws + c.L.GP_in, PI * D, Wcat_in, bws + c.L.Gh_in));
     if (vl) CL_TRY((level_bwd<false, true>(c, level, w, inside_h, inside_s, nullptr, ih, is_, obj, keep, ws, bws)));
     else CL_TRY((level_bwd<false, false>(c, level, w, inside_h, inside_s, nullptr, ih, is_, obj, keep, ws, bws)));
   }
+  }   // CLIORA_PHASE_LEVELS (uses no split-K scratch, so the outside weight phase may run concurrently)
+  if (!(phase & CLIORA_PHASE_WEIGHTS)) return CLIORA_OK;
   // leaf linear layer
   const float* gu = bws + c.L.gu;
   if (grad_x) {

@@ -235,7 +235,8 @@ class ChartFunction(torch.autograd.Function):
             # caching allocator ties their lifetime to `cur` (all side-stream work is joined back into it)
             all_bws = [torch.empty(int(p[3].bws_floats), device=dev, dtype=torch.float32) for p in parts]
             all_grads = [[torch.empty_like(w) for w in weights] for _ in parts]
-            for (b0, b1, _, lay), ws, st, bws, grads in zip(parts, wss, streams, all_bws, all_grads):
+            aux_streams = _streams(dev, 2 * len(parts))[len(parts):]
+            for (b0, b1, _, lay), ws, st, bws, grads, aux in zip(parts, wss, streams, all_bws, all_grads, aux_streams):
                 if st is not cur:
                     st.wait_stream(cur)
                 dims = Dims(b1 - b0, n, D, R, 1 if share else 0, ctx.flags)
@@ -245,17 +246,33 @@ class ChartFunction(torch.autograd.Function):
                     check(L.cliora_chart_bwd_begin(ctypes.byref(dims), _off(g_ih, b0 * C * D), _off(g_is, b0 * C),
                                                    _off(g_oh, b0 * C * D), _off(g_os, b0 * C), ptr(bws), h),
                           'cliora_chart_bwd_begin')
-                    if outside:
+                    def outside_bwd(phase, handle):
                         check(L.cliora_outside_bwd(ctypes.byref(dims), ctypes.byref(W), _off(inside_h, b0 * C * D),
                                                    _off(inside_s, b0 * C), _off(outside_h, b0 * C * D),
-                                                   _off(outside_s, b0 * C), ptr(ws), ptr(bws), ctypes.byref(G), h),
-                              'cliora_outside_bwd')
-                    check(L.cliora_inside_bwd(ctypes.byref(dims), ctypes.byref(W), _off(x, b0 * n * D),
-                                              _off(obj, b0 * R * D), _off(keep, b0 * C * R),
-                                              _off(inside_h, b0 * C * D), _off(inside_s, b0 * C),
-                                              _off(outside_h, b0 * C * D), ptr(ws), ptr(bws), 1 if outside else 0,
-                                              _off(gx, b0 * n * D), _off(gobj, b0 * R * D), ctypes.byref(G), h),
-                          'cliora_inside_bwd')
+                                                   _off(outside_s, b0 * C), ptr(ws), ptr(bws), ctypes.byref(G), phase,
+                                                   handle), 'cliora_outside_bwd')
+
+                    def inside_bwd(phase):
+                        check(L.cliora_inside_bwd(ctypes.byref(dims), ctypes.byref(W), _off(x, b0 * n * D),
+                                                  _off(obj, b0 * R * D), _off(keep, b0 * C * R),
+                                                  _off(inside_h, b0 * C * D), _off(inside_s, b0 * C),
+                                                  _off(outside_h, b0 * C * D), ptr(ws), ptr(bws), 1 if outside else 0,
+                                                  _off(gx, b0 * n * D), _off(gobj, b0 * R * D), ctypes.byref(G), phase,
+                                                  h), 'cliora_inside_bwd')
+
+                    if outside:
+                        # the outside pass's weight-gradient GEMMs (full-GPU tensor-core work) only need the outside
+                        # level chain: run them on an auxiliary stream while the latency-bound inside level chain
+                        # proceeds, and join before the inside weight phase accumulates into the same tensors
+                        outside_bwd(1, h)
+                        aux.wait_stream(st)
+                        with torch.cuda.stream(aux):
+                            outside_bwd(2, aux.cuda_stream)
+                        inside_bwd(1)
+                        st.wait_stream(aux)
+                        inside_bwd(2)
+                    else:
+                        inside_bwd(3)
             for st in streams:
                 if st is not cur:
                     cur.wait_stream(st)

@@ -94,6 +94,8 @@ typedef struct cliora_dims {
   int flags;   /* CLIORA_FLAG_* */
 } cliora_dims;
 
+#define CLIORA_PHASE_LEVELS 1
+#define CLIORA_PHASE_WEIGHTS 2
 #define CLIORA_FLAG_DETERMINISTIC 1 /* reserved */
 /* Reduced-precision mode: the tensor-core GEMMs issue one TF32 pass instead of the fp32-accurate three.
  * Stated tolerance 1e-2 of max on chart vectors (measured ~3e-3); CKY trees are NOT guaranteed identical. */
@@ -164,6 +166,11 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
  * cliora_inside_bwd       inside pass backward, levels n-1 -> 1, leaves, weight grads.
  *                         `had_outside` says whether cliora_outside_bwd ran on this bws.
  * Destroys the Y buffers in ws (overwritten by their gradients).
+ *
+ * `phase` (CLIORA_PHASE_LEVELS | CLIORA_PHASE_WEIGHTS, or either alone in that order): the level chain and
+ * the weight-gradient GEMMs of a pass.  The outside pass's weight phase only reads what the outside level phase
+ * produced, so a caller may run it on a second stream concurrently with the inside level phase, and join before
+ * the inside weight phase (which accumulates into the same gradient tensors when share != 0).
  * ---------------------------------------------------------------------- */
 int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, const float* g_inside_s,
                            const float* g_outside_h, const float* g_outside_s, float* bws,
@@ -171,12 +178,12 @@ int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, con
 
 int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* inside_h,
                        const float* inside_s, const float* outside_h, const float* outside_s, float* ws,
-                       float* bws, cliora_weight_grads* grads, cliora_stream_t stream);
+                       float* bws, cliora_weight_grads* grads, int phase, cliora_stream_t stream);
 
 int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const float* x, const float* obj,
                       const uint8_t* keep, const float* inside_h, const float* inside_s,
                       const float* outside_h, float* ws, float* bws, int had_outside, float* grad_x,
-                      float* grad_obj, cliora_weight_grads* grads, cliora_stream_t stream);
+                      float* grad_obj, cliora_weight_grads* grads, int phase, cliora_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Span-region alignment (replaces the einsums of cliora/net/cliora.py:457-466
