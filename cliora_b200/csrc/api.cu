@@ -877,6 +877,18 @@ int cliora_span_f1(int B, int n, int G, const int32_t* spans, const int32_t* gol
   return CLIORA_OK;
 }
 
+int cliora_grounding_eval(int B, int n, int R, int P, const float* atten_score, const float* boxes,
+                          const int32_t* phrases, const float* gt_boxes, float iou_thresh, int32_t* sel, float* iou,
+                          int32_t* hit, cliora_stream_t stream) {
+  if (B < 1 || n < 1 || R < 1 || P < 0) return CLIORA_ERR_BAD_SHAPE;
+  if (P == 0) return CLIORA_OK;
+  if (!atten_score || !boxes || !phrases || !gt_boxes || !sel || !iou || !hit) return CLIORA_ERR_NULL_POINTER;
+  launch_k(grounding_eval_kernel, ceil_div(P, 4), 128, 0, (cudaStream_t)stream, B, n, R, P, atten_score, boxes, phrases,
+           gt_boxes, iou_thresh, sel, iou, hit);
+  CL_CHECK_LAUNCH("grounding_eval_kernel");
+  return CLIORA_OK;
+}
+
 int cliora_recon_ce_fwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg, float* rowloss,
                         float* probs, cliora_stream_t stream) {
   if (!cell || !pos || !neg || !rowloss || !probs) return CLIORA_ERR_NULL_POINTER;

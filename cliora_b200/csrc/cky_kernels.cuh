@@ -124,4 +124,62 @@ __global__ void span_f1_kernel(int B, int n, int G, const int32_t* __restrict__ 
   o[3] = 2.f * prec * reca / (prec + reca + 1e-8f);
 }
 
+// Phrase grounding recall (scripts/parse.py:174-212, scripts/train.py:158-179): for a phrase covering words
+// [start, end) of sentence b, pick the word whose best region score is highest (first max), take that word's
+// best region (first max), and compare the region's box with the annotated box: hit iff IoU > thresh.
+// IoU follows torchvision.ops.box_iou (areas (x2-x1)(y2-y1), intersection clamped at 0).
+// One warp per phrase; lanes stride over the R regions of a word.  phrases [P,3] = (b, start, end).
+__global__ __launch_bounds__(128) void grounding_eval_kernel(int B, int n, int R, int P,
+                                                             const float* __restrict__ atten,   // [B,n,R]
+                                                             const float* __restrict__ boxes,   // [B,R,4]
+                                                             const int32_t* __restrict__ phrases,
+                                                             const float* __restrict__ gt_boxes,  // [P,4]
+                                                             float thresh, int32_t* __restrict__ sel,
+                                                             float* __restrict__ iou_out, int32_t* __restrict__ hit) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int ph = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ph >= P) return;
+  const int b = phrases[3 * ph], start = max(phrases[3 * ph + 1], 0), end = min(phrases[3 * ph + 2], n);
+  float best = -INFINITY;
+  int bw = -1, br = -1;
+  for (int w = start; w < end; ++w) {
+    const float* row = atten + ((int64_t)b * n + w) * R;
+    float v = -INFINITY;
+    int vi = 0x7fffffff;
+    for (int r = lane; r < R; r += 32) {
+      const float x = row[r];
+      if (x > v) { v = x; vi = r; }      // ascending r per lane: first max within the lane
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+      if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
+    }
+    if (v > best) { best = v; bw = w; br = vi; }   // strict: the first word wins ties
+  }
+  if (lane != 0) return;
+  float iou = 0.f;
+  int h = 0;
+  if (bw >= 0 && br < R) {
+    const float* pb = boxes + ((int64_t)b * R + br) * 4;
+    const float* gb = gt_boxes + (int64_t)ph * 4;
+    const float a1 = __fmul_rn(pb[2] - pb[0], pb[3] - pb[1]);
+    const float a2 = __fmul_rn(gb[2] - gb[0], gb[3] - gb[1]);
+    const float iw = fmaxf(fminf(pb[2], gb[2]) - fmaxf(pb[0], gb[0]), 0.f);
+    const float ih = fmaxf(fminf(pb[3], gb[3]) - fmaxf(pb[1], gb[1]), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
+    iou = __fdiv_rn(inter, uni);
+    h = iou > thresh ? 1 : 0;
+  } else {
+    br = -1;
+  }
+  sel[2 * ph] = bw;
+  sel[2 * ph + 1] = br;
+  iou_out[ph] = iou;
+  hit[ph] = h;
+}
+
 }  // namespace cliora

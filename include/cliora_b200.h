@@ -270,6 +270,16 @@ int cliora_tree_spans(int B, int n, const int32_t* backptr, int32_t* spans, int3
 int cliora_span_f1(int B, int n, int G, const int32_t* spans, const int32_t* gold, const int32_t* gold_len, float* out,
                    cliora_stream_t stream);
 
+/* Phrase-grounding recall on the device (replaces the per-phrase host loop of scripts/parse.py:174-212 and
+ * scripts/train.py:158-179 over `diora.atten_score.cpu()`): phrases [P, 3] int32 = (sentence b, first word,
+ * one-past-last word); for each, the word with the highest best-region score (first max) selects its best region
+ * (first max), whose box [B, R, 4] (x1, y1, x2, y2) is compared with gt_boxes [P, 4] by the IoU of
+ * torchvision.ops.box_iou.  sel [P, 2] = (word, region), iou [P], hit [P] = iou > iou_thresh (reference: 0.5).
+ * An empty word range gives sel = (-1, -1), iou 0, hit 0. */
+int cliora_grounding_eval(int B, int n, int R, int P, const float* atten_score, const float* boxes,
+                          const int32_t* phrases, const float* gt_boxes, float iou_thresh, int32_t* sel, float* iou,
+                          int32_t* hit, cliora_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Dense helper used on both sides of the chart (Embed, ImageEncoder,
  * reconstruction loss; trainer.py:219-224, utils.py:52-55):

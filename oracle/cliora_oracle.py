@@ -171,7 +171,7 @@ def inside_pass(P, leaf_h, obj=None, keep=None, mode='unit', out: Optional[Chart
         L, N = n - level, level
         H = torch.cat(hs, 1)
         S = torch.cat(ss, 1)
-        li, ri = inside_pairs(n, level)
+        li, ri = (t.to(H.device) for t in inside_pairs(n, level))
         lh, rh = H.index_select(1, li).reshape(-1, D), H.index_select(1, ri).reshape(-1, D)
         ls, rs = S.index_select(1, li).reshape(-1, 1), S.index_select(1, ri).reshape(-1, 1)
         pre = [] if out is not None else None
@@ -212,7 +212,7 @@ def outside_pass(P, inside_h, inside_s, mode='unit', out: Optional[ChartOut] = N
     for level in range(n - 2, -1, -1):
         L = n - level
         OH, OS = assemble(lvl_h, D), assemble(lvl_s, 1)
-        pi, si = outside_pairs(n, level)
+        pi, si = (t.to(OH.device) for t in outside_pairs(n, level))
         ph, sh = OH.index_select(1, pi).reshape(-1, D), inside_h.index_select(1, si).reshape(-1, D)
         ps, ss = OS.index_select(1, pi).reshape(-1, 1), inside_s.index_select(1, si).reshape(-1, 1)
         pre = [] if out is not None else None
@@ -275,7 +275,7 @@ def contrastive_loss(all_atten, inside_s, outside_s, margin=0.2, alpha=1.0):
     diag = torch.diagonal(sc, 0, -1).unsqueeze(-1)             # [cells, B, 1]
     txt = (margin + sc - diag).clamp(min=TINY)
     img = (margin + sc - diag.transpose(1, 2)).clamp(min=TINY)
-    eye = torch.eye(B, dtype=torch.bool).unsqueeze(0)
+    eye = torch.eye(B, dtype=torch.bool, device=sc.device).unsqueeze(0)
     txt = txt.masked_fill(eye, 0).mean(2)
     img = img.masked_fill(eye, 0).mean(1)
     vl = (txt + img).t()                                       # [B, cells]
@@ -287,7 +287,7 @@ def vg_loss(vg, alpha=1.0):
     """cliora/net/trainer.py:139-171 (VGLoss.forward, the live 'V1' branch)."""
     B, _, n, _ = vg.shape
     logits = vg.max(-1).values.sum(-1) / n
-    return alpha * torch.nn.functional.cross_entropy(logits, torch.arange(B))
+    return alpha * torch.nn.functional.cross_entropy(logits, torch.arange(B, device=logits.device))
 
 
 def reconstruction_loss(emb_weight, mat, sentences, neg_samples, outside_h):
@@ -299,7 +299,7 @@ def reconstruction_loss(emb_weight, mat, sentences, neg_samples, outside_h):
     xp = (pos * cell).sum(-1, keepdim=True)
     xn = cell @ neg.t()
     score = torch.cat([xp, xn], 2).reshape(B * n, -1)
-    tgt = torch.zeros(B * n, dtype=torch.int64)
+    tgt = torch.zeros(B * n, dtype=torch.int64, device=score.device)
     return torch.nn.functional.cross_entropy(score, tgt)
 
 
@@ -398,22 +398,25 @@ class CpuClioraStep(object):
     Used ONLY as bench.py's cpu_baseline / ``--impl reference`` arm and by tests as a checker."""
 
     def __init__(self, D=400, E=1024, V=8000, F=2048, k_neg=100, seed=1234, lr=2e-3, obj_feats=True,
-                 alpha_vg=1.0, alpha_contr=1.0, margin=0.2):
+                 alpha_vg=1.0, alpha_contr=1.0, margin=0.2, device='cpu'):
+        # device != 'cpu' runs the same dense eager formulation on that device (the "stock PyTorch on the same
+        # GPU" number of SURVEY.md section 8(d)); still a checker/baseline, never a product path
         g = torch.Generator().manual_seed(seed)
         self.obj_feats = obj_feats
-        self.P = {k: v.requires_grad_() for k, v in init_params(D, share=True, seed=seed).items()
+        self.P = {k: v.to(device).requires_grad_() for k, v in init_params(D, share=True, seed=seed).items()
                   if not k.startswith('outside_')}
         for k in list(self.P):
             if k.startswith('inside_'):
                 self.P['outside_' + k[len('inside_'):]] = self.P[k]
-        self.emb = torch.randn(V, E, generator=g)                       # frozen with --obj_feats (trainer.py:538-541)
-        self.mat = torch.randn(D, E, generator=g).requires_grad_()
-        self.mat1 = torch.randn(D, E, generator=g).requires_grad_()
-        self.recon_mat = torch.randn(D, E, generator=g).requires_grad_()
-        self.enc = {'fc.weight': (0.02 * torch.randn(D, F, generator=g)).requires_grad_(),
-                    'fc.bias': (0.02 * torch.randn(D, generator=g)).requires_grad_(),
-                    'fc_vis.weight': (0.02 * torch.randn(D, F, generator=g)).requires_grad_(),
-                    'fc_vis.bias': (0.02 * torch.randn(D, generator=g)).requires_grad_()}
+        dev = lambda t: t.to(device)
+        self.emb = dev(torch.randn(V, E, generator=g))                  # frozen with --obj_feats (trainer.py:538-541)
+        self.mat = dev(torch.randn(D, E, generator=g)).requires_grad_()
+        self.mat1 = dev(torch.randn(D, E, generator=g)).requires_grad_()
+        self.recon_mat = dev(torch.randn(D, E, generator=g)).requires_grad_()
+        self.enc = {'fc.weight': dev(0.02 * torch.randn(D, F, generator=g)).requires_grad_(),
+                    'fc.bias': dev(0.02 * torch.randn(D, generator=g)).requires_grad_(),
+                    'fc_vis.weight': dev(0.02 * torch.randn(D, F, generator=g)).requires_grad_(),
+                    'fc_vis.bias': dev(0.02 * torch.randn(D, generator=g)).requires_grad_()}
         self.alpha_vg, self.alpha_contr, self.margin = alpha_vg, alpha_contr, margin
         uniq = {id(v): v for v in list(self.P.values()) + [self.mat, self.mat1, self.recon_mat] + list(self.enc.values())}
         self.params = list(uniq.values())
