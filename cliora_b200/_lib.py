@@ -118,8 +118,10 @@ def _declare(lib):
     lib.cliora_adam_step.restype = c_int
     lib.cliora_span_f1.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, st]
     lib.cliora_span_f1.restype = c_int
-    lib.cliora_grounding_eval.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, st]
+    lib.cliora_grounding_eval.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_float, vp, vp, vp, st]
     lib.cliora_grounding_eval.restype = c_int
+    lib.cliora_gather_regions.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, st]
+    lib.cliora_gather_regions.restype = c_int
     lib.cliora_tree_spans.argtypes = [c_int, c_int, vp, vp, vp, st]
     lib.cliora_tree_spans.restype = c_int
     lib.cliora_recon_ce_fwd.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, st]
@@ -161,7 +163,7 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_atten_max_bwd', 'cliora_contrastive_loss', 'cliora_vg_loss', 'cliora_cky', 'cliora_linear',
            'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
            'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set',
-           'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn', 'cliora_tc_atten_max_fwd', 'cliora_recon_ce_fwd', 'cliora_recon_ce_bwd', 'cliora_tree_spans', 'cliora_span_f1', 'cliora_grounding_eval', 'cliora_adam_table_bytes',
+           'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn', 'cliora_tc_atten_max_fwd', 'cliora_recon_ce_fwd', 'cliora_recon_ce_bwd', 'cliora_tree_spans', 'cliora_span_f1', 'cliora_grounding_eval', 'cliora_gather_regions', 'cliora_adam_table_bytes',
            'cliora_adam_table_fill', 'cliora_adam_step']
 
 

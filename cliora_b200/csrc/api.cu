@@ -2,11 +2,14 @@
 // Host-side orchestration only: level loops, buffer carving, kernel launches on the caller's stream.
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
+#include <utility>
 
 #include "align_kernels.cuh"
 #include "chart_kernels.cuh"
 #include "cell_warp_kernels.cuh"
 #include "cky_kernels.cuh"
+#include "data_kernels.cuh"
 #include "recon_kernels.cuh"
 #include "optim_kernels.cuh"
 #include "common.cuh"
@@ -22,6 +25,23 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 int g_pdl = env_int("CLIORA_PDL", 0);
+// One shared-memory carveout for every kernel of the library: the tcgen05 GEMMs need the maximum carveout, and an
+// SM has to drain before it can switch configuration, so mixed carveouts serialise neighbouring kernels.
+int g_carveout = env_int("CLIORA_CARVEOUT", 100);
+void apply_carveout(const void* kern) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& d : done)
+    if (d.first == kern) {
+      if (d.second == g_carveout) return;
+      d.second = g_carveout;
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+      return;
+    }
+  done.emplace_back(kern, g_carveout);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+}
 int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel
 
 static int validate(const cliora_dims* d) {
@@ -889,6 +909,24 @@ int cliora_grounding_eval(int B, int n, int R, int P, const float* atten_score, 
   return CLIORA_OK;
 }
 
+int cliora_gather_regions(int B, int R, int F, int feat_dtype, const void* features, const float* bboxes,
+                          const int32_t* classes, const int64_t* pos_bboxes, const int64_t* img_index, float* obj_feats,
+                          float* boxes, int64_t* obj_cates, cliora_stream_t stream) {
+  if (!features || !pos_bboxes || !img_index || !obj_feats) return CLIORA_ERR_NULL_POINTER;
+  if (boxes && !bboxes) return CLIORA_ERR_NULL_POINTER;
+  if (B < 1 || R < 1 || F < 8 || F % 8 || (feat_dtype != 0 && feat_dtype != 1)) return CLIORA_ERR_BAD_SHAPE;
+  ProfScope prof((cudaStream_t)stream, "gather_regions", 0.0,
+                 (double)B * R * F * (feat_dtype ? 6.0 : 8.0) + (double)B * R * 44.0);
+  if (feat_dtype == 0)
+    launch_k(gather_regions_kernel<float>, B * R, 128, 0, (cudaStream_t)stream, B, R, F, (const float*)features, bboxes,
+             classes, pos_bboxes, img_index, obj_feats, boxes, obj_cates);
+  else
+    launch_k(gather_regions_kernel<__half>, B * R, 128, 0, (cudaStream_t)stream, B, R, F, (const __half*)features,
+             bboxes, classes, pos_bboxes, img_index, obj_feats, boxes, obj_cates);
+  CL_CHECK_LAUNCH("gather_regions_kernel");
+  return CLIORA_OK;
+}
+
 int cliora_recon_ce_fwd(int rows, int D, int K, const float* cell, const float* pos, const float* neg, float* rowloss,
                         float* probs, cliora_stream_t stream) {
   if (!cell || !pos || !neg || !rowloss || !probs) return CLIORA_ERR_NULL_POINTER;
@@ -944,7 +982,8 @@ int cliora_matmul_nn(int M, int N, int K, const float* A, const float* Bm, float
 }
 
 void cliora_debug_set(int key, int value) {
-  if (key == 100) { g_pdl = value ? 1 : 0; return; }   // programmatic dependent launch on/off
+  if (key == 100) { g_pdl = value ? 1 : 0; return; }
+  if (key == 101) { g_carveout = value; return; }      // preferred shared-memory carveout, percent (-1: leave)   // programmatic dependent launch on/off
   if (key >= 0 && key < 8) g_debug[key] = value;
 }
 

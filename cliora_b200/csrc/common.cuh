@@ -120,6 +120,8 @@ struct LaunchCtx {
 extern thread_local char g_last_cuda_error[256];
 extern long long g_launch_count;
 extern int g_pdl;   // 1: launch kernels with the programmatic-stream-serialization attribute
+extern int g_carveout;   // >= 0: preferred shared-memory carveout (percent) applied to every kernel once
+void apply_carveout(const void* kern);
 
 inline int record_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
@@ -153,6 +155,7 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // kernel launch with the optional PDL attribute (replaces the triple-chevron syntax everywhere)
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (g_carveout >= 0) apply_carveout(reinterpret_cast<const void*>(kern));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -280,6 +280,17 @@ int cliora_grounding_eval(int B, int n, int R, int P, const float* atten_score, 
                           const int32_t* phrases, const float* gt_boxes, float iou_thresh, int32_t* sel, float* iou,
                           int32_t* hit, cliora_stream_t stream);
 
+/* Batch assembly from the ragged region-feature table, on the device (replaces FlickrDataset.__getitem__,
+ * cliora/data/dataloader.py:205-222, + collate + .cuda(), cliora/data/batch_iterator.py:116-168).  Image i owns
+ * table rows [pos_bboxes[i,0], pos_bboxes[i,1]); batch entry b takes the first min(rows, R) rows of image
+ * img_index[b] and pads the rest (features 0, boxes -1, classes -1).  features: [rows, F] fp32 (feat_dtype 0) or
+ * fp16 (feat_dtype 1, widened to fp32 on the fly); bboxes [rows, 4]; classes [rows] int32 or NULL.  Table
+ * pointers may be device memory or pinned host memory (zero-copy).  Outputs: obj_feats [B, R, F] fp32,
+ * boxes [B, R, 4] (nullable), obj_cates [B, R] int64 (nullable).  img_index (device, int64) must be in range. */
+int cliora_gather_regions(int B, int R, int F, int feat_dtype, const void* features, const float* bboxes,
+                          const int32_t* classes, const int64_t* pos_bboxes, const int64_t* img_index, float* obj_feats,
+                          float* boxes, int64_t* obj_cates, cliora_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Dense helper used on both sides of the chart (Embed, ImageEncoder,
  * reconstruction loss; trainer.py:219-224, utils.py:52-55):

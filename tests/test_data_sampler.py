@@ -1,0 +1,51 @@
+"""Host data path: the sampler / negative sampler mirrors reproduce the reference's batches exactly
+(tests/golden/sampler.json, made by tests/golden/make_golden_sampler.py from the reference classes)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cliora_b200.data.sampler import FixedLengthBatchSampler, NegativeSampler, calculate_freq_dist
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'sampler.json')))
+
+
+@pytest.mark.parametrize('case', GOLD['sampler'], ids=[c['name'] for c in GOLD['sampler']])
+def test_sampler_matches_reference(case):
+    sents = [list(range(l)) for l in case['lengths']]
+    l2s = {int(k): v for k, v in case['length_to_size'].items()} if case.get('length_to_size') else None
+    s = FixedLengthBatchSampler(sents, batch_size=case['batch_size'], rng=np.random.RandomState(case['rng_seed']),
+                                maxlen=case.get('maxlen'), include_partial=case.get('include_partial', False),
+                                length_to_size=l2s)
+    for want in case['epochs']:
+        got = [list(b) for b in s]
+        assert got == want
+        assert len(s) == len(want)
+        for b in got:                                  # the property the chart kernels rely on
+            assert len({case['lengths'][i] for i in b}) == 1
+
+
+def test_sampler_accepts_length_array_and_data_source():
+    lengths = np.array([3, 5, 3, 5, 5, 3, 4, 4], dtype=np.int64)
+
+    class Src:
+        dataset = [list(range(l)) for l in lengths]
+
+        def __len__(self):
+            return len(self.dataset)
+    a = list(FixedLengthBatchSampler(lengths, 2, rng=np.random.RandomState(1), include_partial=True))
+    b = list(FixedLengthBatchSampler(Src(), 2, rng=np.random.RandomState(1), include_partial=True))
+    assert a == b and sorted(i for batch in a for i in batch) == list(range(8))
+
+
+@pytest.mark.parametrize('case', GOLD['negative'], ids=lambda c: 'V%d' % c['V'])
+def test_negative_sampler_matches_reference(case):
+    ns = NegativeSampler(np.asarray(case['freq'], dtype=np.float32), case['power'])
+    ns.set_seed(case['seed'])
+    assert [ns.sample(case['k']).tolist() for _ in range(3)] == case['draws']
+
+
+def test_freq_dist():
+    f = calculate_freq_dist([[0, 1, 1], [3, 1]], 5)
+    assert f.tolist() == [1, 3, 0, 1, 0] and f.dtype == np.float32
