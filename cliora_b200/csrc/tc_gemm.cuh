@@ -716,6 +716,10 @@ inline int64_t tn_tc_scratch_floats(int rows, int Ka, int Kb) { return (int64_t)
 inline int launch_tc_gemm_tn(cudaStream_t st, const PairRef& A, const PairRef& B, int rows, int Ka, int Kb, float* C,
                              int64_t ldc, int accumulate, float* scratch, const char* tag, int mode = 2) {
   if (Ka <= 0 || Kb <= 0) return CLIORA_OK;
+  if (rows <= 0) {   // empty reduction (a chart of single-word sentences has no splits): the sum is zero
+    if (!accumulate) CL_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, Kb * sizeof(float), Ka, st));
+    return CLIORA_OK;
+  }
   using S = TnSmem<kTnBlockN, kTnStages>;
   CUtensorMap tmA, tmB;
   CL_TRY(make_pair_map_mn(&tmA, A.base, A.rows, Ka, A.ld, A.part_stride));
