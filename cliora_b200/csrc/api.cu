@@ -777,9 +777,9 @@ int cliora_atten_scores(int B, int ncell, int D, int R, const float* h, int64_t 
 
 int cliora_atten_max_fwd(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride, const float* obj,
                          float* smax, int32_t* amax, cliora_stream_t stream) {
-  if (!h || !obj || !smax || !amax) return CLIORA_ERR_NULL_POINTER;
   if (B < 1 || ncell < 0 || D < 4 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
-  if (ncell == 0) return CLIORA_OK;
+  if (ncell == 0) return CLIORA_OK;   // single-word sentences: no cell takes part in the loss, outputs are empty
+  if (!h || !obj || !smax || !amax) return CLIORA_ERR_NULL_POINTER;
   dim3 grid(B, ceil_div((int64_t)B * ncell, 64));
   {
     ProfScope prof((cudaStream_t)stream, "atten_max", 2.0 * B * ncell * (double)B * R * D,
@@ -793,9 +793,9 @@ int cliora_atten_max_fwd(int B, int ncell, int D, int R, const float* h, int64_t
 int cliora_atten_max_bwd(int B, int ncell, int D, int R, const float* h, int64_t h_batch_stride, const float* obj,
                          const float* g_smax, const int32_t* amax, float* g_h, int64_t gh_batch_stride,
                          float* g_obj, cliora_stream_t stream) {
-  if (!h || !obj || !g_smax || !amax) return CLIORA_ERR_NULL_POINTER;
   if (B < 1 || ncell < 0 || D < 4 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
   if (ncell == 0) return CLIORA_OK;
+  if (!h || !obj || !g_smax || !amax) return CLIORA_ERR_NULL_POINTER;
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(st, "atten_max_bwd", 4.0 * B * ncell * (double)B * D, 4.0 * 2.0 * B * ncell * (double)B * D);
   if (g_h) {
@@ -1010,9 +1010,9 @@ int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pa
 
 int cliora_tc_atten_max_fwd(int B, int ncell, int D, int R, const float* h_pair, const float* obj_pair, float* smax,
                             int32_t* amax, cliora_stream_t stream) {
-  if (!h_pair || !obj_pair || !smax || !amax) return CLIORA_ERR_NULL_POINTER;
   if (B < 1 || ncell < 0 || D < 32 || D % 4 || R < 1 || R > 64) return CLIORA_ERR_BAD_SHAPE;
   if (ncell == 0) return CLIORA_OK;
+  if (!h_pair || !obj_pair || !smax || !amax) return CLIORA_ERR_NULL_POINTER;
   const int64_t M = (int64_t)B * ncell, N = (int64_t)B * R;
   tc::PairRef A{h_pair, M, D, M * D};
   tc::PairRef W{obj_pair, N, D, N * D};

@@ -88,6 +88,34 @@ def test_cliora_chart_vs_golden(golden, name):
         assert rel_err(getattr(m, k), blob[k]) < TOL, k
 
 
+@pytest.mark.parametrize('B,n,D,R,train', [(1, 1, 32, 4, False), (2, 2, 36, 1, True), (5, 9, 132, 64, False),
+                                           (3, 4, 520, 7, True), (4, 12, 64, 36, False)])
+def test_alignment_tensors_vs_oracle_odd_shapes(B, n, D, R, train):
+    """all_atten_score / vg_atten_score / atten_score (cliora.py:457-466) in train and eval mode at shapes
+    off the tuned path, against the oracle on the same inputs."""
+    from cliora_b200.net.cliora import DioraMLP
+    from oracle import cliora_oracle as O
+    P0 = O.init_params(D, share=True, seed=3)
+    g = torch.Generator().manual_seed(21)
+    x_span, x_word = torch.randn(B, n, D, generator=g), torch.randn(B, n, D, generator=g)
+    obj_span, obj_word = 0.05 * torch.randn(B, R, D, generator=g), 0.05 * torch.randn(B, R, D, generator=g)
+    keep = torch.rand(B, O.num_cells(n), R, generator=g) >= 0.1
+    out = O.chart_forward(P0, x_span, obj_span, keep if train else None)
+    aas = O.all_atten_score(out.inside_h, out.outside_h, obj_span)
+    vg = O.vg_atten_score(x_word, obj_word, training=train, all_atten=aas)
+    m = DioraMLP(D).cuda()
+    _fill(m, P0)
+    m.train() if train else m.eval()
+    if train:
+        m.set_dropout_mask(keep.cuda())
+    with torch.no_grad():
+        m(x_span.cuda(), x_word.cuda(), obj_span.cuda(), obj_word.cuda())
+    assert rel_err(m.inside_h, out.inside_h) < TOL and rel_err(m.outside_h, out.outside_h) < TOL
+    assert rel_err(m.all_atten_score, aas) < TOL
+    assert rel_err(m.vg_atten_score, vg) < TOL
+    assert rel_err(m.atten_score, O.atten_score(vg)) < TOL
+
+
 def _oracle_run(dt, B, n, D, R, share, seed=8):
     from oracle import cliora_oracle as O
     P0 = O.init_params(D, share=share, seed=7)

@@ -37,9 +37,11 @@ def _batch(B=6, n=7, V=200, R=9, F=2048, k_neg=10, seed=0):
                 obj_feats=torch.rand(B, R, F, generator=g).cuda(), batch_size=B, length=n)
 
 
-def test_graphed_step_matches_eager_step():
-    """Same weights, same batches, dropout off: CUDA-graph replay must reproduce the eager losses and weights."""
-    batches = [_batch(seed=i) for i in range(4)]
+@pytest.mark.parametrize('B,n,R', [(6, 7, 9), (2, 1, 3), (1, 2, 1), (5, 3, 64)])
+def test_graphed_step_matches_eager_step(B, n, R):
+    """Same weights, same batches, dropout off: CUDA-graph replay must reproduce the eager losses and weights
+    (also for single-word / single-sentence / single-region batches)."""
+    batches = [_batch(B=B, n=n, R=R, seed=i) for i in range(4)]
     eager, graphed = _trainer(), _trainer()
     for tr in (eager, graphed):
         tr.net.diora.atten_head.dropout.p = 0.0
@@ -56,10 +58,13 @@ def test_graphed_step_matches_eager_step():
         assert torch.allclose(p, q, rtol=1e-2, atol=1e-2), k
 
 
-def test_train_step_losses_vs_cpu_oracle_step():
-    """Net.forward + three losses through the fused product path == the oracle's dense CPU step (first step)."""
+@pytest.mark.parametrize('B,n,R,D,K', [(6, 7, 9, 64, 10), (1, 2, 1, 64, 1), (2, 1, 3, 36, 5), (9, 8, 36, 132, 100),
+                                       (3, 3, 64, 32, 2)])
+def test_train_step_losses_vs_cpu_oracle_step(B, n, R, D, K):
+    """Net.forward + three losses through the fused product path == the oracle's dense CPU step (first step),
+    including degenerate batches (one sentence, one word, one region, one negative)."""
     from oracle.cliora_oracle import CpuClioraStep
-    D, V, E, K, F = 64, 200, 32, 10, 2048
+    V, E, F = 200, 32, 2048
     tr = _trainer(D, V, E, K)
     cpu = CpuClioraStep(D=D, E=E, V=V, F=F, k_neg=K, seed=3)
     net = tr.net
@@ -72,8 +77,7 @@ def test_train_step_losses_vs_cpu_oracle_step():
         net.reconstruct_softmax_loss.mat.copy_(cpu.recon_mat)
         net.img_encoder.fc.weight.copy_(cpu.enc['fc.weight']); net.img_encoder.fc.bias.copy_(cpu.enc['fc.bias'])
         net.img_encoder.fc_vis.weight.copy_(cpu.enc['fc_vis.weight']); net.img_encoder.fc_vis.bias.copy_(cpu.enc['fc_vis.bias'])
-    bt = _batch(V=V, k_neg=K)
-    B, n = bt['sentences'].shape
+    bt = _batch(B=B, n=n, V=V, R=R, k_neg=K)
     keep = torch.rand(B, n * (n + 1) // 2, bt['obj_feats'].shape[1]) >= 0.1
     net.train()
     net.diora.set_dropout_mask(keep.cuda())
@@ -86,8 +90,15 @@ def test_train_step_losses_vs_cpu_oracle_step():
     total.backward()
     from conftest import rel_err
     assert rel_err(net.embed.mat.grad, cpu.mat.grad) < 2e-4
+    assert rel_err(net.embed.mat1.grad, cpu.mat1.grad) < 2e-4
     assert rel_err(net.img_encoder.fc.weight.grad, cpu.enc['fc.weight'].grad) < 2e-4
-    assert rel_err(net.diora.inside_compose_func.h_fcs[2].weight.grad, cpu.P['inside_compose_func.h_fcs.2.weight'].grad) < 2e-4
+    assert rel_err(net.img_encoder.fc_vis.weight.grad, cpu.enc['fc_vis.weight'].grad) < 2e-4
+    assert rel_err(net.reconstruct_softmax_loss.mat.grad, cpu.recon_mat.grad) < 2e-4
+    w2 = cpu.P['inside_compose_func.h_fcs.2.weight'].grad
+    if w2 is None:      # n == 1: the compose MLP is never used
+        assert float(net.diora.inside_compose_func.h_fcs[2].weight.grad.abs().max()) == 0.0
+    else:
+        assert rel_err(net.diora.inside_compose_func.h_fcs[2].weight.grad, w2) < 2e-4
 
 
 def test_split_graph_path_used_for_data_parallel():
