@@ -30,86 +30,90 @@ __global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
   const int chunks = (a.L + kCellsPerCta - 1) / kCellsPerCta;
   const int b = blockIdx.x / chunks;
   const int p = (blockIdx.x % chunks) * kCellsPerCta + warp;
-  if (VL) {
+  if (VL) {   // stage the image's regions asynchronously; they are first needed in step 3
     const float* obj = a.obj + (int64_t)b * a.R * a.D;
-    for (int i = tid * 4; i < a.R * a.D; i += 1024) st4(s_obj + i, ld4(obj + i));
-    __syncthreads();
+    for (int i = tid * 4; i < a.R * a.D; i += 1024) cp_async16(s_obj + i, obj + i);
+    cp_async_commit();
   }
-  if (p >= a.L) return;
+  const bool active = p < a.L;
   float* s_p = s_pbase + warp * a.N;
-  const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + p;
-  const int64_t row0 = (int64_t)b * a.L * a.N + (int64_t)p * a.sp;
-
-  // 1. softmax over the N splits (lanes over k)
-  float sbar = 0.f;
-  if (a.E == nullptr) {
-    if (lane == 0) s_p[0] = 1.f;
-  } else {
-    float mx = -INFINITY;
-    for (int k = lane; k < a.N; k += 32) mx = fmaxf(mx, a.E[row0 + (int64_t)k * a.sk]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int k = lane; k < a.N; k += 32) {
-      const float ex = expf(a.E[row0 + (int64_t)k * a.sk] - mx);
-      s_p[k] = ex;
-      sum += ex;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    for (int k = lane; k < a.N; k += 32) {
-      const float pk = s_p[k] * inv;
-      s_p[k] = pk;
-      a.Pr[row0 + (int64_t)k * a.sk] = pk;
-      sbar = fmaf(pk, a.E[row0 + (int64_t)k * a.sk], sbar);
-    }
-    sbar = warp_sum(sbar);
-  }
-  if (lane == 0) a.chart_s[cell] = sbar;
-  __syncwarp();
-
-  // 2. a = sum_k p_k y_k   (two rows in flight)
-  float4 acc[kColT];
-#pragma unroll
-  for (int t = 0; t < kColT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < a.N; k += 2) {
-    const bool two = k + 1 < a.N;
-    const float p0 = s_p[k], p1 = two ? s_p[k + 1] : 0.f;
-    const float* y0 = a.Y + (row0 + (int64_t)k * a.sk) * a.D;
-    const float* y1 = two ? a.Y + (row0 + (int64_t)(k + 1) * a.sk) * a.D : y0;
-    float4 v0[kColT], v1[kColT];
-#pragma unroll
-    for (int t = 0; t < kColT; ++t) {
-      const int j = lane * 4 + t * 128;
-      if (j < a.D) {
-        v0[t] = ld4(y0 + j);
-        v1[t] = ld4(y1 + j);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < kColT; ++t) {
-      const int j = lane * 4 + t * 128;
-      if (j < a.D) {
-        fma4(acc[t], p0, v0[t]);
-        fma4(acc[t], p1, v1[t]);
-      }
-    }
-  }
-  float ss = 0.f;
-#pragma unroll
-  for (int t = 0; t < kColT; ++t)
-    if (lane * 4 + t * 128 < a.D) ss += dot4(acc[t], acc[t]);
-  ss = warp_sum(ss);
-  const float nrm = fmaxf(sqrtf(ss), kTiny);
-  const float inv_nrm = 1.f / nrm;
+  const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + (active ? p : 0);
+  const int64_t row0 = (int64_t)b * a.L * a.N + (int64_t)(active ? p : 0) * a.sp;
   float4 q[kColT];
+  if (active) {
+    // 1. softmax over the N splits (lanes over k)
+    float sbar = 0.f;
+    if (a.E == nullptr) {
+      if (lane == 0) s_p[0] = 1.f;
+    } else {
+      float mx = -INFINITY;
+      for (int k = lane; k < a.N; k += 32) mx = fmaxf(mx, a.E[row0 + (int64_t)k * a.sk]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int k = lane; k < a.N; k += 32) {
+        const float ex = expf(a.E[row0 + (int64_t)k * a.sk] - mx);
+        s_p[k] = ex;
+        sum += ex;
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      for (int k = lane; k < a.N; k += 32) {
+        const float pk = s_p[k] * inv;
+        s_p[k] = pk;
+        a.Pr[row0 + (int64_t)k * a.sk] = pk;
+        sbar = fmaf(pk, a.E[row0 + (int64_t)k * a.sk], sbar);
+      }
+      sbar = warp_sum(sbar);
+    }
+    if (lane == 0) a.chart_s[cell] = sbar;
+    __syncwarp();
+
+    // 2. a = sum_k p_k y_k   (four rows = 16 independent 16-byte loads per lane in flight)
+    float4 acc[kColT];
 #pragma unroll
-  for (int t = 0; t < kColT; ++t) {
-    const int j = lane * 4 + t * 128;
-    q[t] = make_float4(acc[t].x * inv_nrm, acc[t].y * inv_nrm, acc[t].z * inv_nrm, acc[t].w * inv_nrm);
-    if (j < a.D) st4((VL ? a.q : a.chart_h) + cell * a.D + j, q[t]);
+    for (int t = 0; t < kColT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < a.N; k += 4) {
+      float pk[4];
+      const float* yk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = k + u < a.N;
+        pk[u] = ok ? s_p[k + u] : 0.f;
+        yk[u] = a.Y + (row0 + (int64_t)(ok ? k + u : k) * a.sk) * a.D;
+      }
+      float4 v[4][kColT];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (j < a.D) v[u][t] = ld4(yk[u] + j);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < kColT; ++t)
+          if (lane * 4 + t * 128 < a.D) fma4(acc[t], pk[u], v[u][t]);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t)
+      if (lane * 4 + t * 128 < a.D) ss += dot4(acc[t], acc[t]);
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), kTiny);
+    const float inv_nrm = 1.f / nrm;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      q[t] = make_float4(acc[t].x * inv_nrm, acc[t].y * inv_nrm, acc[t].z * inv_nrm, acc[t].w * inv_nrm);
+      if (j < a.D) st4((VL ? a.q : a.chart_h) + cell * a.D + j, q[t]);
+    }
+    if (lane == 0) a.nrm[cell] = nrm;
   }
-  if (lane == 0) a.nrm[cell] = nrm;
   if (!VL) return;
+  cp_async_wait_all();
+  __syncthreads();
+  if (!active) return;
 
   // 3. attention against the staged regions: logits owned by lane r % 32 (R <= 64)
   float lg0 = -INFINITY, lg1 = -INFINITY;
@@ -185,7 +189,9 @@ __global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g)
   const bool active = p < a.L;
   if (VL) {
     const float* obj = a.obj + (int64_t)b * a.R * a.D;
-    for (int i = tid * 4; i < a.R * a.D; i += 1024) st4(s_obj + i, ld4(obj + i));
+    for (int i = tid * 4; i < a.R * a.D; i += 1024) cp_async16(s_obj + i, obj + i);
+    cp_async_commit();
+    cp_async_wait_all();   // the cell's own vectors are tiny: nothing worth overlapping before the first use
     __syncthreads();
   }
   if (active) {
@@ -303,39 +309,63 @@ __global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g)
   if (a.E == nullptr) return;   // uniform over the CTA
   __syncthreads();
   const int ncell = min(kCellsPerCta, a.L - p0);
-  for (int it = warp; it < ncell * a.N; it += kCellsPerCta) {
-    const int cw = it / a.N, k = it % a.N;
-    const int64_t row = (int64_t)b * a.L * a.N + (int64_t)(p0 + cw) * a.sp + (int64_t)k * a.sk;
-    float* y = a.Y + row * a.D;
-    const float pk = a.Pr[row];
-    const float gs = s_sc[cw * 2], cm = s_sc[cw * 2 + 1];
-    float d = 0.f;
+  const int items = ncell * a.N;
+  // (cell, split) items over the 8 warps, four items (16 independent 16-byte loads per lane) in flight per warp
+  for (int it0 = warp; it0 < items; it0 += 4 * kCellsPerCta) {
+    float4 yv[4][kColT];
+    int64_t row[4];
+    int cw[4];
+    float pk[4], ev[4];
 #pragma unroll
-    for (int t = 0; t < kColT; ++t) {
-      const int j = lane * 4 + t * 128;
-      if (j < a.D) {
-        const float4 yv = ld4(y + j);
-        const float4 gg = ld4(s_ga + cw * a.D + j);
-        d += dot4(yv, gg);
-        float4 o;
-        o.x = yv.x > 0.f ? pk * gg.x : 0.f;
-        o.y = yv.y > 0.f ? pk * gg.y : 0.f;
-        o.z = yv.z > 0.f ? pk * gg.z : 0.f;
-        o.w = yv.w > 0.f ? pk * gg.w : 0.f;
-        if (a.y_lo_off != 0) {
-          float4 hi, lo;
-          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
-          st4(y + j, hi);
-          st4(y + a.y_lo_off + j, lo);
-        } else {
-          st4(y + j, o);
+    for (int u = 0; u < 4; ++u) {
+      const int it = it0 + u * kCellsPerCta;
+      const bool ok = it < items;            // warp-uniform
+      cw[u] = ok ? it / a.N : 0;
+      const int k = ok ? it % a.N : 0;
+      row[u] = (int64_t)b * a.L * a.N + (int64_t)(p0 + cw[u]) * a.sp + (int64_t)k * a.sk;
+      if (ok) {
+        const float* y = a.Y + row[u] * a.D;
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (j < a.D) yv[u][t] = ld4(y + j);
         }
+        pk[u] = a.Pr[row[u]];
+        ev[u] = a.E[row[u]];
       }
     }
-    d = warp_sum(d);
-    if (lane == 0) {
-      const float gp = d + a.E[row] * gs;
-      g.GE[row] = pk * (gs + gp - cm);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (it0 + u * kCellsPerCta >= items) break;
+      float* y = a.Y + row[u] * a.D;
+      const float gs = s_sc[cw[u] * 2], cm = s_sc[cw[u] * 2 + 1];
+      float d = 0.f;
+#pragma unroll
+      for (int t = 0; t < kColT; ++t) {
+        const int j = lane * 4 + t * 128;
+        if (j < a.D) {
+          const float4 gg = ld4(s_ga + cw[u] * a.D + j);
+          d += dot4(yv[u][t], gg);
+          float4 o;
+          o.x = yv[u][t].x > 0.f ? pk[u] * gg.x : 0.f;
+          o.y = yv[u][t].y > 0.f ? pk[u] * gg.y : 0.f;
+          o.z = yv[u][t].z > 0.f ? pk[u] * gg.z : 0.f;
+          o.w = yv[u][t].w > 0.f ? pk[u] * gg.w : 0.f;
+          if (a.y_lo_off != 0) {
+            float4 hi, lo;
+            split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+            st4(y + j, hi);
+            st4(y + a.y_lo_off + j, lo);
+          } else {
+            st4(y + j, o);
+          }
+        }
+      }
+      d = warp_sum(d);
+      if (lane == 0) {
+        const float gp = d + ev[u] * gs;
+        g.GE[row[u]] = pk[u] * (gs + gp - cm);
+      }
     }
   }
 }

@@ -84,34 +84,47 @@ __global__ __launch_bounds__(256) void split_build_kernel(const SplitArgs a) {
   const float* h1 = a.ih + g1 * a.D;
   float* z = a.Z + m * a.D;
   float dot = 0.f;
-  for (int t = 0; t * 128 < a.D; ++t) {          // warp-uniform trip count: the ballots below need every lane
-    const int j = lane * 4 + t * 128;
-    const bool valid = j < a.D;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      const float4 x = ld4(Al + j), y = ld4(Ar + j), bb = ld4(a.b1 + j);
-      o.x = fmaxf(x.x + y.x + bb.x, 0.f);
-      o.y = fmaxf(x.y + y.y + bb.y, 0.f);
-      o.z = fmaxf(x.z + y.z + bb.z, 0.f);
-      o.w = fmaxf(x.w + y.w + bb.w, 0.f);
-      if (a.z_lo_off != 0) {
-        float4 hi, lo;
-        split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
-        st4(z + j, hi);
-        st4(z + a.z_lo_off + j, lo);
-      } else {
-        st4(z + j, o);
+  // warp-uniform trip counts (the ballots need every lane); four 128-column chunks per round so that all of a
+  // row's gathers (up to 16 independent 16-byte loads per lane) are in flight before the first use
+  for (int t0 = 0; t0 * 128 < a.D; t0 += 4) {
+    float4 x[4], y[4], hv[4], vv[4], bb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane * 4 + (t0 + u) * 128;
+      if (j < a.D) {
+        x[u] = ld4(Al + j); y[u] = ld4(Ar + j); bb[u] = ld4(a.b1 + j);
+        hv[u] = ld4(h1 + j); vv[u] = ld4(V + j);
       }
-      const float4 hv = ld4(h1 + j), vv = ld4(V + j);
-      dot = fmaf(hv.x, vv.x, dot);
-      dot = fmaf(hv.y, vv.y, dot);
-      dot = fmaf(hv.z, vv.z, dot);
-      dot = fmaf(hv.w, vv.w, dot);
     }
-    if (a.zmask != nullptr) {   // ReLU bits for the backward GEMM epilogue (invalid lanes contribute zeros)
-      const unsigned b0 = __ballot_sync(0xffffffffu, o.x > 0.f), b1 = __ballot_sync(0xffffffffu, o.y > 0.f);
-      const unsigned b2 = __ballot_sync(0xffffffffu, o.z > 0.f), b3 = __ballot_sync(0xffffffffu, o.w > 0.f);
-      if (lane == 0 && t < 4) *reinterpret_cast<uint4*>(a.zmask + m * 16 + t * 4) = make_uint4(b0, b1, b2, b3);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      if (t * 128 >= a.D) break;                   // uniform
+      const int j = lane * 4 + t * 128;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < a.D) {
+        o.x = fmaxf(x[u].x + y[u].x + bb[u].x, 0.f);
+        o.y = fmaxf(x[u].y + y[u].y + bb[u].y, 0.f);
+        o.z = fmaxf(x[u].z + y[u].z + bb[u].z, 0.f);
+        o.w = fmaxf(x[u].w + y[u].w + bb[u].w, 0.f);
+        if (a.z_lo_off != 0) {
+          float4 hi, lo;
+          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+          st4(z + j, hi);
+          st4(z + a.z_lo_off + j, lo);
+        } else {
+          st4(z + j, o);
+        }
+        dot = fmaf(hv[u].x, vv[u].x, dot);
+        dot = fmaf(hv[u].y, vv[u].y, dot);
+        dot = fmaf(hv[u].z, vv[u].z, dot);
+        dot = fmaf(hv[u].w, vv[u].w, dot);
+      }
+      if (a.zmask != nullptr) {   // ReLU bits for the backward GEMM epilogue (invalid lanes contribute zeros)
+        const unsigned b0 = __ballot_sync(0xffffffffu, o.x > 0.f), b1 = __ballot_sync(0xffffffffu, o.y > 0.f);
+        const unsigned b2 = __ballot_sync(0xffffffffu, o.z > 0.f), b3 = __ballot_sync(0xffffffffu, o.w > 0.f);
+        if (lane == 0 && t < 4) *reinterpret_cast<uint4*>(a.zmask + m * 16 + t * 4) = make_uint4(b0, b1, b2, b3);
+      }
     }
   }
   dot = warp_sum(dot);
@@ -193,6 +206,7 @@ __global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
   float ss = 0.f;
   for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
     for (int k = 0; k < a.N; ++k) {
       const float pk = s_p[k];
       const float4 y = ld4(a.Y + (row0 + (int64_t)k * a.sk) * a.D + j);
@@ -414,21 +428,30 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
       float* y = a.Y + row * a.D;
       const float pk = a.Pr[row];
       float d = 0.f;
-      for (int j = lane * 4; j < a.D; j += 128) {
-        const float4 yv = ld4(y + j), gv = ld4(s_g + j);
-        d = fmaf(yv.x, gv.x, d); d = fmaf(yv.y, gv.y, d); d = fmaf(yv.z, gv.z, d); d = fmaf(yv.w, gv.w, d);
-        float4 o;
-        o.x = yv.x > 0.f ? pk * gv.x : 0.f;
-        o.y = yv.y > 0.f ? pk * gv.y : 0.f;
-        o.z = yv.z > 0.f ? pk * gv.z : 0.f;
-        o.w = yv.w > 0.f ? pk * gv.w : 0.f;
-        if (a.y_lo_off != 0) {
-          float4 hi, lo;
-          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
-          st4(y + j, hi);
-          st4(y + a.y_lo_off + j, lo);
-        } else {
-          st4(y + j, o);
+      for (int j0 = lane * 4; j0 < a.D; j0 += 512) {   // the row's loads are issued together
+        float4 yq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u * 128 < a.D) yq[u] = ld4(y + j0 + u * 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 128;
+          if (j >= a.D) break;
+          const float4 yv = yq[u], gv = ld4(s_g + j);
+          d = fmaf(yv.x, gv.x, d); d = fmaf(yv.y, gv.y, d); d = fmaf(yv.z, gv.z, d); d = fmaf(yv.w, gv.w, d);
+          float4 o;
+          o.x = yv.x > 0.f ? pk * gv.x : 0.f;
+          o.y = yv.y > 0.f ? pk * gv.y : 0.f;
+          o.z = yv.z > 0.f ? pk * gv.z : 0.f;
+          o.w = yv.w > 0.f ? pk * gv.w : 0.f;
+          if (a.y_lo_off != 0) {
+            float4 hi, lo;
+            split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+            st4(y + j, hi);
+            st4(y + a.y_lo_off + j, lo);
+          } else {
+            st4(y + j, o);
+          }
         }
       }
       d = warp_sum(d);
@@ -473,13 +496,23 @@ __global__ __launch_bounds__(256) void split_scatter_kernel(const ScatterArgs g)
   float* dAr = OUTSIDE ? g.GP_out + g2 * 2 * a.D : g.GP_in + g2 * a.ldPin + a.D;
   float* dV = OUTSIDE ? g.GP_out + g2 * 2 * a.D + a.D : g.GP_in + g2 * a.ldPin + 2 * a.D;
   float* dh1 = g.Gh_in + g1 * a.D;
-  for (int j = lane * 4; j < a.D; j += 128) {
-    const float4 z = ld4(gz + j);
-    red_add4(dAl + j, z);
-    red_add4(dAr + j, z);
-    const float4 vv = ld4(V + j), hv = ld4(h1 + j);
-    red_add4(dh1 + j, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
-    red_add4(dV + j, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
+  for (int j0 = lane * 4; j0 < a.D; j0 += 512) {   // four chunks per round: 12 independent loads before the reds
+    float4 z[4], vv[4], hv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 128;
+      if (j < a.D) { z[u] = ld4(gz + j); vv[u] = ld4(V + j); hv[u] = ld4(h1 + j); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 128;
+      if (j < a.D) {
+        red_add4(dAl + j, z[u]);
+        red_add4(dAr + j, z[u]);
+        red_add4(dh1 + j, make_float4(ge * vv[u].x, ge * vv[u].y, ge * vv[u].z, ge * vv[u].w));
+        red_add4(dV + j, make_float4(ge * hv[u].x, ge * hv[u].y, ge * hv[u].z, ge * hv[u].w));
+      }
+    }
   }
   if (lane == 0) {
     atomicAdd(g.Gs_in + g1, ge);

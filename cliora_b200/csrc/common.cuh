@@ -103,6 +103,14 @@ CL_D void red_add4(float* p, float4 v) {
                : "memory");
 }
 
+// ---- asynchronous global -> shared copies (16 bytes, L1-bypassing) ----
+CL_D void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+CL_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+CL_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- programmatic dependent launch (PDL) ----
 // First statement of every kernel: let the next kernel in the stream get scheduled while this one runs, then
 // wait until the previous kernel has completed and flushed its memory.  All global accesses come after the
