@@ -42,7 +42,7 @@ void apply_carveout(const void* kern) {
   done.emplace_back(kern, g_carveout);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
 }
-int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel
+int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -114,6 +114,8 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   L.gu = take(B * n * D);
   L.GPp = take(2 * B * C * PI * D);   // split pairs of the projection-gradient accumulators (tensor-core wgrad)
   L.Hp = take(2 * B * C * D);         // split pair of the chart vectors
+  L.CSin = take(B * C * D);           // per-cell sums of the GY rows (zero for cells without splits)
+  L.CSout = take(B * C * D);
   L.bws_floats = o;
   return CLIORA_OK;
 }
@@ -344,7 +346,7 @@ static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
       configured = smem;
     }
     const int chunks = ceil_div(a.L, kCellsPerCta);
-    launch_k(cell_fwd_warp_kernel<true>, a.B * chunks, 256, smem, c.st, a);
+    launch_k(cell_fwd_warp_kernel<true>, a.B * chunks, kCellThreads, smem, c.st, a);
     CL_CHECK_LAUNCH("cell_fwd_warp_kernel");
     return CLIORA_OK;
   }
@@ -354,8 +356,16 @@ static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
   return CLIORA_OK;
 }
 
+// db2 = column sum of the GY rows.  The block-per-cell backward kernel leaves per-cell sums of those rows in
+// CSin / CSout, so the column sum runs over B*C rows instead of all split rows (19x fewer at n = 20).
+static bool cellsum_enabled(const Ctx& c, bool outside) {
+  if (c.d.D > 512 || g_debug[4] != 0) return false;
+  const bool warp_bwd = !outside && c.d.R > 0 && c.d.D <= 128 * kColT && (g_debug[3] & 2) == 0;
+  return !warp_bwd;
+}
+
 template <bool VL>
-static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
+static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g, float* cellsum) {
   const double rows = (double)g.c.B * g.c.L * g.c.N;
   ProfScope prof(c.st, "cell_bwd", 4.0 * rows * g.c.D, 4.0 * (2.0 * rows * (g.c.D + 2) + 3.0 * g.c.B * g.c.L * g.c.D));
   if (VL && g.c.D <= 128 * kColT && (g_debug[3] & 2) == 0) {
@@ -366,12 +376,14 @@ static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g) {
       configured = smem;
     }
     const int chunks = ceil_div(g.c.L, kCellsPerCta);
-    launch_k(cell_bwd_warp_kernel<true>, g.c.B * chunks, 256, smem, c.st, g);
+    launch_k(cell_bwd_warp_kernel<true>, g.c.B * chunks, kCellThreads, smem, c.st, g);
     CL_CHECK_LAUNCH("cell_bwd_warp_kernel");
     return CLIORA_OK;
   }
-  const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64) * sizeof(float);
-  launch_k(cell_bwd_kernel<VL>, g.c.B * g.c.L, 256, smem, c.st, g);
+  CellBwdArgs gb = g;
+  if (g.c.D <= 512 && g.c.E != nullptr && g_debug[4] == 0) gb.cellsum = cellsum;
+  const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64 + (gb.cellsum ? 8 * g.c.D + 4 : 0)) * sizeof(float);
+  launch_k(cell_bwd_kernel<VL>, g.c.B * g.c.L, 256, smem, c.st, gb);
   CL_CHECK_LAUNCH("cell_bwd_kernel");
   return CLIORA_OK;
 }
@@ -394,7 +406,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   g.gu = bws + c.L.gu;
   // GE is level-local here: point the kernel at a level block starting at GE[0]
   // (cell_bwd indexes GE with the same row ids as E, relative to the level block).
-  CL_TRY(launch_cell_bwd<VL>(c, g));
+  CL_TRY(launch_cell_bwd<VL>(c, g, bws + (OUTSIDE ? c.L.CSout : c.L.CSin)));
   if (g.c.E == nullptr) return CLIORA_OK;  // leaf level: no splits
 
   const float* W2 = (OUTSIDE && !c.d.share) ? w->oW2 : w->W2;
@@ -610,6 +622,7 @@ int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, con
   CL_TRY(seed(bws + c.L.Gs_out, g_outside_s, BC));
   CL_CUDA(cudaMemsetAsync(bws + c.L.GP_in, 0, BC * c.L.PI * D * sizeof(float), c.st));
   CL_CUDA(cudaMemsetAsync(bws + c.L.GP_out, 0, BC * 2 * D * sizeof(float), c.st));
+  CL_CUDA(cudaMemsetAsync(bws + c.L.CSin, 0, 2 * BC * D * sizeof(float), c.st));   // CSin and CSout are adjacent
   return CLIORA_OK;
 }
 
@@ -658,8 +671,12 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
     }
   }
   if (db2) {
-    CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
-    if (lo_out) CL_TRY(colsum(c.st, GY + lo_out, D, c.L.rows_out, D, db2, 1, scratch));
+    if (cellsum_enabled(c, true)) {
+      CL_TRY(colsum(c.st, bws + c.L.CSout, D, BC, D, db2, 0, scratch));
+    } else {
+      CL_TRY(colsum(c.st, GY, D, c.L.rows_out, D, db2, 0, scratch));
+      if (lo_out) CL_TRY(colsum(c.st, GY + lo_out, D, c.L.rows_out, D, db2, 1, scratch));
+    }
   }
   {
     float* dst[2] = {dW1 ? dW1 + D : nullptr, dWb};
@@ -729,8 +746,12 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
     }
   }
   if (grads->b2) {
-    CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
-    if (lo_in) CL_TRY(colsum(c.st, GY + lo_in, D, c.L.rows_in, D, grads->b2, 1, scratch));
+    if (cellsum_enabled(c, false)) {
+      CL_TRY(colsum(c.st, bws + c.L.CSin, D, BC, D, grads->b2, acc, scratch));
+    } else {
+      CL_TRY(colsum(c.st, GY, D, c.L.rows_in, D, grads->b2, acc, scratch));
+      if (lo_in) CL_TRY(colsum(c.st, GY + lo_in, D, c.L.rows_in, D, grads->b2, 1, scratch));
+    }
   }
   {
     float* dst[4] = {grads->W1, grads->W1 ? grads->W1 + D : nullptr, grads->Wb, nullptr};
@@ -740,7 +761,12 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   }
   if (grads->b1) CL_TRY(colsum(c.st, GPi, ldp, BC, D, grads->b1, 0, scratch));
   if (vl && grad_obj) {
-    dim3 grid(ceil_div(D, 32), B);
+    // cells split over grid.z so that the launch fills the GPU at small batch sizes
+    int zs = (int)((4 * 148 + (int64_t)ceil_div(D, 32) * B - 1) / ((int64_t)ceil_div(D, 32) * B));
+    if (zs > (int)((c.C + 15) / 16)) zs = (int)((c.C + 15) / 16);
+    if (zs < 1) zs = 1;
+    dim3 grid(ceil_div(D, 32), B, zs);
+    if (zs > 1) CL_CUDA(cudaMemsetAsync(grad_obj, 0, (size_t)B * R * D * sizeof(float), c.st));
     launch_k(obj_grad_kernel<64>, grid, dim3(32, 4), 0, c.st, D, R, c.C, bws + c.L.GA2, ws + c.L.q_in, bws + c.L.coef, grad_obj, 0);
     CL_CHECK_LAUNCH("obj_grad_kernel");
   }

@@ -10,7 +10,11 @@
 
 namespace cliora {
 
-constexpr int kCellsPerCta = 8;
+#ifndef CLIORA_CELLS_PER_CTA
+#define CLIORA_CELLS_PER_CTA 8
+#endif
+constexpr int kCellsPerCta = CLIORA_CELLS_PER_CTA;
+constexpr int kCellThreads = kCellsPerCta * 32;
 constexpr int kColT = 4;   // float4 column groups per lane
 
 CL_D float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
@@ -18,10 +22,52 @@ CL_D void fma4(float4& acc, float w, const float4& v) {
   acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
 }
 
+// Dot products of one D-vector (register fragments v[t]) with the R staged region vectors.  Returns the logits
+// in the "lane r % 32 owns region r" layout (lg0: r < 32, lg1: r >= 32).  The first 32 regions are reduced with a
+// transposing butterfly (31 shuffles in total instead of 5 per region); the few beyond 32 with plain reductions.
+CL_D void region_dots(const float4 (&v)[kColT], const float* __restrict__ s_obj, int R, int D, int lane, float& lg0,
+                      float& lg1) {
+  float d[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    float acc = 0.f;
+    if (r < R) {
+#pragma unroll
+      for (int t = 0; t < kColT; ++t) {
+        const int j = lane * 4 + t * 128;
+        if (j < D) acc += dot4(v[t], ld4(s_obj + r * D + j));
+      }
+    }
+    d[r] = acc;
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? d[i] : d[i + s];
+      const float keep = upper ? d[i + s] : d[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  lg0 = d[0];            // lane l now holds the full sum of region l
+  lg1 = 0.f;
+  for (int r = 32; r < R; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < kColT; ++t) {
+      const int j = lane * 4 + t * 128;
+      if (j < D) acc += dot4(v[t], ld4(s_obj + r * D + j));
+    }
+    acc = warp_sum(acc);
+    if ((r & 31) == lane) lg1 = acc;
+  }
+}
+
 // forward: softmax over splits, weighted sum, normalise, region attention, second normalise
 // dynamic smem: (VL ? R*D : 0) + 8*N floats
 template <bool VL>
-__global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
+__global__ __launch_bounds__(kCellThreads) void cell_fwd_warp_kernel(const CellArgs a) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* s_obj = sm;
@@ -32,7 +78,7 @@ __global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
   const int p = (blockIdx.x % chunks) * kCellsPerCta + warp;
   if (VL) {   // stage the image's regions asynchronously; they are first needed in step 3
     const float* obj = a.obj + (int64_t)b * a.R * a.D;
-    for (int i = tid * 4; i < a.R * a.D; i += 1024) cp_async16(s_obj + i, obj + i);
+    for (int i = tid * 4; i < a.R * a.D; i += kCellThreads * 4) cp_async16(s_obj + i, obj + i);
     cp_async_commit();
   }
   const bool active = p < a.L;
@@ -116,20 +162,10 @@ __global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
   if (!active) return;
 
   // 3. attention against the staged regions: logits owned by lane r % 32 (R <= 64)
-  float lg0 = -INFINITY, lg1 = -INFINITY;
-  for (int r = 0; r < a.R; ++r) {
-    float d = 0.f;
-#pragma unroll
-    for (int t = 0; t < kColT; ++t) {
-      const int j = lane * 4 + t * 128;
-      if (j < a.D) d += dot4(q[t], ld4(s_obj + r * a.D + j));
-    }
-    d = warp_sum(d);
-    if ((r & 31) == lane) {
-      if (r < 32) lg0 = d;
-      else lg1 = d;
-    }
-  }
+  float lg0, lg1;
+  region_dots(q, s_obj, a.R, a.D, lane, lg0, lg1);
+  if (lane >= a.R) lg0 = -INFINITY;
+  if (lane + 32 >= a.R) lg1 = -INFINITY;
   const float mx = warp_max(fmaxf(lg0, lg1));
   const float e0 = (lane < a.R) ? expf(lg0 - mx) : 0.f;
   const float e1 = (lane + 32 < a.R) ? expf(lg1 - mx) : 0.f;
@@ -174,7 +210,7 @@ __global__ __launch_bounds__(256) void cell_fwd_warp_kernel(const CellArgs a) {
 // phase 2: all (cell, split) items of the CTA spread over the 8 warps
 // dynamic smem: (VL ? R*D : 0) + 8*D + 32 floats
 template <bool VL>
-__global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g) {
+__global__ __launch_bounds__(kCellThreads) void cell_bwd_warp_kernel(const CellBwdArgs g) {
   pdl_prologue();
   const CellArgs& a = g.c;
   extern __shared__ __align__(16) float sm[];
@@ -189,7 +225,7 @@ __global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g)
   const bool active = p < a.L;
   if (VL) {
     const float* obj = a.obj + (int64_t)b * a.R * a.D;
-    for (int i = tid * 4; i < a.R * a.D; i += 1024) cp_async16(s_obj + i, obj + i);
+    for (int i = tid * 4; i < a.R * a.D; i += kCellThreads * 4) cp_async16(s_obj + i, obj + i);
     cp_async_commit();
     cp_async_wait_all();   // the cell's own vectors are tiny: nothing worth overlapping before the first use
     __syncthreads();
@@ -222,20 +258,10 @@ __global__ __launch_bounds__(256) void cell_bwd_warp_kernel(const CellBwdArgs g)
                             (gv[t].z - hv[t].z * coef) * inv2, (gv[t].w - hv[t].w * coef) * inv2);   // ga2
         if (j < a.D) st4(g.GA2 + cell * a.D + j, gv[t]);
       }
-      float ga0 = 0.f, ga1 = 0.f;   // g_att_r = (ga2 . obj_r) * scale_r, owned by lane r % 32
-      for (int r = 0; r < a.R; ++r) {
-        float d = 0.f;
-#pragma unroll
-        for (int t = 0; t < kColT; ++t) {
-          const int j = lane * 4 + t * 128;
-          if (j < a.D) d += dot4(gv[t], ld4(s_obj + r * a.D + j));
-        }
-        d = warp_sum(d);
-        if ((r & 31) == lane) {
-          if (r < 32) ga0 = d;
-          else ga1 = d;
-        }
-      }
+      float ga0, ga1;   // g_att_r = (ga2 . obj_r) * scale_r, owned by lane r % 32
+      region_dots(gv, s_obj, a.R, a.D, lane, ga0, ga1);
+      if (lane >= a.R) ga0 = 0.f;
+      if (lane + 32 >= a.R) ga1 = 0.f;
       float at0 = 0.f, at1 = 0.f, sc0 = 1.f, sc1 = 1.f;
       if (lane < a.R) {
         at0 = a.att[cell * a.R + lane];

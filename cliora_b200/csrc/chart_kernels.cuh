@@ -323,9 +323,10 @@ struct CellBwdArgs {
   float* coef;           // [B,C,2R] out (VL): patt_r, g_logit_r
   const float* leaf_t;   // leaf mode: tanh outputs [B*n, D]
   float* gu;             // leaf mode out: gradient wrt the pre-tanh activations [B*n, D]
+  float* cellsum;        // [B,C,D] out or null: sum over the cell's splits of the GY rows (colsum of these = db2)
 };
 
-// One block per cell.  Dynamic shared memory: (2D + 3R + 64) floats.
+// One block per cell.  Dynamic shared memory: (2D + 3R + 64) floats, + 8D when cellsum != null.
 template <bool VL>
 __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
   pdl_prologue();
@@ -423,6 +424,10 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
     const float gs = g.Gs[cell];
     const float cm = nrm * ad + a.chart_s[cell] * gs;   // sum_m p_m gp_m
     // ---- per split: ge, gy ----
+    const bool want_sum = g.cellsum != nullptr;     // only offered for D <= 512 (one 4-chunk round per row)
+    float4 bacc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) bacc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = warp; k < a.N; k += nwarps) {
       const int64_t row = row0 + (int64_t)k * a.sk;
       float* y = a.Y + row * a.D;
@@ -444,6 +449,7 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
           o.y = yv.y > 0.f ? pk * gv.y : 0.f;
           o.z = yv.z > 0.f ? pk * gv.z : 0.f;
           o.w = yv.w > 0.f ? pk * gv.w : 0.f;
+          if (want_sum) { bacc[u].x += o.x; bacc[u].y += o.y; bacc[u].z += o.z; bacc[u].w += o.w; }
           if (a.y_lo_off != 0) {
             float4 hi, lo;
             split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
@@ -458,6 +464,23 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
       if (lane == 0) {
         const float gp = d + a.E[row] * gs;
         g.GE[row] = pk * (gs + gp - cm);
+      }
+    }
+    if (want_sum) {   // warps -> block: the cell's sum of GY rows
+      float* s_part = sm + ((2 * a.D + 3 * a.R + 64 + 3) & ~3);   // [nwarps][D], 16-byte aligned
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = lane * 4 + u * 128;
+        if (j < a.D) st4(s_part + warp * a.D + j, bacc[u]);
+      }
+      __syncthreads();
+      for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
+        float4 t = ld4(s_part + j);
+        for (int w = 1; w < nwarps; ++w) {
+          const float4 x = ld4(s_part + w * a.D + j);
+          t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+        }
+        st4(g.cellsum + cell * a.D + j, t);
       }
     }
   }
@@ -545,8 +568,9 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
                                                        const float* __restrict__ q, const float* __restrict__ coef,
                                                        float* __restrict__ g_obj, int accumulate) {
   pdl_prologue();
-  constexpr int RQ = (RMAX + 3) / 4;   // regions per threadIdx.y
+  constexpr int RQ = (RMAX + 3) / 4;   // upper bound of regions per threadIdx.y
   constexpr int CH = 16;               // cells per chunk
+  const int rq = (R + 3) / 4;          // regions per threadIdx.y for this R (balanced over the 4 thread rows)
   const int b = blockIdx.y;
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -554,9 +578,12 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
   float acc[RQ];
 #pragma unroll
   for (int i = 0; i < RQ; ++i) acc[i] = 0.f;
-  const int r0 = threadIdx.y * RQ;
-  for (int64_t c0 = 0; c0 < C; c0 += CH) {
-    const int nc = (int)min((int64_t)CH, C - c0);
+  const int r0 = threadIdx.y * rq;
+  // cells are split over blockIdx.z (partials are red.add'ed into a zero-filled g_obj when gridDim.z > 1)
+  const int64_t per = (C + gridDim.z - 1) / gridDim.z;
+  const int64_t c_begin = blockIdx.z * per, c_end = min(C, c_begin + per);
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += CH) {
+    const int nc = (int)min((int64_t)CH, c_end - c0);
     __syncthreads();
     for (int t = tid; t < nc * 2 * R; t += 128) {
       const int cc = t / (2 * R), k = t % (2 * R);
@@ -577,7 +604,7 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
 #pragma unroll
         for (int i = 0; i < RQ; ++i) {
           const int r = r0 + i;
-          if (r < R) acc[i] = fmaf(s_c[cc][r], gv[cc], fmaf(s_c[cc][R + r], qv[cc], acc[i]));
+          if (i < rq && r < R) acc[i] = fmaf(s_c[cc][r], gv[cc], fmaf(s_c[cc][R + r], qv[cc], acc[i]));
         }
       }
     }
@@ -586,9 +613,10 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
 #pragma unroll
     for (int i = 0; i < RQ; ++i) {
       const int r = r0 + i;
-      if (r < R) {
+      if (i < rq && r < R) {
         float* dst = g_obj + ((int64_t)b * R + r) * D + j;
-        *dst = accumulate ? *dst + acc[i] : acc[i];
+        if (gridDim.z > 1) atomicAdd(dst, acc[i]);
+        else *dst = accumulate ? *dst + acc[i] : acc[i];
       }
     }
   }

@@ -129,6 +129,7 @@ typedef struct cliora_layout {
   int64_t GPp, Hp;
   /* forward workspace: ReLU bitmasks of the hidden activations, 16 x uint32 per split row (D <= 512), else -1 */
   int64_t Mbin, Mbout;
+  int64_t CSin, CSout;        /* bws: per-cell sums over splits of the compose-output gradients [B,C,D] (-> db2) */
 } cliora_layout;
 
 int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);
