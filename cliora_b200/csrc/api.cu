@@ -42,7 +42,7 @@ void apply_carveout(const void* kern) {
   done.emplace_back(kern, g_carveout);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
 }
-int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums
+int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums, [5] = 1: per-cell GEMMs on the fp32 SIMT kernel instead of mma.sync 3xTF32
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -148,6 +148,7 @@ static int project_level(const Ctx& c, int level, const float* chart_h, const fl
   p.C = P; p.ldc = ncols; p.cmap = level_rows(c.d.n, level);
   p.M = c.d.B * (c.d.n - level); p.N = ncols; p.K = c.d.D;
   p.tag = "gemm_cell_project";
+  p.mma_ok = c.use_tc && g_debug[5] == 0;
   p.accumulate = 1;   // P was zero-filled at the start of the pass: lets small levels split K with red.add
   return launch_gemm(c.st, /*nt=*/true, p, /*atomic_ok=*/true);
 }
@@ -160,6 +161,7 @@ static int cellgrad_level(const Ctx& c, int level, const float* GP, int ncols, c
   p.C = Gh; p.ldc = c.d.D; p.cmap = level_rows(c.d.n, level);
   p.M = c.d.B * (c.d.n - level); p.N = c.d.D; p.K = ncols;
   p.accumulate = 1;
+  p.mma_ok = c.use_tc && g_debug[5] == 0;
   p.tag = "gemm_cell_grad";
   return launch_gemm(c.st, /*nt=*/false, p, /*atomic_ok=*/true);
 }

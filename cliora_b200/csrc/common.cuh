@@ -110,6 +110,8 @@ CL_D void cp_async16(void* smem_dst, const void* gmem_src) {
 }
 CL_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 CL_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+CL_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- programmatic dependent launch (PDL) ----
 // First statement of every kernel: let the next kernel in the stream get scheduled while this one runs, then

@@ -31,6 +31,7 @@ struct GemmParams {
   const char* tag;          // profiler label (host only)
   int64_t a_lo_off, w_lo_off;  // operands stored as split pairs: value = X[i] + X[i + lo_off] (0: plain)
   int atomic_splitk;           // k_chunk > 0 and partials are red.add'ed straight into C (bias by split 0)
+  int mma_ok;                  // caller allows the 3xTF32 mma.sync kernel (fp32-grade, not bit-exact fp32 FMA order)
 };
 
 constexpr int kBN = 64;
@@ -303,6 +304,150 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Small-M GEMM on the warp-level tensor-core path (mma.sync m16n8k8 TF32, 3xTF32 error compensation done in
+// registers: x = hi + lo, acc += lo*hi + hi*lo + hi*hi in fp32).  Used for the per-cell projection and
+// cell-gradient GEMMs (M = B * cells-of-a-level <= a few hundred rows): those launches are one wave, so the
+// tcgen05 kernel's fixed cost (TMEM allocation, descriptor fetch, first TMA round trip, ~6 us) and its operand
+// pair format buy nothing there, while the fp32 FMA pipe caps the SIMT kernel.  A row-major [M,K] with RowMap;
+// W is [N,K] (B_KMAJOR = false, "NT") or [K,N] (B_KMAJOR = true, "NN").  No activation / mask.
+// 64x64x16 tiles, 8 warps as 2 (m) x 4 (n), warp tile 32x16.  Shared tiles are laid out so that every
+// fragment load is bank-conflict free: [row][k] with stride 20, or [k][n] with stride 72.
+// ------------------------------------------------------------------------------------------
+CL_D void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+CL_D void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+CL_D void red_add2(float* p, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+}
+
+template <bool B_KMAJOR>
+__global__ __launch_bounds__(256) void gemm_mma_kernel(const GemmParams p) {
+  pdl_prologue();
+  constexpr int BM = 64, LDK = kBK + 4, LDN = kBN + 8, ST = 4;   // 4-stage cp.async pipeline
+  __shared__ __align__(16) float As[ST][BM][LDK];
+  __shared__ __align__(16) float Bs[ST][B_KMAJOR ? kBK * LDN : kBN * LDK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * kBN;
+  int k_begin = 0, k_end = p.K;
+  if (p.k_chunk > 0) {
+    k_begin = blockIdx.z * p.k_chunk;
+    k_end = min(p.K, k_begin + p.k_chunk);
+  }
+  // one 16-byte asynchronous copy of A and one of W per thread per k-tile (zero fill outside the matrix)
+  const int a_r = tid >> 2, a_q = (tid & 3) * 4;
+  const bool a_ok = m0 + a_r < p.M;
+  const float* a_src = a_ok ? p.A + map_row(p.amap, m0 + a_r) * p.lda : p.A;
+  const int b_r = B_KMAJOR ? tid >> 4 : tid >> 2;             // k row, or n row
+  const int b_q = B_KMAJOR ? (tid & 15) * 4 : (tid & 3) * 4;  // n quad, or k quad
+  const bool b_ok = B_KMAJOR ? (n0 + b_q < p.N) : (n0 + b_r < p.N);   // N % 4 == 0 on this path
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto issue = [&](int kt) {
+    const int buf = kt % ST, k0 = k_begin + kt * kBK;
+    float* da = &As[buf][a_r][a_q];
+    if (a_ok && k0 + a_q < k_end) cp_async16(da, a_src + k0 + a_q);      // K % 4 == 0, chunks % 16 == 0
+    else st4(da, zero4);
+    if (!B_KMAJOR) {
+      float* db = &Bs[buf][b_r * LDK + b_q];
+      if (b_ok && k0 + b_q < k_end) cp_async16(db, p.W + (int64_t)(n0 + b_r) * p.ldw + k0 + b_q);
+      else st4(db, zero4);
+    } else {
+      float* db = &Bs[buf][b_r * LDN + b_q];
+      if (b_ok && k0 + b_r < k_end) cp_async16(db, p.W + (int64_t)(k0 + b_r) * p.ldw + n0 + b_q);
+      else st4(db, zero4);
+    }
+  };
+  float acc[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+  const int nk = (k_end - k_begin + kBK - 1) / kBK;
+#pragma unroll
+  for (int s0 = 0; s0 < ST - 1; ++s0) {
+    if (s0 < nk) issue(s0);
+    cp_async_commit();              // one group per k-tile, empty ones included, so the wait count is uniform
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt % ST;
+    cp_async_wait<ST - 2>();        // k-tile kt has landed (for this thread's copies) ...
+    __syncthreads();                // ... and for everyone's; also: everyone is done reading tile kt-1
+    if (kt + ST - 1 < nk) issue(kt + ST - 1);   // overwrites the buffer of tile kt-1
+    cp_async_commit();
+#pragma unroll
+    for (int kb = 0; kb < kBK; kb += 8) {
+      uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = wm * 32 + mi * 16 + g;
+        tf32_split(As[cur][r][kb + t], ah[mi][0], al[mi][0]);
+        tf32_split(As[cur][r + 8][kb + t], ah[mi][1], al[mi][1]);
+        tf32_split(As[cur][r][kb + t + 4], ah[mi][2], al[mi][2]);
+        tf32_split(As[cur][r + 8][kb + t + 4], ah[mi][3], al[mi][3]);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int cidx = wn * 16 + ni * 8 + g;
+        const float b0 = B_KMAJOR ? Bs[cur][(kb + t) * LDN + cidx] : Bs[cur][cidx * LDK + kb + t];
+        const float b1 = B_KMAJOR ? Bs[cur][(kb + t + 4) * LDN + cidx] : Bs[cur][cidx * LDK + kb + t + 4];
+        tf32_split(b0, bh[ni][0], bl[ni][0]);
+        tf32_split(b1, bh[ni][1], bl[ni][1]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          mma_tf32(acc[mi][ni], al[mi], bh[ni]);   // small terms first
+          mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
+          mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+        }
+    }
+  }
+
+  // ---- epilogue: c0,c1 -> (row g, cols 2t, 2t+1); c2,c3 -> (row g+8, same cols) ----
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = m0 + wm * 32 + mi * 16 + g + half * 8;
+      if (r >= p.M) continue;
+      float* crow = p.C + map_row(p.cmap, r) * p.ldc;
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int col = n0 + wn * 16 + ni * 8 + 2 * t;
+        if (col >= p.N) continue;            // N even on this path
+        float x = acc[mi][ni][half * 2], y = acc[mi][ni][half * 2 + 1];
+        if (p.bias != nullptr && (!p.atomic_splitk || blockIdx.z == 0)) {
+          x += p.bias[col];
+          y += p.bias[col + 1];
+        }
+        if (p.atomic_splitk) {
+          red_add2(crow + col, x, y);
+        } else {
+          float2* dst = reinterpret_cast<float2*>(crow + col);
+          if (p.accumulate) {
+            const float2 old = *dst;
+            x += old.x;
+            y += old.y;
+          }
+          *dst = make_float2(x, y);
+        }
+      }
+    }
+}
+
 // C[i*ldc + j] (+)= sum_z part[z][i][j]
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int Mo,
                                      int No, float* __restrict__ C, int64_t ldc, int accumulate) {
@@ -344,6 +489,15 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = 
       grid.z = ceil_div(p.K, p.k_chunk);
       p.atomic_splitk = 1;
     }
+  }
+  const bool mma = p.mma_ok && !big && p.act == 0 && p.mask == nullptr && p.a_lo_off == 0 && p.w_lo_off == 0 &&
+                   p.vec_a && p.vec_w && p.K % 4 == 0 && p.N % 4 == 0 && p.ldc % 2 == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.C) & 7) == 0 && (p.k_chunk == 0 || p.atomic_splitk);
+  if (mma) {
+    if (nt) launch_k(gemm_mma_kernel<false>, grid, 256, 0, st, p);
+    else launch_k(gemm_mma_kernel<true>, grid, 256, 0, st, p);
+    CL_CHECK_LAUNCH("gemm_mma_kernel");
+    return CLIORA_OK;
   }
   if (nt) {
     if (big) launch_k(gemm_simt_kernel<8, false, false>, grid, 256, 0, st, p);

@@ -192,17 +192,16 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], mode == 1 ? S::A_BYTES + S::B_BYTES : S::STAGE_BYTES);
         uint8_t* s = smem + stage * S::STAGE_BYTES;
+        // each box holds the hi tile followed by the lo tile (1-part boxes in single-pass mode)
         tma_load_3d(s, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 0);
         tma_load_3d(s + 2 * S::A_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 0);
-        if (mode != 1) {   // single-pass TF32 never touches the remainder parts
-          tma_load_3d(s + S::A_BYTES, &tmA, &full[stage], kb * kBlockK, a_row0 + m0, 1);
-          tma_load_3d(s + 2 * S::A_BYTES + S::B_BYTES, &tmB, &full[stage], kb * kBlockK, n0, 1);
-        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(n_cur);
+      // (tried: A_hi x [W_hi; W_lo] as one UMMA of N = 2 * BLOCK_N, i.e. 2 instead of 3 UMMAs per k-step --
+      // measured 10 % slower per k-block than three N = 80 UMMAs, so not used)
       uint32_t acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int stage = kb % STAGES;
@@ -615,7 +614,7 @@ inline EncodeTiledFn encode_fn() {
 // Tensor map over a split pair [2, rows, K] (fp32, K contiguous, row pitch ld floats, part pitch part_stride
 // floats), box {32, box_rows, 1}, 128-byte swizzle, zero fill out of bounds.
 inline int make_pair_map(CUtensorMap* tm, const float* base, int64_t rows, int K, int64_t ld, int64_t part_stride,
-                         int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                         int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_parts = 1) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not available");
@@ -623,7 +622,7 @@ inline int make_pair_map(CUtensorMap* tm, const float* base, int64_t rows, int K
   }
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)part_stride * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, (cuuint32_t)box_parts};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -659,8 +658,11 @@ inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, 
                                  const TcEpilogue& ep, const char* tag, int mode) {
   using S = TcSmem<BLOCK_N, STAGES>;
   CUtensorMap tmA, tmB;
-  CL_TRY(make_pair_map(&tmA, A.base, A.rows, K, A.ld, A.part_stride, kBlockM));
-  CL_TRY(make_pair_map(&tmB, W.base, W.rows, K, W.ld, W.part_stride, BLOCK_N));
+  // one box carries the hi and the lo tile of an operand (they are adjacent in the stage buffer): 2 TMA
+  // operations per k-block instead of 4; the single-pass mode only ever needs the hi part
+  const int parts = mode == 1 ? 1 : 2;
+  CL_TRY(make_pair_map(&tmA, A.base, A.rows, K, A.ld, A.part_stride, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B, parts));
+  CL_TRY(make_pair_map(&tmB, W.base, W.rows, K, W.ld, W.part_stride, BLOCK_N, CU_TENSOR_MAP_SWIZZLE_128B, parts));
   static bool attr_set = false;
   if (!attr_set) {
     CL_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
