@@ -728,6 +728,7 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
     p.W = w->W_leaf; p.ldw = D;
     p.C = grad_x; p.ldc = D; p.cmap = dense_rows();
     p.M = B * n; p.N = D; p.K = D;
+    p.mma_ok = c.use_tc && g_debug[5] == 0;
     CL_TRY(launch_gemm(c.st, /*nt=*/false, p));
   }
   if (grads->W_leaf) CL_TRY(launch_gemm_tn(c.st, B * n, D, D, gu, D, x, D, grads->W_leaf, D, 0, scratch));

@@ -475,7 +475,10 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = 
   p.vec_w = aligned16(p.W) && (p.ldw % 4 == 0);
   p.vec_c = aligned16(p.C) && (p.ldc % 4 == 0);
   const int64_t ctas128 = (int64_t)ceil_div(p.M, 128) * ceil_div(p.N, kBN);
-  const bool big = ctas128 >= 2 * 148;
+  const bool mma = p.mma_ok && p.act == 0 && p.mask == nullptr && p.a_lo_off == 0 && p.w_lo_off == 0 &&
+                   p.vec_a && p.vec_w && p.K % 4 == 0 && p.N % 4 == 0 && p.ldc % 2 == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.C) & 7) == 0;
+  const bool big = !mma && ctas128 >= 2 * 148;     // the mma kernel always works on 64-row tiles
   ProfScope prof(st, p.tag ? p.tag : "gemm", 2.0 * p.M * p.N * p.K,
                  4.0 * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * (p.mask ? 2 : 1)));
   dim3 grid(ceil_div(p.N, kBN), ceil_div(p.M, big ? 128 : 64), 1);
@@ -490,9 +493,6 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = 
       p.atomic_splitk = 1;
     }
   }
-  const bool mma = p.mma_ok && !big && p.act == 0 && p.mask == nullptr && p.a_lo_off == 0 && p.w_lo_off == 0 &&
-                   p.vec_a && p.vec_w && p.K % 4 == 0 && p.N % 4 == 0 && p.ldc % 2 == 0 &&
-                   (reinterpret_cast<uintptr_t>(p.C) & 7) == 0 && (p.k_chunk == 0 || p.atomic_splitk);
   if (mma) {
     if (nt) launch_k(gemm_mma_kernel<false>, grid, 256, 0, st, p);
     else launch_k(gemm_mma_kernel<true>, grid, 256, 0, st, p);
