@@ -368,7 +368,10 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
     const float* obj = a.obj + (int64_t)b * a.R * a.D;
     for (int r = warp; r < a.R; r += nwarps) {
       float d = 0.f;
-      for (int j = lane; j < a.D; j += 32) d = fmaf(s_g[j], obj[(int64_t)r * a.D + j], d);
+      for (int j = lane * 4; j < a.D; j += 128) {     // 16-byte loads (D % 4 == 0)
+        const float4 gv = ld4(s_g + j), ov = ld4(obj + (int64_t)r * a.D + j);
+        d = fmaf(gv.x, ov.x, d); d = fmaf(gv.y, ov.y, d); d = fmaf(gv.z, ov.z, d); d = fmaf(gv.w, ov.w, d);
+      }
       d = warp_sum(d);
       if (lane == 0) {
         float sc = 1.f;
@@ -392,11 +395,17 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
     __syncthreads();
     // gq = ga2 + sum_r g_logit_r obj_r
     float qd = 0.f;
-    for (int j = tid; j < a.D; j += blockDim.x) {
-      float v = s_g[j];
-      for (int r = 0; r < a.R; ++r) v = fmaf(s_r0[r], obj[(int64_t)r * a.D + j], v);
-      s_g[j] = v;
-      qd = fmaf(s_q[j], v, qd);
+    for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
+      float4 v = ld4(s_g + j);
+#pragma unroll 6
+      for (int r = 0; r < a.R; ++r) {
+        const float w = s_r0[r];
+        const float4 ov = ld4(obj + (int64_t)r * a.D + j);
+        v.x = fmaf(w, ov.x, v.x); v.y = fmaf(w, ov.y, v.y); v.z = fmaf(w, ov.z, v.z); v.w = fmaf(w, ov.w, v.w);
+      }
+      st4(s_g + j, v);
+      const float4 qv = ld4(s_q + j);
+      qd = fmaf(qv.x, v.x, qd); qd = fmaf(qv.y, v.y, qd); qd = fmaf(qv.z, v.z, qd); qd = fmaf(qv.w, v.w, qd);
     }
     hd = block_sum(qd, s_red);
   }
