@@ -765,7 +765,7 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   if (grads->b1) CL_TRY(colsum(c.st, GPi, ldp, BC, D, grads->b1, 0, scratch));
   if (vl && grad_obj) {
     // cells split over grid.z so that the launch fills the GPU at small batch sizes
-    int zs = (int)((4 * 148 + (int64_t)ceil_div(D, 32) * B - 1) / ((int64_t)ceil_div(D, 32) * B));
+    int zs = (int)((8 * 148 + (int64_t)ceil_div(D, 32) * B - 1) / ((int64_t)ceil_div(D, 32) * B));
     if (zs > (int)((c.C + 15) / 16)) zs = (int)((c.C + 15) / 16);
     if (zs < 1) zs = 1;
     dim3 grid(ceil_div(D, 32), B, zs);

@@ -577,13 +577,13 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
                                                        const float* __restrict__ q, const float* __restrict__ coef,
                                                        float* __restrict__ g_obj, int accumulate) {
   pdl_prologue();
-  constexpr int RQ = (RMAX + 3) / 4;   // upper bound of regions per threadIdx.y
+  constexpr int RQ = RMAX / 4;         // upper bound of regions per threadIdx.y
   constexpr int CH = 16;               // cells per chunk
-  const int rq = (R + 3) / 4;          // regions per threadIdx.y for this R (balanced over the 4 thread rows)
+  const int rq = ((R + 15) / 16) * 4;  // regions per threadIdx.y, a multiple of 4 so coefficients are read 16 bytes at a time
   const int b = blockIdx.y;
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  __shared__ float s_c[CH][2 * RMAX];
+  __shared__ __align__(16) float s_c[CH][2 * RMAX];   // [cell][patt_r (r < RMAX) | g_logit_r], zero padded
   float acc[RQ];
 #pragma unroll
   for (int i = 0; i < RQ; ++i) acc[i] = 0.f;
@@ -594,9 +594,10 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
   for (int64_t c0 = c_begin; c0 < c_end; c0 += CH) {
     const int nc = (int)min((int64_t)CH, c_end - c0);
     __syncthreads();
-    for (int t = tid; t < nc * 2 * R; t += 128) {
-      const int cc = t / (2 * R), k = t % (2 * R);
-      s_c[cc][k] = coef[((int64_t)b * C + c0 + cc) * 2 * R + k];
+    for (int t = tid; t < CH * 2 * RMAX; t += 128) {
+      const int cc = t / (2 * RMAX), k = t % (2 * RMAX);
+      const int half = k / RMAX, r = k % RMAX;
+      s_c[cc][k] = (cc < nc && r < R) ? coef[((int64_t)b * C + c0 + cc) * 2 * R + half * R + r] : 0.f;
     }
     float gv[CH], qv[CH];
 #pragma unroll
@@ -607,13 +608,18 @@ __global__ __launch_bounds__(128) void obj_grad_kernel(int D, int R, int64_t C, 
       qv[cc] = ok ? q[cell * D + j] : 0.f;
     }
     __syncthreads();
+    if (r0 < R) {
 #pragma unroll
-    for (int cc = 0; cc < CH; ++cc) {
-      if (cc < nc) {
+      for (int cc = 0; cc < CH; ++cc) {
 #pragma unroll
-        for (int i = 0; i < RQ; ++i) {
-          const int r = r0 + i;
-          if (i < rq && r < R) acc[i] = fmaf(s_c[cc][r], gv[cc], fmaf(s_c[cc][R + r], qv[cc], acc[i]));
+        for (int i = 0; i < RQ; i += 4) {
+          if (i < rq) {
+            const float4 pa = ld4(&s_c[cc][r0 + i]), gl = ld4(&s_c[cc][RMAX + r0 + i]);
+            acc[i + 0] = fmaf(pa.x, gv[cc], fmaf(gl.x, qv[cc], acc[i + 0]));
+            acc[i + 1] = fmaf(pa.y, gv[cc], fmaf(gl.y, qv[cc], acc[i + 1]));
+            acc[i + 2] = fmaf(pa.z, gv[cc], fmaf(gl.z, qv[cc], acc[i + 2]));
+            acc[i + 3] = fmaf(pa.w, gv[cc], fmaf(gl.w, qv[cc], acc[i + 3]));
+          }
         }
       }
     }
