@@ -140,8 +140,10 @@ struct TcSmem {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const TcEpilogue ep, int a_row0, int M, int N, int K, int mode) {
+                  const TcEpilogue ep, int a_row0, int M, int N, int K, int mode_in) {
   pdl_prologue();
+  const int mode = mode_in & 0xff;              // bit 8: allocate only the TMEM columns the mode needs
+  const bool small_tmem = (mode_in & 0x100) != 0;
   using S = TcSmem<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -158,7 +160,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // accumulator sets: kSets x (main, cross); consecutive k-steps rotate over the sets so back-to-back UMMAs
   // never depend on each other's TMEM write-back, and each accumulator sees 1/kSets of the truncating adds
   constexpr int kSets = (6 * BLOCK_N <= 512) ? 3 : ((4 * BLOCK_N <= 512) ? 2 : 1);
-  constexpr uint32_t TMEM_COLS = tmem_cols(2 * kSets * BLOCK_N);
+  // TMEM columns: (main, cross) accumulators; the rotating-set mode 3 needs kSets of them.  Allocating only what the
+  // mode uses lets two CTAs (e.g. one per sentence chain) share an SM's 512 columns.
+  const uint32_t TMEM_COLS = (mode == 3 || !small_tmem) ? tmem_cols(2 * kSets * BLOCK_N) : tmem_cols(2 * BLOCK_N);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -644,7 +648,9 @@ struct PairRef {            // a split-pair operand in global memory
 // Two tile configurations.  Wide (256 columns, 2 stages): 21.8 MAC per shared-memory byte read by the UMMAs, main +
 // cross accumulators fill the 512 TMEM columns -- used whenever the narrow grid would exceed one wave.  Narrow (80
 // columns, 4 stages): 5 CTAs per 128 rows at N = 400, more SMs busy on the small chart levels.
-constexpr int kTcNarrowN = 80, kTcNarrowStages = 4;   // (2 stages / 2 CTAs per SM was tried: the tile is smem-bound, no gain)
+extern int g_tc_narrow_stages;   // debug knob: pipeline depth of the narrow tile (2 default, 3, 4)
+extern int g_tc_small_tmem;   // debug knob: narrow-tile CTAs allocate 256 instead of 512 TMEM columns (two per SM possible)
+constexpr int kTcNarrowN = 80, kTcNarrowStages = 3;   // (2 stages / 2 CTAs per SM was tried: the tile is smem-bound, no gain)
 constexpr int kTcWideN = 256, kTcWideStages = 2;
 constexpr int kTcMidN = 160, kTcMidStages = 3;       // 216 KB: A tile reused over 2x the columns of narrow, 3 stages
 
@@ -671,7 +677,8 @@ inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, 
   }
   dim3 grid(ceil_div(N, ep.n_stride > 0 ? ep.n_stride : BLOCK_N), ceil_div(M, kBlockM));
   ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
-  launch_k(tc_gemm_nt_kernel<BLOCK_N, STAGES>, grid, kThreads, S::TOTAL, st, tmA, tmB, ep, a_row0, M, N, K, mode);
+  launch_k(tc_gemm_nt_kernel<BLOCK_N, STAGES>, grid, kThreads, S::TOTAL, st, tmA, tmB, ep, a_row0, M, N, K,
+           mode | (g_tc_small_tmem ? 0x100 : 0));
   CL_CHECK_LAUNCH("tc_gemm_nt_kernel");
   return CLIORA_OK;
 }
@@ -692,6 +699,8 @@ inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, cons
   if (cfg != 1 && mode == 3) mode = 2;   // only the narrow tile has room for rotating accumulator sets
   if (cfg == 3) return launch_tc_gemm_nt_cfg<kTcMidN, kTcMidStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
   if (cfg == 2) return launch_tc_gemm_nt_cfg<kTcWideN, kTcWideStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
+  if (g_tc_narrow_stages == 4) return launch_tc_gemm_nt_cfg<kTcNarrowN, 4>(st, A, a_row0, W, M, N, K, ep, tag, mode);
+  if (g_tc_narrow_stages == 3) return launch_tc_gemm_nt_cfg<kTcNarrowN, 3>(st, A, a_row0, W, M, N, K, ep, tag, mode);
   return launch_tc_gemm_nt_cfg<kTcNarrowN, kTcNarrowStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
 }
 
