@@ -65,8 +65,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources() if os.path.exists(s))
 
 
+def build_pytrees(force: bool = False) -> str:
+    """Compile the CPython helper that turns backpointer tables into nested tuples (host glue, plain gcc)."""
+    import sysconfig
+    src = os.path.join(_HERE, 'csrc', 'pytrees.c')
+    out = os.path.join(_HERE, '_pytrees' + (sysconfig.get_config_var('EXT_SUFFIX') or '.so'))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cmd = [os.environ.get('CC', 'gcc'), '-O2', '-shared', '-fPIC', '-I' + sysconfig.get_paths()['include'], src,
+           '-o', out]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('gcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/api.cu for sm_100a into cliora_b200/libcliora_b200.so (nvcc cross-compiles without a GPU)."""
+    build_pytrees(force)
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get('NVCC', 'nvcc')

@@ -77,6 +77,17 @@ def span_f1(diora, gold_spans):
     return out
 
 
+def trees_from_table(bp, n):
+    """List of nested-tuple trees from an int32 [B, cells] backpointer tensor: one device->host copy, then the
+    CPython helper (csrc/pytrees.c); falls back to the Python recursion if the helper was not built."""
+    host = bp.to('cpu', torch.int32).contiguous()
+    try:
+        from .. import _pytrees
+    except ImportError:
+        return [tree_from_backpointers(r, n) for r in host.tolist()]
+    return _pytrees.build(host.numpy(), host.shape[0], n)
+
+
 class ParsePredictor(object):
     def __init__(self, net):
         self.net = net
@@ -84,8 +95,7 @@ class ParsePredictor(object):
     def parse_batch(self, batch_map):
         n = batch_map['sentences'].shape[1]
         bp, _ = backpointers(self.net)
-        rows = bp.cpu().tolist()           # the single device->host transfer
-        return [tree_from_backpointers(r, n) for r in rows]
+        return trees_from_table(bp, n)      # the single device->host transfer
 
     def parse_spans(self, batch_map=None):
         """Predicted constituent spans as a device tensor [B, n-1, 2] (no host tree building)."""
