@@ -311,7 +311,7 @@ __global__ __launch_bounds__(256) void gemm_simt_kernel(const GemmParams p) {
 // tcgen05 kernel's fixed cost (TMEM allocation, descriptor fetch, first TMA round trip, ~6 us) and its operand
 // pair format buy nothing there, while the fp32 FMA pipe caps the SIMT kernel.  A row-major [M,K] with RowMap;
 // W is [N,K] (B_KMAJOR = false, "NT") or [K,N] (B_KMAJOR = true, "NN").  No activation / mask.
-// 64x64x16 tiles, 8 warps as 2 (m) x 4 (n), warp tile 32x16.  Shared tiles are laid out so that every
+// 64x64x16 tiles, 4 warps as 2 (m) x 2 (n), warp tile 32x32.  Shared tiles are laid out so that every
 // fragment load is bank-conflict free: [row][k] with stride 20, or [k][n] with stride 72.
 // ------------------------------------------------------------------------------------------
 CL_D void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
@@ -329,48 +329,54 @@ CL_D void red_add2(float* p, float x, float y) {
 }
 
 template <bool B_KMAJOR>
-__global__ __launch_bounds__(256) void gemm_mma_kernel(const GemmParams p) {
+__global__ __launch_bounds__(128) void gemm_mma_kernel(const GemmParams p) {
   pdl_prologue();
+  // 4 warps as 2 (m) x 2 (n), warp tile 32x32: every fragment value is split (cvt, sub, cvt) by the warp that
+  // loads it, so the split cost per MMA falls with the warp tile (ncu on the 8-warp / 32x16 version: issue slots
+  // 58 % busy, legacy tensor pipe 36 % -- instruction-issue bound by the splitting, not by the MMAs)
   constexpr int BM = 64, LDK = kBK + 4, LDN = kBN + 8, ST = 4;   // 4-stage cp.async pipeline
   __shared__ __align__(16) float As[ST][BM][LDK];
   __shared__ __align__(16) float Bs[ST][B_KMAJOR ? kBK * LDN : kBN * LDK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp >> 1, wn = warp & 1;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * kBN;
   int k_begin = 0, k_end = p.K;
   if (p.k_chunk > 0) {
     k_begin = blockIdx.z * p.k_chunk;
     k_end = min(p.K, k_begin + p.k_chunk);
   }
-  // one 16-byte asynchronous copy of A and one of W per thread per k-tile (zero fill outside the matrix)
-  const int a_r = tid >> 2, a_q = (tid & 3) * 4;
-  const bool a_ok = m0 + a_r < p.M;
-  const float* a_src = a_ok ? p.A + map_row(p.amap, m0 + a_r) * p.lda : p.A;
-  const int b_r = B_KMAJOR ? tid >> 4 : tid >> 2;             // k row, or n row
-  const int b_q = B_KMAJOR ? (tid & 15) * 4 : (tid & 3) * 4;  // n quad, or k quad
-  const bool b_ok = B_KMAJOR ? (n0 + b_q < p.N) : (n0 + b_r < p.N);   // N % 4 == 0 on this path
+  // two 16-byte asynchronous copies of A and two of W per thread per k-tile (zero fill outside the matrix)
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto issue = [&](int kt) {
     const int buf = kt % ST, k0 = k_begin + kt * kBK;
-    float* da = &As[buf][a_r][a_q];
-    if (a_ok && k0 + a_q < k_end) cp_async16(da, a_src + k0 + a_q);      // K % 4 == 0, chunks % 16 == 0
-    else st4(da, zero4);
-    if (!B_KMAJOR) {
-      float* db = &Bs[buf][b_r * LDK + b_q];
-      if (b_ok && k0 + b_q < k_end) cp_async16(db, p.W + (int64_t)(n0 + b_r) * p.ldw + k0 + b_q);
-      else st4(db, zero4);
-    } else {
-      float* db = &Bs[buf][b_r * LDN + b_q];
-      if (b_ok && k0 + b_r < k_end) cp_async16(db, p.W + (int64_t)(k0 + b_r) * p.ldw + n0 + b_q);
-      else st4(db, zero4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int idx = tid + h * 128;
+      const int a_r = idx >> 2, a_q = (idx & 3) * 4;
+      float* da = &As[buf][a_r][a_q];
+      if (m0 + a_r < p.M && k0 + a_q < k_end)       // K % 4 == 0, chunks % 16 == 0
+        cp_async16(da, p.A + map_row(p.amap, m0 + a_r) * p.lda + k0 + a_q);
+      else
+        st4(da, zero4);
+      if (!B_KMAJOR) {
+        const int b_r = idx >> 2, b_q = (idx & 3) * 4;       // n row, k quad
+        float* db = &Bs[buf][b_r * LDK + b_q];
+        if (n0 + b_r < p.N && k0 + b_q < k_end) cp_async16(db, p.W + (int64_t)(n0 + b_r) * p.ldw + k0 + b_q);
+        else st4(db, zero4);
+      } else {
+        const int b_r = idx >> 4, b_q = (idx & 15) * 4;      // k row, n quad (N % 4 == 0 on this path)
+        float* db = &Bs[buf][b_r * LDN + b_q];
+        if (n0 + b_q < p.N && k0 + b_r < k_end) cp_async16(db, p.W + (int64_t)(k0 + b_r) * p.ldw + n0 + b_q);
+        else st4(db, zero4);
+      }
     }
   };
-  float acc[2][2][4];
+  float acc[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
@@ -388,7 +394,7 @@ __global__ __launch_bounds__(256) void gemm_mma_kernel(const GemmParams p) {
     cp_async_commit();
 #pragma unroll
     for (int kb = 0; kb < kBK; kb += 8) {
-      uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         const int r = wm * 32 + mi * 16 + g;
@@ -398,8 +404,8 @@ __global__ __launch_bounds__(256) void gemm_mma_kernel(const GemmParams p) {
         tf32_split(As[cur][r + 8][kb + t + 4], ah[mi][3], al[mi][3]);
       }
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        const int cidx = wn * 16 + ni * 8 + g;
+      for (int ni = 0; ni < 4; ++ni) {
+        const int cidx = wn * 32 + ni * 8 + g;
         const float b0 = B_KMAJOR ? Bs[cur][(kb + t) * LDN + cidx] : Bs[cur][cidx * LDK + kb + t];
         const float b1 = B_KMAJOR ? Bs[cur][(kb + t + 4) * LDN + cidx] : Bs[cur][cidx * LDK + kb + t + 4];
         tf32_split(b0, bh[ni][0], bl[ni][0]);
@@ -408,7 +414,7 @@ __global__ __launch_bounds__(256) void gemm_mma_kernel(const GemmParams p) {
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni) {
+        for (int ni = 0; ni < 4; ++ni) {
           mma_tf32(acc[mi][ni], al[mi], bh[ni]);   // small terms first
           mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
           mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
@@ -425,8 +431,8 @@ __global__ __launch_bounds__(256) void gemm_mma_kernel(const GemmParams p) {
       if (r >= p.M) continue;
       float* crow = p.C + map_row(p.cmap, r) * p.ldc;
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        const int col = n0 + wn * 16 + ni * 8 + 2 * t;
+      for (int ni = 0; ni < 4; ++ni) {
+        const int col = n0 + wn * 32 + ni * 8 + 2 * t;
         if (col >= p.N) continue;            // N even on this path
         float x = acc[mi][ni][half * 2], y = acc[mi][ni][half * 2 + 1];
         if (p.bias != nullptr && (!p.atomic_splitk || blockIdx.z == 0)) {
@@ -494,8 +500,8 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = 
     }
   }
   if (mma) {
-    if (nt) launch_k(gemm_mma_kernel<false>, grid, 256, 0, st, p);
-    else launch_k(gemm_mma_kernel<true>, grid, 256, 0, st, p);
+    if (nt) launch_k(gemm_mma_kernel<false>, grid, 128, 0, st, p);
+    else launch_k(gemm_mma_kernel<true>, grid, 128, 0, st, p);
     CL_CHECK_LAUNCH("gemm_mma_kernel");
     return CLIORA_OK;
   }
