@@ -25,7 +25,8 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 int g_pdl = env_int("CLIORA_PDL", 0);
-namespace tc { int g_tc_small_tmem = 0; int g_tc_narrow_stages = kTcNarrowStages; }
+int g_splitk_target = 4 * 148;
+namespace tc { int g_tc_xnarrow = env_int("CLIORA_TC_XNARROW", 0); int g_tc_small_tmem = 0; int g_tc_narrow_stages = kTcNarrowStages; }
 // One shared-memory carveout for every kernel of the library: the tcgen05 GEMMs need the maximum carveout, and an
 // SM has to drain before it can switch configuration, so mixed carveouts serialise neighbouring kernels.
 int g_carveout = env_int("CLIORA_CARVEOUT", 100);
@@ -1015,7 +1016,9 @@ void cliora_debug_set(int key, int value) {
   if (key == 100) { g_pdl = value ? 1 : 0; return; }
   if (key == 101) { g_carveout = value; return; }
   if (key == 102) { tc::g_tc_small_tmem = value; return; }
-  if (key == 103) { tc::g_tc_narrow_stages = value; return; }      // preferred shared-memory carveout, percent (-1: leave)   // programmatic dependent launch on/off
+  if (key == 103) { tc::g_tc_narrow_stages = value; return; }
+  if (key == 104) { g_splitk_target = value; return; }
+  if (key == 105) { tc::g_tc_xnarrow = value; return; }      // preferred shared-memory carveout, percent (-1: leave)   // programmatic dependent launch on/off
   if (key >= 0 && key < 8) g_debug[key] = value;
 }
 

@@ -34,6 +34,7 @@ struct GemmParams {
   int mma_ok;                  // caller allows the 3xTF32 mma.sync kernel (fp32-grade, not bit-exact fp32 FMA order)
 };
 
+extern int g_splitk_target;   // CTAs a small GEMM is split up to along K (default 4 x 148: 296 / 444 / 592 measured 5814 / 5834 / 5837 sent/s)
 constexpr int kBN = 64;
 constexpr int kBK = 16;
 
@@ -491,7 +492,7 @@ inline int launch_gemm(cudaStream_t st, bool nt, GemmParams p, bool atomic_ok = 
   if (atomic_ok && !big && p.act == 0 && p.mask == nullptr) {
     const int ctas = grid.x * grid.y;
     const int ktiles = ceil_div(p.K, kBK);
-    int splits = (2 * 148 + ctas - 1) / ctas;
+    int splits = (g_splitk_target + ctas - 1) / ctas;
     if (splits > ktiles / 4) splits = ktiles / 4;   // at least 4 k-tiles (64 k) per split
     if (splits > 1) {
       p.k_chunk = ceil_div(ktiles, splits) * kBK;

@@ -648,6 +648,8 @@ struct PairRef {            // a split-pair operand in global memory
 // Two tile configurations.  Wide (256 columns, 2 stages): 21.8 MAC per shared-memory byte read by the UMMAs, main +
 // cross accumulators fill the 512 TMEM columns -- used whenever the narrow grid would exceed one wave.  Narrow (80
 // columns, 4 stages): 5 CTAs per 128 rows at N = 400, more SMs busy on the small chart levels.
+extern int g_tc_xnarrow;         // 1: allow the 128x48 tile for one-wave launches
+constexpr int kTcXNarrowN = 48;
 extern int g_tc_narrow_stages;   // debug knob: pipeline depth of the narrow tile (2 default, 3, 4)
 extern int g_tc_small_tmem;   // debug knob: narrow-tile CTAs allocate 256 instead of 512 TMEM columns (two per SM possible)
 constexpr int kTcNarrowN = 80, kTcNarrowStages = 3;   // (2 stages / 2 CTAs per SM was tried: the tile is smem-bound, no gain)
@@ -695,7 +697,13 @@ inline int launch_tc_gemm_nt(cudaStream_t st, const PairRef& A, int a_row0, cons
     auto cost = [&](int bn, double t_cta) { return ceil_div((int64_t)mt * ceil_div(N, bn), 148) * t_cta * kscale; };
     const double cn = cost(kTcNarrowN, 16.5), cm = cost(kTcMidN, 22.0), cw = cost(kTcWideN, 32.0);
     cfg = (cn <= cm && cn <= cw) ? 1 : (cm <= cw ? 3 : 2);
+    // extra-narrow 128x48 tiles for launches that still fit one wave with them (small chart levels): less W per
+    // k-block and shorter UMMAs per CTA, i.e. a shorter critical path when SMs would otherwise idle
+    if (cfg == 1 && g_tc_xnarrow && ep.n_stride == 0 && ep.gmax == nullptr &&
+        (int64_t)mt * ceil_div(N, kTcXNarrowN) <= 148)
+      cfg = 4;
   }
+  if (cfg == 4) return launch_tc_gemm_nt_cfg<kTcXNarrowN, 4>(st, A, a_row0, W, M, N, K, ep, tag, mode);
   if (cfg != 1 && mode == 3) mode = 2;   // only the narrow tile has room for rotating accumulator sets
   if (cfg == 3) return launch_tc_gemm_nt_cfg<kTcMidN, kTcMidStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
   if (cfg == 2) return launch_tc_gemm_nt_cfg<kTcWideN, kTcWideStages>(st, A, a_row0, W, M, N, K, ep, tag, mode);
