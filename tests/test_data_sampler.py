@@ -49,3 +49,26 @@ def test_negative_sampler_matches_reference(case):
 def test_freq_dist():
     f = calculate_freq_dist([[0, 1, 1], [3, 1]], 5)
     assert f.tolist() == [1, 3, 0, 1, 0] and f.dtype == np.float32
+
+
+@pytest.mark.parametrize('size,ngpus', [(32, 2), (32, 8), (7, 2), (9, 4), (5, 1)])
+def test_shard_before_loading_equals_chunk_after_loading(size, ngpus):
+    """The rank's slice of the index list == what the reference keeps after torch.chunk on the loaded batch
+    (batch_iterator.py:52-66,134-136), for every rank."""
+    import torch
+    from cliora_b200.data import shard_indices
+    index = [100 + i for i in range(size)]
+    loaded = torch.arange(size) + 100
+    pieces = torch.chunk(loaded, ngpus, dim=0)
+    for rank in range(len(pieces)):
+        assert shard_indices(index, ngpus, rank) == pieces[rank].tolist()
+    got = [i for rank in range(ngpus) for i in shard_indices(index, ngpus, rank)]
+    assert got == index          # a partition of the batch, in order
+
+
+def test_feature_store_has_no_cpu_path():
+    import numpy as np
+    from cliora_b200.data import RegionFeatureStore
+    with pytest.raises(RuntimeError):
+        RegionFeatureStore(np.zeros((4, 8), np.float32), np.zeros((4, 4), np.float32), np.array([[0, 4]]),
+                           device='cpu')
