@@ -62,3 +62,44 @@ def test_cpu_tensors_are_rejected_not_computed():
     m = DioraMLP(8)
     with pytest.raises(_lib.ClioraError):
         m(torch.randn(2, 3, 8), None)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under cliora_b200/ (nor bench.py outside its CPU legs) may import
+    it, and nothing in the product reads /root/reference at run time."""
+    import ast
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for dirpath, _, files in os.walk(os.path.join(root, 'cliora_b200')):
+        for f in files:
+            if not f.endswith('.py'):
+                continue
+            path = os.path.join(dirpath, f)
+            src = open(path).read()
+            for node in ast.walk(ast.parse(src)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or '']
+                if any(n == 'oracle' or n.startswith('oracle.') for n in names):
+                    offenders.append(path)
+            if '/root/reference' in src:
+                offenders.append(path + ' (reads /root/reference)')
+    assert offenders == []
+
+
+def test_layout_struct_matches_header():
+    """The ctypes mirror of cliora_layout lists exactly the int64 fields the header declares, in order."""
+    import os
+    import re
+    from cliora_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, 'include', 'cliora_b200.h')).read()
+    body = re.search(r'typedef struct cliora_layout \{(.*?)\} cliora_layout;', hdr, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in re.findall(r'int64_t\s+([^;]+);', body):
+        fields += [x.strip() for x in decl.split(',')]
+    assert fields == [name for name, _ in _lib.Layout._fields_]
