@@ -236,7 +236,7 @@ class Trainer(object):
         torch.nn.utils.clip_grad_norm_(params, 5.0)
         self.optimizer.step()
 
-    def capture(self, batch_map, warmup=3):
+    def capture(self, batch_map, warmup=3, pool=None):
         """Capture one training step for the shapes of ``batch_map`` into CUDA graph(s).
 
         The step is ~500 dependent small kernels at batch 32 / length 20; replaying a graph removes the
@@ -250,12 +250,20 @@ class Trainer(object):
         self.net.train()
         dev = next(self.net.parameters()).device
         self._static = {k: (v.to(dev).clone() if torch.is_tensor(v) else v) for k, v in batch_map.items()}
+        # The chart module keeps the last step's (autograd-connected) outputs, which keeps the parameters'
+        # AccumulateGrad nodes alive -- bound to whatever stream that step ran on.  If that was the legacy default
+        # stream, a captured backward would have to make it wait on the capturing stream, which CUDA forbids.
+        # Dropping those outputs lets the warm-up below re-create the nodes on its side stream.
+        self._drop_autograd_state()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        self._warmup_loss = None
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 out = self.run_net(self._static, None, compute_loss=True)
-                self.gradient_update(out['total_loss'].mean(dim=0).sum())
+                self._warmup_loss = out['total_loss'].mean(dim=0).sum()
+                self.gradient_update(self._warmup_loss)
+                self._warmup_loss = self._warmup_loss.detach()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         split = self.grad_sync is not None
@@ -263,7 +271,8 @@ class Trainer(object):
         self._graph_opt = torch.cuda.CUDAGraph() if split else None
         self.optimizer.zero_grad(set_to_none=True)
         before = _lib.launch_count()
-        with torch.cuda.graph(self._graph):
+        gkw = {} if pool is None else {'pool': pool}
+        with torch.cuda.graph(self._graph, **gkw):
             out = self.run_net(self._static, None, compute_loss=True)
             self._static_loss = out['total_loss'].mean(dim=0).sum()
             if split:
@@ -274,9 +283,67 @@ class Trainer(object):
         self.launches_per_step = _lib.launch_count() - before   # library kernels baked into the graph
         if split:
             self.grad_sync()
-            with torch.cuda.graph(self._graph_opt):
+            with torch.cuda.graph(self._graph_opt, **gkw):
                 self._optimizer_update()
+        self._graph_grads = [p.grad for p in self.net.parameters() if p.requires_grad]
+        self._static_loss = self._static_loss.detach()     # only its value is read from here on
         return self
+
+    def _drop_autograd_state(self):
+        d = self.net.diora
+        d.reset()
+        d._run = None
+
+    # ---- graph replay for a stream of batches whose shape varies (length-bucketed training) ----
+    _GRAPH_STATE = ('_static', '_graph', '_graph_opt', '_static_loss', '_static_out', 'launches_per_step',
+                    '_graph_grads')
+
+    @staticmethod
+    def _shape_key(batch_map):
+        return tuple((k, tuple(v.shape)) for k, v in sorted(batch_map.items()) if torch.is_tensor(v))
+
+    def step_auto(self, batch_map, capture_after=2, max_graphs=64):
+        """One training step on a batch of any shape, replaying a CUDA graph whenever one exists for that shape.
+
+        The reference's sampler yields one sentence length per batch (cliora/data/dataloader.py:11-113), so a
+        training run sees a few dozen distinct shapes over and over.  A shape is run eagerly until it has been seen
+        ``capture_after`` times; that occurrence runs eagerly once more and is then captured, and later
+        occurrences replay the graph.  All graphs share one memory pool (they are replayed one at a time and each
+        is self-contained), so device memory is the maximum over shapes, not the sum.  Returns the total loss as
+        a 0-d device tensor (a copy: valid until you drop it)."""
+        if not hasattr(self, '_graphs'):
+            self._graphs, self._seen, self._active_key = {}, {}, None
+            self._pool = torch.cuda.graph_pool_handle()
+            self._auto_stream = torch.cuda.Stream(device=next(self.net.parameters()).device)
+        key = self._shape_key(batch_map)
+        entry = self._graphs.get(key)
+        if entry is None:
+            seen = self._seen[key] = self._seen.get(key, 0) + 1
+            if seen < capture_after or len(self._graphs) >= max_graphs:
+                self._active_key = None
+                # eager steps run on a side stream too: autograd state created on the legacy default stream
+                # could not take part in a later capture (see capture())
+                cur = torch.cuda.current_stream()
+                self._auto_stream.wait_stream(cur)
+                with torch.cuda.stream(self._auto_stream):
+                    loss = self.step(batch_map, train=True, sync_result=False)['total_loss']
+                cur.wait_stream(self._auto_stream)
+                loss.record_stream(cur)
+                return loss
+            self.__dict__.pop('_stage', None)            # prefetch slots belong to one captured shape
+            self.capture(batch_map, warmup=1, pool=self._pool)    # the warm-up step IS this batch's training step
+            self._graphs[key] = {k: getattr(self, k) for k in self._GRAPH_STATE}
+            self._active_key = key
+            return self._warmup_loss.clone()
+        if self._active_key != key:
+            self.__dict__.pop('_stage', None)
+            for k, v in entry.items():
+                setattr(self, k, v)
+            params = [p for p in self.net.parameters() if p.requires_grad]
+            for prm, g in zip(params, entry['_graph_grads']):   # the tensors this graph's backward writes and
+                prm.grad = g                                    # the eager all-reduce (data parallel) reads
+            self._active_key = key
+        return self.step_graphed(batch_map).clone()
 
     def prefetch(self, batch_map):
         """Start the host->device copy of a (pinned) batch on a side stream into one of two staging slots and

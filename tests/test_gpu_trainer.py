@@ -178,3 +178,28 @@ def test_torch_adam_path_still_works():
     l1 = tr.step_graphed(b).item()
     l2 = tr.step_graphed(b).item()
     assert l2 < l1          # same batch twice: the update must reduce its loss
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_step_auto_replays_per_shape_graphs(split):
+    """A stream of batches with varying (batch, length): step_auto runs a shape eagerly, captures it on its
+    second occurrence and replays afterwards; losses follow the eager trainer step for step.  ``split`` puts a
+    (dummy) gradient-sync hook in, i.e. the data-parallel two-graph form with per-graph gradient tensors."""
+    shapes = [(6, 7), (4, 5), (6, 3)]
+    order = [0, 1, 0, 2, 0, 1, 1, 2, 0, 2, 1, 0]
+    batches = [_batch(B=shapes[s][0], n=shapes[s][1], seed=i) for i, s in enumerate(order)]
+    eager, auto = _trainer(), _trainer()
+    calls = []
+    if split:
+        auto.grad_sync = lambda: calls.append(1)
+    for tr in (eager, auto):
+        tr.net.diora.atten_head.dropout.p = 0.0
+    auto.net.load_state_dict({k: v.clone() for k, v in eager.net.state_dict().items()})
+    la = [eager.step(x, train=True, sync_result=False)['total_loss'].item() for x in batches]
+    lb = [auto.step_auto(x).item() for x in batches]
+    assert len(auto._graphs) == 3
+    for i, (x, y) in enumerate(zip(la, lb)):
+        # Adam amplifies fp noise on near-zero gradients, so the trajectories drift apart slowly
+        assert abs(x - y) <= (2e-4 + 2e-3 * i) * abs(x), (i, la, lb)
+    if split:
+        assert len(calls) == len(batches) + 3      # one per step, plus one during each capture
