@@ -1,5 +1,5 @@
-"""CPU restatement of the reference's visual batch assembly.  TEST INFRASTRUCTURE ONLY: nothing under
-cliora_b200/ may import this.
+"""CPU restatement of the reference's visual batch assembly.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py):
+nothing under cliora_b200/ may import this.
 
 ``flickr_item`` follows FlickrDataset.__getitem__ (cliora/data/dataloader.py:205-222) on the arrays that class
 reads from its HDF5 file; ``collate`` follows collate_fn + the rank partition
