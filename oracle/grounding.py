@@ -5,9 +5,9 @@ The reference has no function for it: the logic is inlined in its eval loops
 (cliora/scripts/parse.py:174-212 and cliora/scripts/train.py:158-179, two spellings of the same selection).
 ``ground_phrases`` follows parse.py line by line on CPU tensors; ``ground_phrases_train_py`` follows train.py;
 tests check the two agree and pin ``box_iou`` against torchvision.ops.box_iou (what the reference calls).
-Pinning status: the IoU arithmetic is pinned to the reference's dependency bit for bit; the word/region
-selection has no importable reference function to run (it lives inside the scripts' eval loops), so it is
-pinned only by the agreement of the two spellings restated here.
+Pinning: tests/golden/grounding.pt holds the outputs of the reference's own scoring blocks, cut out of the
+unmodified script files and executed on seeded inputs (tests/golden/make_golden_grounding.py);
+tests/test_grounding.py checks this restatement against them, and the IoU arithmetic against torchvision.
 """
 import torch
 

@@ -70,3 +70,31 @@ def test_grounding_no_phrases():
     phrases, gts = flatten_targets([({}, None), ({}, None)])
     sel, iou, hit = grounding_eval(torch.randn(2, 4, 5).cuda(), torch.rand(2, 5, 4).cuda(), phrases, gts)
     assert sel.shape == (0, 2) and iou.numel() == 0 and hit.numel() == 0
+
+
+def test_oracle_matches_reference_code_golden():
+    """tests/golden/grounding.pt was produced by executing the reference's own scoring blocks (cut out of
+    scripts/parse.py and scripts/train.py, see make_golden_grounding.py): the oracle must reproduce them."""
+    import os
+    cases = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'grounding.pt'), weights_only=False)
+    assert sum(c['recall_num'] for c in cases) > 0 and sum(c['total_num'] - c['recall_num'] for c in cases) > 0
+    for c in cases:
+        got = og.ground_phrases(c['atten'], c['boxes'], c['targets'])
+        per_sentence = [[] for _ in c['targets']]
+        for bid, s, e, _, _, _, hit in got:
+            per_sentence[bid].append(((s, e - 1), hit))
+        assert per_sentence == c['ground_res']
+        assert sum(g[6] for g in got) == c['recall_num'] and len(got) == c['total_num']
+
+
+@pytest.mark.gpu
+def test_grounding_kernel_vs_reference_code_golden():
+    import os
+    from cliora_b200.analysis.grounding import grounding_recall
+    cases = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'grounding.pt'), weights_only=False)
+    for c in cases:
+        class _D:
+            atten_score = c['atten'].cuda()
+        rec, tot, res = grounding_recall(_D, {'VG_GT': c['targets'], 'boxes': c['boxes']})
+        assert (rec, tot) == (c['recall_num'], c['total_num'])
+        assert res == c['ground_res']
