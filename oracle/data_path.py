@@ -5,6 +5,8 @@ nothing under cliora_b200/ may import this.
 reads from its HDF5 file; ``collate`` follows collate_fn + the rank partition
 (cliora/data/batch_iterator.py:116-138).  The HDF5/pickle/json lookups in front (img_id -> feat_index,
 class name -> id) are replaced by already-resolved integer arrays; there is no arithmetic in them to pin.
+Pinning: tests/golden/datapath.npz holds what the reference's own FlickrDataset.__getitem__ returned on a small
+seeded table (tests/golden/make_golden_datapath.py); tests/test_data_sampler.py checks ``flickr_item`` against it.
 """
 import numpy as np
 import torch

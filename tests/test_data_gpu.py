@@ -101,3 +101,17 @@ def test_batch_iterator_feeds_trainer():
     trainer = _trainer(D=D, V=V, k_neg=7)
     losses = [trainer.step(bm)['total_loss'] for bm in it.get_iterator()]
     assert len(losses) == 4 and all(np.isfinite(l) for l in losses)
+
+
+@pytest.mark.gpu
+def test_gather_regions_vs_reference_golden():
+    """The gather kernel reproduces what the reference's own FlickrDataset.__getitem__ returned (golden)."""
+    import os
+    from cliora_b200.data import RegionFeatureStore
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'datapath.npz'))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    store = RegionFeatureStore(g['features'], g['bboxes'], g['pos'], g['classes'], regions=36)
+    obj, bx, ct = store.gather(g['image_index'])
+    assert torch.equal(obj.cpu(), g['obj_feats'])
+    assert torch.equal(bx.cpu(), g['boxes'])
+    assert torch.equal(ct.cpu(), g['obj_cates'])

@@ -72,3 +72,17 @@ def test_feature_store_has_no_cpu_path():
     with pytest.raises(RuntimeError):
         RegionFeatureStore(np.zeros((4, 8), np.float32), np.zeros((4, 4), np.float32), np.array([[0, 4]]),
                            device='cpu')
+
+
+def test_datapath_oracle_matches_reference_getitem():
+    """tests/golden/datapath.npz: outputs of the reference's own FlickrDataset.__getitem__
+    (tests/golden/make_golden_datapath.py); the oracle's restatement must reproduce them exactly."""
+    import os
+    import torch
+    from oracle import data_path as od
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'datapath.npz'))
+    items = [od.flickr_item(z['features'], z['bboxes'], z['pos'], z['classes'], int(i)) for i in z['image_index']]
+    want = od.collate([[0]] * 64, list(range(len(items))), items)
+    assert torch.equal(want['obj_feats'], torch.from_numpy(z['obj_feats']))
+    assert torch.equal(want['boxes'], torch.from_numpy(z['boxes']))
+    assert torch.equal(want['obj_cates'], torch.from_numpy(z['obj_cates']))
