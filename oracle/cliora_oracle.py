@@ -15,7 +15,9 @@ Parity pinning: ``tests/golden/make_golden.py`` imports the unmodified
 reference in the build container, runs it on seeded inputs and commits the
 outputs (chart tensors, losses, gradients, CKY trees, index tensors) as
 fixtures; ``tests/test_oracle_vs_golden.py`` checks this oracle against every
-one of them.  The reference ships no tests or golden vectors of its own
+one of them, and ``tests/test_oracle_step_golden.py`` checks ``CpuClioraStep``
+against three steps of the reference's own ``build_net`` + ``Trainer.step``
+(``tests/golden/make_golden_step.py``).  The reference ships no tests or golden vectors of its own
 (SURVEY.md section 4), so those fixtures are the pin.
 """
 from __future__ import annotations
