@@ -203,3 +203,34 @@ def test_step_auto_replays_per_shape_graphs(split):
         assert abs(x - y) <= (2e-4 + 2e-3 * i) * abs(x), (i, la, lb)
     if split:
         assert len(calls) == len(batches) + 3      # one per step, plus one during each capture
+
+
+def test_product_trainer_matches_reference_trainer_golden():
+    """tests/golden/train_step.pt: three Trainer.step calls of the UNMODIFIED reference (build_net, CPU).  The
+    product's build_net loads the reference's state_dict as is (same keys) and must reproduce the losses of all
+    three steps (steps 2 and 3 depend on the clip+Adam updates) and the updated weights."""
+    import os
+    from cliora_b200.net.trainer import build_net
+    g = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'train_step.pt'), weights_only=False)
+    opts = argparse.Namespace(arch='mlp', hidden_dim=g['D'], k_neg=g['K'], margin=1.0, vl_margin=g['vl_margin'],
+                              alpha_contr=g['alpha_contr'], alpha_vg=g['alpha_vg'], vg_loss=True, use_contr=True,
+                              use_contr_ce=False, obj_feats=True, normalize='unit', share=True, cuda=True,
+                              lr=g['lr'])
+    tr = build_net(opts, torch.nn.Embedding(g['V'], g['E']))
+    tr.net.load_state_dict(g['init'], strict=True)
+    for i, s in enumerate(g['steps']):
+        batch = {k: v.cuda() for k, v in s['batch'].items()}
+        batch.update(batch_size=batch['sentences'].shape[0], length=batch['sentences'].shape[1])
+        tr.net.train()
+        tr.net.diora.set_dropout_mask(s['keep'].cuda())
+        res = tr.step(batch, train=True)
+        for k, v in s['result'].items():
+            assert res[k] == pytest.approx(v, rel=5e-4, abs=1e-5), (i, k, res, s['result'])
+    lr = g['lr']
+    sd = tr.net.state_dict()
+    for k, ref in g['final'].items():
+        if k == 'img_encoder.fc_vis.bias':      # zero true gradient: Adam amplifies rounding noise (see the oracle test)
+            continue
+        d = (sd[k].cpu() - ref).abs()
+        assert float(d.max()) <= 3 * 2 * lr + 1e-6, k     # hard bound: at most lr per step per element, both ways
+        assert float(d.mean()) <= 0.1 * lr, k
