@@ -313,7 +313,17 @@ int cliora_matmul_tn(int M, int Ka, int Kb, const float* A, const float* B, floa
  *   C[M,N] = act(A[M,K] W[N,K]^T + bias)   with fp32-grade accuracy (~1e-6 of max)
  * ---------------------------------------------------------------------- */
 int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_t stream);
-/* Development knob (key 0: accumulation mode of the tensor-core GEMM). */
+/* Development / measurement knobs (process-global; defaults are what ships):
+ *   0  accumulation mode of the tcgen05 GEMM (2 = cross terms in a second TMEM accumulator [default], 0 = single
+ *      accumulator, 1 = plain TF32, 3 = rotating accumulator sets)
+ *   1  1 = every GEMM on the exact-fp32 SIMT kernel (no tensor cores)
+ *   2  tcgen05 tile: 0 = cost model, 1 = 128x80, 2 = 128x256, 3 = 128x160
+ *   3  vision-language cell kernels: bit 0 = block-per-cell forward, bit 1 = block-per-cell backward (default 2)
+ *   4  1 = bias gradient db2 from the full GY rows instead of the per-cell sums
+ *   5  1 = per-cell GEMMs on the fp32 SIMT kernel instead of the mma.sync 3xTF32 kernel
+ * 100  programmatic dependent launch on/off (default off)      101  shared-memory carveout percent (default 100)
+ * 102  1 = narrow tcgen05 tile allocates 256 TMEM columns       103  narrow tile pipeline depth (2, 3 [default], 4)
+ * 104  CTA target of the small-GEMM split-K (default 4 x 148)   105  1 = allow the 128x48 tcgen05 tile */
 void cliora_debug_set(int key, int value);
 int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pair, const float* bias, int act,
                      float* C, cliora_stream_t stream);
