@@ -196,6 +196,53 @@ class Trainer(object):
         self.ngpus = ngpus
         self.grad_sync = None     # set by cliora_b200.parallel for data-parallel runs
 
+    # ---- bookkeeping helpers of the reference Trainer (trainer.py:350-435), same names and file format ----
+    def freeze_diora(self):
+        for p in self.net.diora.parameters():
+            p.requires_grad = False
+
+    def freeze_except_vis(self):
+        for name, p in self.net.named_parameters():
+            if '_vis' not in name:
+                p.requires_grad = False
+
+    def parameter_norm(self, requires_grad=True, diora=False):
+        net = self.net.diora if diora else self.net
+        return sum(p.norm().item() for p in net.parameters() if p.requires_grad or not requires_grad)
+
+    @staticmethod
+    def get_single_net(net):
+        return getattr(net, 'module', net) if isinstance(net, torch.nn.parallel.DistributedDataParallel) else net
+
+    def save_model(self, save_emb, model_file):
+        """``{'state_dict': ...}`` like the reference (trainer.py:382-397); ``save_emb=False`` leaves the (frozen,
+        large) embedding tables out.  Files are interchangeable with the reference's in both directions."""
+        state = {k: v for k, v in self.net.state_dict().items() if save_emb or 'embeddings' not in k}
+        torch.save({'state_dict': state}, model_file)
+
+    @staticmethod
+    def load_model(origin_emb, net, model_file):
+        """Load a checkpoint written by either implementation (trainer.py:399-435): a DDP ``module.`` prefix is
+        stripped, unknown keys are dropped, embedding tables are kept from ``net`` unless ``origin_emb``, missing
+        ``*_vis`` tensors outside the image encoder start from their non-visual twin, anything else missing keeps
+        its current value."""
+        target = Trainer.get_single_net(net)
+        own = target.state_dict()
+        loaded = torch.load(model_file, map_location='cpu')['state_dict']
+        loaded = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in loaded.items()}
+        loaded = {k: v for k, v in loaded.items() if k in own}
+        present = set(loaded)
+        for k in own:
+            if not origin_emb and 'embeddings' in k:
+                loaded[k] = own[k]
+            elif k not in present:
+                twin = k.replace('_vis', '')
+                if '_vis' in k and 'img_encoder' not in k and twin in loaded:
+                    loaded[k] = loaded[twin]
+                else:
+                    loaded[k] = own[k]
+        target.load_state_dict(loaded)
+
     def init_optimizer(self, optimizer_cls=optim.Adam, optimizer_kwargs=None, fused=None):
         """Adam(lr, betas, eps) like the reference (trainer.py:580).  On CUDA the default is the library's fused
         clip(5.0)+Adam (three launches for all tensors, cliora_b200/optim.py); ``fused=False`` keeps torch's."""
@@ -412,14 +459,22 @@ def build_net(options, embeddings=None, random_seed=None):
         from .cliora import DioraMLP as Diora
     else:
         from .diora import DioraMLP as Diora
-    embedding_layer = embeddings
-    if options.obj_feats:
-        embedding_layer.weight.requires_grad = False
+    emb_kind = getattr(options, 'emb', 'none')
+    origin_emb = emb_kind == 'none'
+    if origin_emb:
+        embedding_layer = embeddings
+        if options.obj_feats:     # fine-tuning CLIORA from DIORA keeps the word table frozen (trainer.py:538-541)
+            embedding_layer.weight.requires_grad = False
+    else:                         # pretrained vectors: frozen table, row 0 is padding (trainer.py:542-546)
+        table = torch.from_numpy(embeddings) if emb_kind == 'skip' and not torch.is_tensor(embeddings) else embeddings
+        embedding_layer = nn.Embedding.from_pretrained(table, freeze=True, padding_idx=0)
     embed = Embed(embedding_layer, input_size=embedding_layer.weight.size(1), size=size)
     image_encoder = ImageEncoder(input_size=2048, size=size)
     diora = Diora(size, outside=True, normalize=options.normalize, compress=False, share=options.share)
     loss_funcs = get_loss_funcs(options, embedding_layer)
     net = Net(embed, image_encoder, diora, obj_feats=options.obj_feats, visualize=False, loss_funcs=loss_funcs)
+    if getattr(options, 'load_model_path', None) is not None:
+        Trainer.load_model(origin_emb, net, options.load_model_path)
     if options.cuda:
         net.cuda()
         diora.cuda()
