@@ -434,6 +434,17 @@ class Trainer(object):
             self._graph_opt.replay()
         return self._static_loss
 
+    def prepare_info(self, batch_map):
+        return {}
+
+    def prepare_result(self, batch_map, model_output):
+        """trainer.py:456-463: batch size, length and every ``*loss*`` entry as a Python float."""
+        result = {'batch_size': batch_map['batch_size'], 'length': batch_map['length']}
+        for k, v in model_output.items():
+            if 'loss' in k:
+                result[k] = v.mean(dim=0).sum().item()
+        return result
+
     def step(self, batch_map, idx2word=None, train=True, compute_loss=True, sync_result=True):
         self.net.train() if train else self.net.eval()
         with torch.set_grad_enabled(train):

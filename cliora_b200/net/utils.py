@@ -27,3 +27,11 @@ class BatchInfo(object):
     def __init__(self, **kwargs):
         for k, v in kwargs.items():
             setattr(self, k, v)
+
+
+def __getattr__(name):
+    # the reference keeps ImageEncoder in cliora/net/utils.py:37-55; here it lives next to the fused GEMM wrappers
+    if name == 'ImageEncoder':
+        from .trainer import ImageEncoder
+        return ImageEncoder
+    raise AttributeError(name)

@@ -81,3 +81,27 @@ def test_checkpoints_interchange_with_the_reference(tmp_path):
     ref.Trainer.load_model(True, theirs.net, p2)                      # this implementation's file -> reference
     for (k, x), (_, y) in zip(mine.net.state_dict().items(), theirs.net.state_dict().items()):
         assert torch.equal(x, y), k
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/cliora'), reason='needs the reference checkout')
+def test_public_surface_matches_the_reference():
+    """Every public name of the reference's trainer/net classes exists here, except the ones INTEGRATION.md lists
+    as fused away or out of scope."""
+    sys.path.insert(0, '/root/reference')
+    import cliora.net.cliora as rc
+    import cliora.net.diora as rd
+    import cliora.net.trainer as rt
+    import cliora_b200.net.cliora as mc
+    import cliora_b200.net.diora as md
+    import cliora_b200.net.trainer as mt
+    import cliora_b200.net.utils as mu
+
+    def pub(o):
+        return {n for n in dir(o) if not n.startswith('_')}
+    fused = {'initialize_outside_root', 'inside_func', 'inside_pass', 'leaf_transform', 'outside_func', 'outside_pass'}
+    assert pub(rd.DioraMLP(16)) - pub(md.DioraMLP(16)) == fused
+    assert pub(rc.DioraMLP(16)) - pub(mc.DioraMLP(16)) == fused
+    for cls, allowed in [('Trainer', set()), ('Net', {'visualization'}), ('Embed', set()),
+                         ('ReconstructionSoftmaxLoss', set()), ('ContrastiveLoss', set()), ('VGLoss', set())]:
+        assert pub(getattr(rt, cls)) - pub(getattr(mt, cls)) == allowed, cls
+    assert mu.ImageEncoder is mt.ImageEncoder
