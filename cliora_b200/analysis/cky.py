@@ -88,9 +88,51 @@ def trees_from_table(bp, n):
     return _pytrees.build(host.numpy(), host.shape[0], n)
 
 
+def pack_scalars(scalars, B, n):
+    """The reference's per-cell score dict (``net.saved_scalars`` filled by the inside hook,
+    analysis/utils.py:78-95: ``scalars[level][pos]`` is ``[B, level]`` or ``[B, level, 1]``) as one flat tensor in
+    the CKY kernel's order: level blocks ``[B, n-level, level]`` one after the other, levels 1 .. n-1."""
+    parts = []
+    for level in range(1, n):
+        cells = [scalars[level][pos].reshape(B, level) for pos in range(n - level)]
+        parts.append(torch.stack(cells, 1).reshape(-1))
+    if not parts:
+        return torch.zeros(4, dtype=torch.float32)
+    return torch.cat(parts).to(torch.float32).contiguous()
+
+
 class ParsePredictor(object):
     def __init__(self, net):
         self.net = net
+
+    def batched_cky(self, batch_map, scalars):
+        """cky.py:31-99 for callers that bring their own score dict (e.g. ``net.saved_scalars`` after editing it):
+        the scores are packed and decoded by the same kernel ``parse_batch`` uses."""
+        B, n = batch_map['sentences'].shape[0], batch_map['sentences'].shape[1]
+        dev = self.net.device
+        scores = pack_scalars(scalars, B, n).to(dev)
+        # The kernel subtracts each cell's maximum itself, which is a no-op on hook-made scores (the hook already
+        # did it) but would change the result for scores that are not normalised that way: refuse those.
+        for level in range(1, n):
+            for pos in range(n - level):
+                if float(scalars[level][pos].reshape(B, level).max(1)[0].abs().max()) > 1e-6:
+                    raise NotImplementedError('batched_cky expects per-cell max-normalised scores (as saved by '
+                                              'override_inside_hook); got a cell whose maximum is not 0')
+        C = n * (n + 1) // 2
+        bp = torch.empty(B, C, device=dev, dtype=torch.int32)
+        best = torch.empty(B, C, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cliora_cky(B, n, ptr(scores), ptr(bp), ptr(best), _lib.stream()), 'cliora_cky')
+        return trees_from_table(bp, n)
+
+    def follow_backpointers(self, bp, pair):
+        """cky.py:101-109 on the reference's own backpointer structure (``bp[level][pos]`` = pair of (level, pos)
+        children, ints at the leaves)."""
+        if isinstance(pair, int):
+            return pair
+        left, right = pair
+        return (self.follow_backpointers(bp, bp[left[0]][left[1]]),
+                self.follow_backpointers(bp, bp[right[0]][right[1]]))
 
     def parse_batch(self, batch_map):
         n = batch_map['sentences'].shape[1]

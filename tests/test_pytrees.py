@@ -42,3 +42,38 @@ def test_c_helper_rejects_bad_input():
         _pytrees.build(torch.full((1, 3), 7, dtype=torch.int32).numpy(), 1, 2)     # backpointer out of range
     with pytest.raises(ValueError):
         _pytrees.build(torch.zeros(2, dtype=torch.int32).numpy(), 1, 3)            # buffer too small
+
+
+def _cky_scalar_cases():
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'cky_scalars.pt'), weights_only=False)
+
+
+def test_pack_scalars_layout_against_reference_batched_cky():
+    """tests/golden/cky_scalars.pt: trees the reference's own ParsePredictor produced from a score dict.  Packing
+    that dict into the kernel's flat layout and decoding with the oracle's CKY must give the same trees - this pins
+    the layout batched_cky() hands to the kernel (the kernel itself is bit-exact against the oracle on the GPU)."""
+    from cliora_b200.analysis.cky import pack_scalars
+    from oracle import cliora_oracle as O
+    for c in _cky_scalar_cases():
+        B, n = c['B'], c['n']
+        flat = pack_scalars(c['scalars'], B, n)
+        scores, o = {}, 0
+        for level in range(1, n):
+            rows = B * (n - level) * level
+            scores[level] = flat[o:o + rows].reshape(B, n - level, level, 1)
+            o += rows
+        assert o == flat.numel()
+        _, bp = O.cky_backpointers(scores, B, n)
+        assert [O.tree_from_backpointers(bp[b].tolist(), n) for b in range(B)] == c['trees']
+
+
+@pytest.mark.gpu
+def test_batched_cky_from_scalars_vs_reference_golden():
+    from cliora_b200.analysis.cky import ParsePredictor
+    import types
+    for c in _cky_scalar_cases():
+        net = types.SimpleNamespace(device=torch.device('cuda', 0))
+        scalars = {l: {p: t.cuda() for p, t in d.items()} for l, d in c['scalars'].items()}
+        trees = ParsePredictor(net).batched_cky({'sentences': torch.zeros(c['B'], c['n'], dtype=torch.int64)}, scalars)
+        assert trees == c['trees']
