@@ -86,3 +86,30 @@ def test_datapath_oracle_matches_reference_getitem():
     assert torch.equal(want['obj_feats'], torch.from_numpy(z['obj_feats']))
     assert torch.equal(want['boxes'], torch.from_numpy(z['boxes']))
     assert torch.equal(want['obj_cates'], torch.from_numpy(z['obj_cates']))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/cliora'), reason='needs the reference checkout')
+def test_sampler_matches_reference_live_on_random_configurations():
+    """Beyond the committed golden cases: 40 random (data set, batch size, maxlen, length_to_size, include_partial)
+    configurations against the reference class itself, two epochs each (the random stream carries over)."""
+    import sys
+    import types
+    sys.modules.setdefault('h5py', types.ModuleType('h5py'))
+    sys.path.insert(0, '/root/reference')
+    from cliora.data.dataloader import FixedLengthBatchSampler as RefSampler, SimpleDataset
+    rng = np.random.RandomState(123)
+    for trial in range(40):
+        count = int(rng.randint(1, 300))
+        lo = int(rng.randint(1, 6))
+        hi = lo + int(rng.randint(0, 25))
+        sents = [list(range(int(l))) for l in rng.randint(lo, hi + 1, size=count)]
+        kw = dict(batch_size=int(rng.randint(1, 40)), include_partial=bool(rng.randint(0, 2)),
+                  maxlen=[None, 0, int(rng.randint(lo, hi + 2))][int(rng.randint(0, 3))],
+                  length_to_size=[None, {int(rng.randint(2, 15)): int(rng.randint(1, 20)),
+                                         int(rng.randint(15, 30)): int(rng.randint(1, 10))}][int(rng.randint(0, 2))])
+        seed = int(rng.randint(0, 1000))
+        ref = RefSampler(SimpleDataset(sents), rng=np.random.RandomState(seed), **kw)
+        mine = FixedLengthBatchSampler(sents, rng=np.random.RandomState(seed), **kw)
+        for _ in range(2):
+            assert [list(map(int, b)) for b in ref] == [list(b) for b in mine], (trial, kw)
+            assert len(ref) == len(mine)
