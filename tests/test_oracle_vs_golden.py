@@ -131,3 +131,64 @@ def test_cky_trees(golden):
     for level, s in blob['split_scores'].items():
         assert rel_err(out.split_scores[level], s) < TOL
     assert O.cky_trees(out.split_scores, blob['B'], blob['n']) == blob['trees']
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/cliora'), reason='needs the reference checkout')
+@pytest.mark.parametrize('B,n,D,R,share,seed', [(2, 3, 8, 0, True, 1), (1, 12, 20, 0, False, 2), (3, 8, 36, 7, True, 3),
+                                                (2, 10, 16, 36, True, 4), (5, 4, 12, 1, True, 5),
+                                                (2, 16, 24, 0, True, 6)])
+def test_oracle_against_the_imported_reference_live(B, n, D, R, share, seed):
+    """Beyond the committed fixtures: the oracle next to the unmodified reference modules (imported from
+    /root/reference, eval mode) on further shapes - chart tensors, alignment tensors and every gradient."""
+    import sys
+    sys.path.insert(0, '/root/reference')
+    if R:
+        from cliora.net.cliora import DioraMLP
+        m = DioraMLP(D, outside=True, normalize='unit', compress=False, share=share)
+    else:
+        from cliora.net.diora import DioraMLP
+        m = DioraMLP(D, outside=True, normalize='unit', compress=False, share=share)
+    torch.manual_seed(seed)
+    m.reset_parameters() if hasattr(m, 'reset_parameters') else None
+    m.eval()
+    g = torch.Generator().manual_seed(seed + 100)
+    x = torch.randn(B, n, D, generator=g, requires_grad=True)
+    xw = torch.randn(B, n, D, generator=g, requires_grad=True)
+    obj = (0.3 * torch.randn(B, max(R, 1), D, generator=g)).requires_grad_()
+    objw = (0.3 * torch.randn(B, max(R, 1), D, generator=g)).requires_grad_()
+    if R:
+        m(x, xw, obj, objw)
+    else:
+        m(x, xw)
+    names = ('inside_h', 'inside_s', 'outside_h', 'outside_s')
+    ct = {k: torch.randn(getattr(m, k).shape, generator=g) for k in names}
+    loss = sum((getattr(m, k) * ct[k]).sum() for k in names)
+    if R:
+        loss = loss + (m.all_atten_score * 0.01).sum() + (m.vg_atten_score * 0.01).sum()
+    loss.backward()
+
+    P = _share_alias({k: v.detach().clone().requires_grad_() for k, v in m.state_dict().items()
+                      if not (share and k.startswith('outside_'))}, share)
+    x2, xw2 = x.detach().clone().requires_grad_(), xw.detach().clone().requires_grad_()
+    obj2, objw2 = obj.detach().clone().requires_grad_(), objw.detach().clone().requires_grad_()
+    out = O.chart_forward(P, x2, obj2 if R else None, None)
+    for k in names:
+        assert rel_err(getattr(out, k), getattr(m, k)) < TOL, k
+    loss2 = sum((getattr(out, k) * ct[k]).sum() for k in names)
+    if R:
+        aas = O.all_atten_score(out.inside_h, out.outside_h, obj2)
+        vg = O.vg_atten_score(xw2, objw2, training=False, all_atten=aas)
+        assert rel_err(aas, m.all_atten_score) < TOL and rel_err(vg, m.vg_atten_score) < TOL
+        loss2 = loss2 + (aas * 0.01).sum() + (vg * 0.01).sum()
+    loss2.backward()
+    assert rel_err(x2.grad, x.grad) < 1e-4
+    if R:
+        assert rel_err(obj2.grad, obj.grad) < 1e-4 and rel_err(objw2.grad, objw.grad) < 1e-4
+        assert rel_err(xw2.grad, xw.grad) < 1e-4
+    for k, p in m.named_parameters():
+        if share and k.startswith('outside_'):
+            continue
+        if p.grad is None:
+            assert P[k].grad is None or float(P[k].grad.abs().max()) == 0.0, k
+        else:
+            assert rel_err(P[k].grad, p.grad) < 1e-4, k
