@@ -137,6 +137,15 @@ def main():
     ap.add_argument('--debug-set', default='', help='dev knobs: comma list of key=value passed to cliora_debug_set')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ and args.impl != 'reference':
+        # called plainly with --gpus N (the driver launches torch.distributed.run itself): start one rank per GPU
+        import socket
+        with socket.socket() as sk:
+            sk.bind(('127.0.0.1', 0))
+            port = sk.getsockname()[1]
+        os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node',
+                                   str(args.gpus), '--master-addr', '127.0.0.1', '--master-port', str(port),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
     cfg = dict(CFG, B=args.batch, n=args.length)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
