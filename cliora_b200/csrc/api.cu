@@ -2,6 +2,7 @@
 // Host-side orchestration only: level loops, buffer carving, kernel launches on the caller's stream.
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <mutex>
 #include <utility>
 
@@ -18,7 +19,7 @@
 
 namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 Profiler g_prof;
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -30,18 +31,38 @@ namespace tc { int g_tc_xnarrow = env_int("CLIORA_TC_XNARROW", 0); int g_tc_smal
 // One shared-memory carveout for every kernel of the library: the tcgen05 GEMMs need the maximum carveout, and an
 // SM has to drain before it can switch configuration, so mixed carveouts serialise neighbouring kernels.
 int g_carveout = env_int("CLIORA_CARVEOUT", 100);
+namespace {
+struct AttrKey {
+  int dev;
+  const void* kern;
+  int attr;
+  bool operator<(const AttrKey& o) const {
+    if (dev != o.dev) return dev < o.dev;
+    if (kern != o.kern) return kern < o.kern;
+    return attr < o.attr;
+  }
+};
+std::mutex g_attr_mu;
+std::map<AttrKey, int> g_attr_done;
+}  // namespace
+cudaError_t func_attr_at_least(const void* kern, cudaFuncAttribute attr, int value) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_attr_mu);
+  auto it = g_attr_done.find(AttrKey{dev, kern, (int)attr});
+  if (it != g_attr_done.end() && it->second >= value) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, attr, value);
+  if (e == cudaSuccess) g_attr_done[AttrKey{dev, kern, (int)attr}] = value;
+  return e;
+}
 void apply_carveout(const void* kern) {
-  static std::mutex mu;
-  static std::vector<std::pair<const void*, int>> done;
-  std::lock_guard<std::mutex> lock(mu);
-  for (auto& d : done)
-    if (d.first == kern) {
-      if (d.second == g_carveout) return;
-      d.second = g_carveout;
-      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
-      return;
-    }
-  done.emplace_back(kern, g_carveout);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_attr_mu);
+  auto key = AttrKey{dev, kern, (int)cudaFuncAttributePreferredSharedMemoryCarveout};
+  auto it = g_attr_done.find(key);
+  if (it != g_attr_done.end() && it->second == g_carveout) return;
+  g_attr_done[key] = g_carveout;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
 }
 int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums, [5] = 1: per-cell GEMMs on the fp32 SIMT kernel instead of mma.sync 3xTF32
@@ -344,11 +365,9 @@ static int launch_cell_aggregate(const Ctx& c, const CellArgs& a) {
   if (VL && a.D <= 128 * kColT && (g_debug[3] & 1) == 0) {
     // warp per cell, 8 cells of one sentence per CTA, the image's regions staged once in shared memory
     const size_t smem = ((size_t)a.R * a.D + (size_t)kCellsPerCta * a.N) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      CL_CUDA(cudaFuncSetAttribute(cell_fwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    if (smem > 48 * 1024)
+      CL_CUDA(func_attr_at_least(reinterpret_cast<const void*>(cell_fwd_warp_kernel<true>),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int chunks = ceil_div(a.L, kCellsPerCta);
     launch_k(cell_fwd_warp_kernel<true>, a.B * chunks, kCellThreads, smem, c.st, a);
     CL_CHECK_LAUNCH("cell_fwd_warp_kernel");
@@ -374,11 +393,9 @@ static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g, float* cellsum) {
   ProfScope prof(c.st, "cell_bwd", 4.0 * rows * g.c.D, 4.0 * (2.0 * rows * (g.c.D + 2) + 3.0 * g.c.B * g.c.L * g.c.D));
   if (VL && g.c.D <= 128 * kColT && (g_debug[3] & 2) == 0) {
     const size_t smem = ((size_t)g.c.R * g.c.D + (size_t)kCellsPerCta * g.c.D + 32) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      CL_CUDA(cudaFuncSetAttribute(cell_bwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    if (smem > 48 * 1024)
+      CL_CUDA(func_attr_at_least(reinterpret_cast<const void*>(cell_bwd_warp_kernel<true>),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int chunks = ceil_div(g.c.L, kCellsPerCta);
     launch_k(cell_bwd_warp_kernel<true>, g.c.B * chunks, kCellThreads, smem, c.st, g);
     CL_CHECK_LAUNCH("cell_bwd_warp_kernel");

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/cliora_b200.h"
@@ -128,10 +129,13 @@ struct LaunchCtx {
   int status = CLIORA_OK;
 };
 extern thread_local char g_last_cuda_error[256];
-extern long long g_launch_count;
+extern std::atomic<long long> g_launch_count;
 extern int g_pdl;   // 1: launch kernels with the programmatic-stream-serialization attribute
 extern int g_carveout;   // >= 0: preferred shared-memory carveout (percent) applied to every kernel once
 void apply_carveout(const void* kern);
+// cudaFuncSetAttribute is per device: raise an attribute of `kern` to at least `value` on the CURRENT device, once
+// (the cache is keyed by device, kernel and attribute, so a process that drives several GPUs configures each).
+cudaError_t func_attr_at_least(const void* kern, cudaFuncAttribute attr, int value);
 
 inline int record_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));

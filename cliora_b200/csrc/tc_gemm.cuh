@@ -671,12 +671,8 @@ inline int launch_tc_gemm_nt_cfg(cudaStream_t st, const PairRef& A, int a_row0, 
   const int parts = mode == 1 ? 1 : 2;
   CL_TRY(make_pair_map(&tmA, A.base, A.rows, K, A.ld, A.part_stride, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B, parts));
   CL_TRY(make_pair_map(&tmB, W.base, W.rows, K, W.ld, W.part_stride, BLOCK_N, CU_TENSOR_MAP_SWIZZLE_128B, parts));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CL_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 S::TOTAL));
-    attr_set = true;
-  }
+  CL_CUDA(func_attr_at_least(reinterpret_cast<const void*>(tc_gemm_nt_kernel<BLOCK_N, STAGES>),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   dim3 grid(ceil_div(N, ep.n_stride > 0 ? ep.n_stride : BLOCK_N), ceil_div(M, kBlockM));
   ProfScope prof(st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N));
   launch_k(tc_gemm_nt_kernel<BLOCK_N, STAGES>, grid, kThreads, S::TOTAL, st, tmA, tmB, ep, a_row0, M, N, K,
@@ -743,12 +739,8 @@ inline int launch_tc_gemm_tn(cudaStream_t st, const PairRef& A, const PairRef& B
   CUtensorMap tmA, tmB;
   CL_TRY(make_pair_map_mn(&tmA, A.base, A.rows, Ka, A.ld, A.part_stride));
   CL_TRY(make_pair_map_mn(&tmB, B.base, B.rows, Kb, B.ld, B.part_stride));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CL_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<kTnBlockN, kTnStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 S::TOTAL));
-    attr_set = true;
-  }
+  CL_CUDA(func_attr_at_least(reinterpret_cast<const void*>(tc_gemm_tn_kernel<kTnBlockN, kTnStages>),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const int splits = tn_tc_splits(rows, Ka, Kb);
   int per = ceil_div(ceil_div(rows, kTnBlockK), splits) * kTnBlockK;
   if (per < kTnBlockK) per = kTnBlockK;

@@ -4,6 +4,8 @@ reference's cliora/net/trainer.py and cliora/net/utils.py:37-55, built on the fu
 Class names, constructor arguments, ``forward`` signatures, returned ``(loss, dict)`` pairs and
 ``state_dict`` keys follow the reference so ``build_net`` / ``Trainer.step`` callers keep working.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.optim as optim
@@ -313,7 +315,9 @@ class Trainer(object):
                 self._warmup_loss = self._warmup_loss.detach()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        split = self.grad_sync is not None
+        # data parallel: by default the all-reduce stays between two graphs; CLIORA_GRAPH_ALLREDUCE=1 captures the
+        # NCCL call inside the one step graph instead (no eager gap between backward and clip+Adam)
+        split = self.grad_sync is not None and os.environ.get('CLIORA_GRAPH_ALLREDUCE', '0') != '1'
         self._graph = torch.cuda.CUDAGraph()
         self._graph_opt = torch.cuda.CUDAGraph() if split else None
         self.optimizer.zero_grad(set_to_none=True)
@@ -329,7 +333,8 @@ class Trainer(object):
             self._static_out = {k: v.detach() for k, v in out.items() if 'loss' in k}
         self.launches_per_step = _lib.launch_count() - before   # library kernels baked into the graph
         if split:
-            self.grad_sync()
+            # no collective here: the captured backward has not run, its gradient tensors hold garbage, and a
+            # rank that captures while its peers replay would pair this call with their real all-reduce
             with torch.cuda.graph(self._graph_opt, **gkw):
                 self._optimizer_update()
         self._graph_grads = [p.grad for p in self.net.parameters() if p.requires_grad]

@@ -38,37 +38,55 @@ class FusedClipAdam(object):
                     p.grad.zero_()
 
     def _bind(self):
-        """(Re)build the device table when gradient tensors appear or move."""
-        for p in self.params:
+        """(Re)build the device table when gradient tensors appear or move, or the set of trainable tensors changes
+        (a parameter frozen after construction -- Trainer.freeze_diora / freeze_except_vis -- is skipped, like
+        torch's Adam skips tensors without a gradient: no moment update, no drift on old momentum)."""
+        active = [i for i, p in enumerate(self.params) if p.requires_grad]
+        for i in active:
+            p = self.params[i]
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
-        ptrs = [p.grad.data_ptr() for p in self.params]
-        if self._grads == ptrs:
+        key = (tuple(active), tuple(self.params[i].grad.data_ptr() for i in active))
+        if self._grads == key:
             return
-        n = len(self.params)
+        n = len(active)
+        self._n_active = n
+        if n == 0:
+            self._grads = key
+            return
         L = _lib.lib()
         arr = lambda vals: (ctypes.c_void_p * n)(*vals)
-        numel = (ctypes.c_int64 * n)(*[p.numel() for p in self.params])
+        numel = (ctypes.c_int64 * n)(*[self.params[i].numel() for i in active])
         nbytes = int(L.cliora_adam_table_bytes(n))
-        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)   # pinned: the copy below is graph-capturable
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing or getattr(self, '_host_eager', None) is None:
+            host = torch.empty(int(L.cliora_adam_table_bytes(len(self.params))), dtype=torch.uint8, pin_memory=True)
+            if capturing:
+                self._host_tables.append(host)   # a captured graph re-reads its staging copy on every replay
+            else:
+                self._host_eager = host          # eager rebinds reuse one pinned table (copied synchronously)
+        else:
+            host = self._host_eager
         total = ctypes.c_int64(0)
-        check(L.cliora_adam_table_fill(n, arr([p.data_ptr() for p in self.params]), arr(ptrs),
-                                       arr([t.data_ptr() for t in self.exp_avg]),
-                                       arr([t.data_ptr() for t in self.exp_avg_sq]), numel, host.data_ptr(),
+        check(L.cliora_adam_table_fill(n, arr([self.params[i].data_ptr() for i in active]), arr(list(key[1])),
+                                       arr([self.exp_avg[i].data_ptr() for i in active]),
+                                       arr([self.exp_avg_sq[i].data_ptr() for i in active]), numel, host.data_ptr(),
                                        ctypes.byref(total)), 'cliora_adam_table_fill')
         dev = self.params[0].device
-        self._host_tables.append(host)
-        self._table.copy_(host, non_blocking=True)
+        self._table[:nbytes].copy_(host[:nbytes], non_blocking=capturing)
         self._blocks = int(total.value)
-        if getattr(self, '_scratch', None) is None:
+        if getattr(self, '_scratch', None) is None or self._scratch.numel() < self._blocks:
             self._scratch = torch.empty(self._blocks, device=dev, dtype=torch.float32)
-        self._grads = ptrs
+        self._grads = key
 
     @torch.no_grad()
     def step(self):
         self._bind()
+        if self._n_active == 0:
+            return
+        self.lr = float(self.param_groups[0]['lr'])     # schedulers / manual changes write param_groups
         with torch.cuda.device(self.params[0].device):
-            check(_lib.lib().cliora_adam_step(self._table.data_ptr(), len(self.params), self._blocks, self.lr,
+            check(_lib.lib().cliora_adam_step(self._table.data_ptr(), self._n_active, self._blocks, self.lr,
                                               self.betas[0], self.betas[1], self.eps, self.max_norm,
                                               self.state.data_ptr(), self._scratch.data_ptr(), _lib.stream()),
                   'cliora_adam_step')

@@ -400,17 +400,19 @@ class CpuClioraStep(object):
     Used ONLY as bench.py's cpu_baseline / ``--impl reference`` arm and by tests as a checker."""
 
     def __init__(self, D=400, E=1024, V=8000, F=2048, k_neg=100, seed=1234, lr=2e-3, obj_feats=True,
-                 alpha_vg=1.0, alpha_contr=1.0, margin=0.2, device='cpu'):
-        # device != 'cpu' runs the same dense eager formulation on that device (the "stock PyTorch on the same
+                 alpha_vg=1.0, alpha_contr=1.0, margin=0.2, device='cpu', dtype=torch.float32):
+        # dtype=torch.float64 makes this step the arbiter for gradient checks at deep charts (same values, drawn
+        # in float32 and widened).  device != 'cpu' runs the same dense eager formulation on that device (the "stock PyTorch on the same
         # GPU" number of SURVEY.md section 8(d)); still a checker/baseline, never a product path
         g = torch.Generator().manual_seed(seed)
         self.obj_feats = obj_feats
-        self.P = {k: v.to(device).requires_grad_() for k, v in init_params(D, share=True, seed=seed).items()
+        self.dtype = dtype
+        self.P = {k: v.to(device, dtype).requires_grad_() for k, v in init_params(D, share=True, seed=seed).items()
                   if not k.startswith('outside_')}
         for k in list(self.P):
             if k.startswith('inside_'):
                 self.P['outside_' + k[len('inside_'):]] = self.P[k]
-        dev = lambda t: t.to(device)
+        dev = lambda t: t.to(device, dtype)
         self.emb = dev(torch.randn(V, E, generator=g))                  # frozen with --obj_feats (trainer.py:538-541)
         self.mat = dev(torch.randn(D, E, generator=g)).requires_grad_()
         self.mat1 = dev(torch.randn(D, E, generator=g)).requires_grad_()
@@ -427,7 +429,7 @@ class CpuClioraStep(object):
     def loss(self, sentences, neg_samples, obj_feats=None, keep=None):
         x_span, x_word = embed(self.emb, self.mat, self.mat1, sentences)
         if self.obj_feats:
-            obj_span, obj_word = image_encoder(self.enc, obj_feats)
+            obj_span, obj_word = image_encoder(self.enc, obj_feats.to(self.dtype))
             out = chart_forward(self.P, x_span, obj_span, keep)
             aas = all_atten_score(out.inside_h, out.outside_h, obj_span)
             vg = vg_atten_score(x_word, obj_word, training=True)

@@ -147,7 +147,7 @@ def _oracle_run(dt, B, n, D, R, share, seed=8):
 
 
 @pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True)])
-def test_chart_vs_oracle_live(B, n, D, R, share):
+def test_chart_vs_oracle_live(B, n, D, R, share, chains=None):
     """Same seeded inputs through the CUDA path and the CPU oracle, fwd + bwd, at the real hidden size.
 
     The arbiter is the oracle in float64.  Chart tensors must be within 1e-4 (of max).  Gradients must be
@@ -166,6 +166,7 @@ def test_chart_vs_oracle_live(B, n, D, R, share):
         P0, x, obj, keep, ct, ref64 = _oracle_run(torch.float64, B, n, D, R, share, seed)
         pre_in, pre_out = ref64.pop('pre')
         m = DioraMLP(D, share=share).cuda()
+        m.chains = chains
         _fill(m, P0)
         xc = x.cuda().requires_grad_()
         oc = obj.cuda().requires_grad_() if R else None
@@ -283,3 +284,11 @@ def test_tf32_single_pass_mode_has_its_own_tolerance():
         errs[prec] = max(rel_err(getattr(m, k), ref64[k]) for k in ct)
     assert errs['fp32'] < 1e-4, errs
     assert 1e-5 < errs['tf32'] < 1e-2, errs     # really a different arithmetic, within its stated tolerance
+
+
+@pytest.mark.parametrize('B,n,chains', [(16, 10, 2), (16, 10, 4), (32, 20, 2)])
+def test_multi_chain_backward_vs_oracle(B, n, chains):
+    """The configuration that is timed runs the batch as 2 (batch 32) or 4 (batch >= 64) sentence chains on
+    separate streams with per-chain weight-gradient buffers: forward and every gradient against the float64
+    oracle with chains > 1, at D=400, R=36 (the last case is the bench workload's chart: B=32, n=20)."""
+    test_chart_vs_oracle_live(B, n, 400, 36, True, chains=chains)

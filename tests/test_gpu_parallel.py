@@ -1,0 +1,87 @@
+"""Data parallelism of the real CLIORA net over NCCL (SURVEY.md section 8e verification row): two ranks, each
+with its own sentence shard, gradients averaged by GradSync == a single process that runs both shards and averages.
+Skipped on a single-GPU box (the driver's multi-GPU tier and bench.py --gpus N exercise the same code)."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cfg():
+    return dict(B=8, n=9, D=400, R=36, F=2048, V=300, E=64, k_neg=20)
+
+
+def _trainer(cfg, seed):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import build_trainer
+    tr = build_trainer(cfg, seed=seed)
+    tr.net.diora.atten_head.dropout.p = 0.0
+    return tr
+
+
+def _shard(cfg, rank, dev):
+    from bench import make_batch
+    return make_batch(cfg, 500 + rank, device=dev)
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from cliora_b200.parallel import GradSync
+    cfg = _cfg()
+    tr = _trainer(cfg, seed=10 + rank)              # different weights per rank: the broadcast must fix that
+    params = [p for p in tr.net.parameters() if p.requires_grad]
+    sync = GradSync(params, world)
+    assert sync.in_sync()
+    tr.net.train()
+    outp = tr.run_net(_shard(cfg, rank, torch.device('cuda', rank)), None, compute_loss=True)
+    outp['total_loss'].mean(dim=0).sum().backward()
+    sync()
+    if rank == 0:
+        torch.save({'grads': [p.grad.cpu() for p in params],
+                    'weights': {k: v.cpu() for k, v in tr.net.state_dict().items()}}, out)
+    # a few real optimizer steps through the data-parallel trainer path: replicas must stay bit-identical
+    tr.grad_sync = sync
+    for i in range(3):
+        tr.step(_shard(cfg, rank + 2 * i, torch.device('cuda', rank)), train=True, sync_result=False)
+    assert sync.in_sync()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_real_net_nccl_grads_equal_single_process_average(tmp_path):
+    import torch.multiprocessing as mp
+    from conftest import rel_err
+    world, port, out = 2, _free_port(), str(tmp_path / 'g.pt')
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    cfg = _cfg()
+    tr = _trainer(cfg, seed=10)
+    tr.net.load_state_dict(got['weights'])
+    params = [p for p in tr.net.parameters() if p.requires_grad]
+    tr.net.train()
+    acc = None
+    for r in range(world):
+        for p in params:
+            p.grad = None
+        o = tr.run_net(_shard(cfg, r, torch.device('cuda', 0)), None, compute_loss=True)
+        o['total_loss'].mean(dim=0).sum().backward()
+        g = [p.grad.clone() / world for p in params]
+        acc = g if acc is None else [a + b for a, b in zip(acc, g)]
+    for a, b in zip(got['grads'], acc):
+        assert rel_err(a, b) < 1e-5

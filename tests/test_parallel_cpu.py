@@ -33,13 +33,21 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from cliora_b200.parallel import GradSync
-    m = _model()
-    sync = GradSync(list(m.parameters()), world)
+    m = _model(seed=rank)      # every rank draws its OWN weights (the reference never seeds torch) ...
+    sync = GradSync(list(m.parameters()), world)     # ... and the wrap broadcasts rank 0's, like DDP
+    assert sync.in_sync()
+    ref = _model(seed=0)
+    for p, q in zip(m.parameters(), ref.parameters()):
+        assert torch.equal(p, q)
     x, y = _shard(rank)
     ((m(x) - y) ** 2).mean().backward()
     sync()
     if rank == 0:
         torch.save([p.grad.clone() for p in m.parameters()], out)
+    with torch.no_grad():      # a rank-dependent update must be noticed
+        if rank == 1:
+            next(m.parameters()).add_(1e-3)
+    assert not sync.in_sync()
     dist.barrier()
     dist.destroy_process_group()
 
