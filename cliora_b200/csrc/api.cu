@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "tc_gemm.cuh"
+#include "level_kernels.cuh"
 
 namespace cliora {
 thread_local char g_last_cuda_error[256] = "";
@@ -65,7 +66,8 @@ void apply_carveout(const void* kern) {
   g_attr_done[key] = g_carveout;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
 }
-int g_debug[8] = {2, 0, 0, 2, 0, 0, 0, 0};   // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums, [5] = 1: per-cell GEMMs on the fp32 SIMT kernel instead of mma.sync 3xTF32
+int g_debug[16] = {2, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [6] = 1: unfused per-level forward (split_build + GEMM + cell_aggregate), [7] = 1: unfused backward
+// [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums, [5] = 1: per-cell GEMMs on the fp32 SIMT kernel instead of mma.sync 3xTF32
 
 static int validate(const cliora_dims* d) {
   if (d == nullptr) return CLIORA_ERR_NULL_POINTER;
@@ -409,6 +411,56 @@ static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g, float* cellsum) {
   return CLIORA_OK;
 }
 
+// One launch for a whole forward level (gather + compose GEMM + softmax-weighted sums + cell finalize): lvl::level_fwd_kernel.
+// Returns false when the shape is outside what the fused kernel covers (the unfused chain then runs).
+static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g) {
+  if (!c.use_tc || g_debug[6] != 0 || N < 1 || N > lvl::kRows) return false;
+  if (!lvl::level_geom(c.d.D, g)) return false;
+  if (c.d.D > 1024) return false;
+  return true;
+}
+
+static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::LevelGeom& geom, const cliora_weights* w,
+                           const float* ih, const float* is_, const float* os_, float* chart_h, float* chart_s,
+                           const float* obj, const uint8_t* keep, float* ws) {
+  const int n = c.d.n, D = c.d.D, B = c.d.B;
+  const bool sh = c.d.share != 0;
+  lvl::LevelFwdArgs a{};
+  a.B = B; a.n = n; a.level = level; a.L = n - level; a.N = outside ? n - level - 1 : level; a.D = D;
+  a.R = outside ? 0 : c.d.R;
+  a.cells = B * a.L;
+  a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
+  a.G = lvl::level_cells_per_tile(a.cells, a.N, a.R, a.nc);
+  if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
+  a.mode = c.tc_mode == 1 ? 1 : 2;
+  a.outside = outside ? 1 : 0;
+  a.C = c.C;
+  const int ldPin = (int)(c.L.PI * D);
+  a.P1 = ws + c.L.Pin; a.ld1 = ldPin; a.off_a1 = (outside && !sh) ? 3 * D : 0;
+  if (!outside) { a.P2 = ws + c.L.Pin; a.ld2 = ldPin; a.off_a2 = D; a.off_v2 = 2 * D; }
+  else { a.P2 = ws + c.L.Pout; a.ld2 = 2 * D; a.off_a2 = 0; a.off_v2 = D; }
+  a.h1 = ih; a.s1 = is_; a.s2 = outside ? os_ : is_;
+  a.b1 = (outside && !sh) ? w->ob1 : w->b1;
+  a.b2 = (outside && !sh) ? w->ob2 : w->b2;
+  const int64_t r0 = outside ? B * outside_rows_before(n, level) : B * inside_rows_before(n, level);
+  const int64_t total = outside ? c.L.rows_out : c.L.rows_in;
+  a.Z = ws + (outside ? c.L.Zout : c.L.Zin) + r0 * D;
+  a.z_lo_off = total * D;
+  const int64_t mb = outside ? c.L.Mbout : c.L.Mbin;
+  a.zmask = mb >= 0 ? reinterpret_cast<uint32_t*>(ws + mb) + r0 * 16 : nullptr;
+  a.Y = ws + (outside ? c.L.Yout : c.L.Yin) + r0 * D;
+  a.E = ws + (outside ? c.L.Eout : c.L.Ein) + r0;
+  a.Pr = ws + (outside ? c.L.Prout : c.L.Prin) + r0;
+  a.chart_h = chart_h; a.chart_s = chart_s;
+  a.q = (!outside && c.d.R > 0) ? ws + c.L.q_in : nullptr;
+  a.nrm = ws + (outside ? c.L.nrm_out : c.L.nrm_in);
+  a.nrm2 = (!outside && c.d.R > 0) ? ws + c.L.nrm2_in : nullptr;
+  a.att = (!outside && c.d.R > 0) ? ws + c.L.att_in : nullptr;
+  a.obj = obj; a.keep = keep;
+  const float* W2pair = ws + (outside ? c.L.oW2p : c.L.W2p);
+  return lvl::launch_level_fwd(c.st, a, W2pair, outside ? "level_fwd_outside" : "level_fwd_inside");
+}
+
 // shared by both passes: cell backward, GZ GEMM, scatter for one level
 template <bool OUTSIDE, bool VL>
 static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const float* ih, const float* is_,
@@ -571,6 +623,12 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
   // leaves: t = tanh(W_leaf x + b); h = finalize(t)
   CL_TRY(dense_linear(c.st, B * n, D, D, x, w->W_leaf, w->b_leaf, 2, ws + c.L.leaf_t));
   for (int level = 0; level < n; ++level) {
+    lvl::LevelGeom geom;
+    if (level > 0 && fused_level_ok(c, level, geom)) {
+      CL_TRY(fused_level_fwd(c, level, false, geom, w, inside_h, inside_s, nullptr, inside_h, inside_s, obj, keep, ws));
+      if (level < n - 1) CL_TRY(project_level(c, level, inside_h, Wcat_in, PI * D, ws + c.L.Pin));
+      continue;
+    }
     if (level > 0) {
       SplitArgs s = split_args(c, level, false, inside_h, inside_s, nullptr, ws, w->b1);
       const int64_t rows = (int64_t)B * s.L * s.N;
@@ -608,6 +666,13 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
   CL_CHECK_LAUNCH("outside_root_kernel");
   if (n > 1) CL_TRY(project_level(c, n - 1, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
   for (int level = n - 2; level >= 0; --level) {
+    lvl::LevelGeom geom;
+    if (fused_level_ok(c, n - level - 1, geom)) {
+      CL_TRY(fused_level_fwd(c, level, true, geom, w, inside_h, inside_s, outside_s, outside_h, outside_s, nullptr,
+                             nullptr, ws));
+      if (level > 0) CL_TRY(project_level(c, level, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
+      continue;
+    }
     SplitArgs s = split_args(c, level, true, inside_h, inside_s, outside_s, ws, ob1);
     const int64_t rows = (int64_t)B * s.L * s.N;
     {
@@ -1036,7 +1101,7 @@ void cliora_debug_set(int key, int value) {
   if (key == 103) { tc::g_tc_narrow_stages = value; return; }
   if (key == 104) { g_splitk_target = value; return; }
   if (key == 105) { tc::g_tc_xnarrow = value; return; }      // preferred shared-memory carveout, percent (-1: leave)   // programmatic dependent launch on/off
-  if (key >= 0 && key < 8) g_debug[key] = value;
+  if (key >= 0 && key < 16) g_debug[key] = value;
 }
 
 int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_t stream) {

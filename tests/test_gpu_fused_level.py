@@ -1,0 +1,83 @@
+"""The fused per-level forward kernel (csrc/level_kernels.cuh: gather + compose GEMM + softmax-weighted sums + cell
+finalize in one launch per level) against the unfused kernel chain it replaces (split_build -> tcgen05 GEMM ->
+cell_aggregate), buffer by buffer: chart tensors, split scores / probabilities, the compose MLP's hidden and output
+rows, ReLU bit masks and the per-cell tensors saved for backward.  Parity with the reference itself is what the other
+GPU tests check with whichever path is the default; this one localises a disagreement to a buffer."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(B, n, D, R, share, fused, train, seed=3):
+    from cliora_b200 import _lib
+    from oracle import cliora_oracle as O
+    from test_gpu_chart import _fill
+    if R:
+        from cliora_b200.net.cliora import DioraMLP
+    else:
+        from cliora_b200.net.diora import DioraMLP
+    _lib.lib().cliora_debug_set(6, 0 if fused else 1)
+    try:
+        P0 = O.init_params(D, share=share, seed=seed)
+        g = torch.Generator().manual_seed(seed + 1)
+        x = torch.randn(B, n, D, generator=g).cuda()
+        obj = (0.05 * torch.randn(B, R, D, generator=g)).cuda() if R else None
+        keep = (torch.rand(B, O.num_cells(n), R, generator=g) >= 0.1).cuda() if R else None
+        m = DioraMLP(D, share=share).cuda()
+        m.chains = 1
+        _fill(m, P0)
+        m.train() if train else m.eval()
+        if R and train:
+            m.set_dropout_mask(keep)
+        with torch.no_grad():
+            if R:
+                m(x, x, obj, obj)
+            else:
+                m(x, x)
+        torch.cuda.synchronize()
+        lay = m._run.layout
+        ws = m._run.ws.clone()
+        out = {k: getattr(m, k).clone() for k in ('inside_h', 'inside_s', 'outside_h', 'outside_s')}
+        return out, ws, lay
+    finally:
+        _lib.lib().cliora_debug_set(6, 0)
+
+
+SHAPES = [(4, 10, 400, 36, True, True), (3, 8, 400, 0, False, False), (2, 20, 400, 36, True, True),
+          (5, 11, 132, 7, False, True), (7, 13, 260, 33, True, False), (2, 33, 64, 5, True, True),
+          (1, 3, 36, 1, True, False), (2, 4, 520, 64, True, True), (1, 2, 32, 0, True, False),
+          (16, 20, 400, 36, True, True)]
+
+
+@pytest.mark.parametrize('B,n,D,R,share,train', SHAPES)
+def test_fused_level_forward_matches_unfused_chain(B, n, D, R, share, train):
+    ref, ws0, lay = _run(B, n, D, R, share, False, train)
+    got, ws1, _ = _run(B, n, D, R, share, True, train)
+    C = n * (n + 1) // 2
+    rows_in, rows_out = int(lay.rows_in), int(lay.rows_out)
+
+    def seg(ws, off, count):
+        return ws[off: off + count]
+    checks = [('Ein', lay.Ein, rows_in, 2e-5), ('Prin', lay.Prin, rows_in, 2e-5), ('Eout', lay.Eout, rows_out, 2e-5),
+              ('Prout', lay.Prout, rows_out, 2e-5), ('Yin', lay.Yin, rows_in * D, 2e-5),
+              ('Yout', lay.Yout, rows_out * D, 2e-5), ('nrm_in', lay.nrm_in, B * C, 2e-5),
+              ('nrm_out', lay.nrm_out, B * C, 2e-5)]
+    if R:
+        checks += [('q_in', lay.q_in, B * C * D, 2e-5), ('nrm2_in', lay.nrm2_in, B * C, 2e-5),
+                   ('att_in', lay.att_in, B * C * R, 2e-5)]
+    for name, off, count, tol in checks:
+        if count:
+            assert rel_err(seg(ws1, off, count), seg(ws0, off, count)) < tol, name
+    # hidden activations: the very same fp32 adds in both paths -> identical pairs and identical ReLU masks
+    for name, off, count in (('Zin', lay.Zin, 2 * rows_in * D), ('Zout', lay.Zout, 2 * rows_out * D)):
+        if count:
+            assert torch.equal(seg(ws1, off, count), seg(ws0, off, count)), name
+    if lay.Mbin >= 0:
+        for name, off, count in (('Mbin', lay.Mbin, rows_in * 16), ('Mbout', lay.Mbout, rows_out * 16)):
+            if count:
+                assert torch.equal(seg(ws1, off, count).view(torch.int32), seg(ws0, off, count).view(torch.int32)), name
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 2e-5, k
