@@ -102,6 +102,8 @@ def _declare(lib):
     lib.cliora_last_cuda_error.restype = c_char_p
     lib.cliora_abi_version.restype = c_int
     lib.cliora_launch_count.restype = c_int64
+    lib.cliora_debug_ptr.argtypes = [c_int, c_void_p]
+    lib.cliora_debug_ptr.restype = None
     lib.cliora_num_cells.restype = c_int64
     lib.cliora_num_cells.argtypes = [c_int]
     lib.cliora_level_offset.restype = c_int64
@@ -180,7 +182,7 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
            'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set',
            'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn', 'cliora_tc_atten_max_fwd', 'cliora_recon_ce_fwd', 'cliora_recon_ce_bwd', 'cliora_tree_spans', 'cliora_span_f1', 'cliora_grounding_eval', 'cliora_gather_regions', 'cliora_adam_table_bytes',
-           'cliora_adam_table_fill', 'cliora_adam_step']
+           'cliora_adam_table_fill', 'cliora_adam_step', 'cliora_debug_ptr']
 
 
 def lib():

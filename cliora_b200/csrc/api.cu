@@ -66,6 +66,22 @@ void apply_carveout(const void* kern) {
   g_attr_done[key] = g_carveout;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
 }
+namespace lvl {
+long long* g_level_dbg = nullptr;
+int max_active_clusters(int nc, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, std::pair<int, size_t>>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, std::make_pair(nc, smem));
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int n = max_active_clusters_query(nc, smem);
+  cache[key] = n;
+  return n;
+}
+}  // namespace lvl
 int g_debug[16] = {2, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [6] = 1: unfused per-level forward (split_build + GEMM + cell_aggregate), [7] = 1: unfused backward
 // [0] = tc accumulate mode, [1] = 1: force the SIMT GEMMs, [2] = tc tile (0 auto, 1 narrow, 2 wide), [3] = bit0: block-per-cell VL forward kernel, bit1: block-per-cell VL backward kernel, [4] = 1: db2 from the full GY rows instead of the per-cell sums, [5] = 1: per-cell GEMMs on the fp32 SIMT kernel instead of mma.sync 3xTF32
 
@@ -293,7 +309,8 @@ static int compose_gemm(const Ctx& c, bool outside, int64_t r0, int64_t rows, co
 }
 
 // GZ[level rows] = (GY[level rows] W2) * (Z > 0)
-static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows, const float* W2, float* ws,
+static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g);
+static int compose_gemm_bwd(const Ctx& c, bool outside, int level, int64_t r0, int64_t rows, const float* W2, float* ws,
                             float* GZ) {
   const int D = c.d.D;
   const int64_t total = outside ? c.L.rows_out : c.L.rows_in;
@@ -306,7 +323,10 @@ static int compose_gemm_bwd(const Ctx& c, bool outside, int64_t r0, int64_t rows
     ep.C = GZ; ep.ldc = D; ep.cmap = dense_rows();
     ep.mask = Zb + r0 * D; ep.ldm = D; ep.mask_lo_off = total * D;
     const int64_t mb = outside ? c.L.Mbout : c.L.Mbin;
-    if (mb >= 0) ep.maskbits = reinterpret_cast<const uint32_t*>(ws + mb) + r0 * 16;
+    lvl::LevelGeom geom;
+    const int nsplit = outside ? c.d.n - level - 1 : level;
+    const bool bits_written = !fused_level_ok(c, nsplit, geom) || g_debug[10] != 0;   // the fused forward skips them
+    if (mb >= 0 && bits_written) ep.maskbits = reinterpret_cast<const uint32_t*>(ws + mb) + r0 * 16;
     return tc::launch_tc_gemm_nt(c.st, A, (int)r0, W, (int)rows, D, D, ep, "tc_gemm_compose_w2_bwd", c.tc_mode, g_debug[2]);
   }
   GemmParams p{};
@@ -430,7 +450,8 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   a.R = outside ? 0 : c.d.R;
   a.cells = B * a.L;
   a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
-  a.G = lvl::level_cells_per_tile(a.cells, a.N, a.R, a.nc);
+  a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, a.R, geom,
+                                  lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)), a.max_sent);
   if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
   a.mode = c.tc_mode == 1 ? 1 : 2;
   a.outside = outside ? 1 : 0;
@@ -447,7 +468,8 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   a.Z = ws + (outside ? c.L.Zout : c.L.Zin) + r0 * D;
   a.z_lo_off = total * D;
   const int64_t mb = outside ? c.L.Mbout : c.L.Mbin;
-  a.zmask = mb >= 0 ? reinterpret_cast<uint32_t*>(ws + mb) + r0 * 16 : nullptr;
+  // ReLU bit masks are only produced on request: the backward reads the sign of the stored Z pair instead
+  a.zmask = (mb >= 0 && g_debug[10] != 0) ? reinterpret_cast<uint32_t*>(ws + mb) + r0 * 16 : nullptr;
   a.Y = ws + (outside ? c.L.Yout : c.L.Yin) + r0 * D;
   a.E = ws + (outside ? c.L.Eout : c.L.Ein) + r0;
   a.Pr = ws + (outside ? c.L.Prout : c.L.Prin) + r0;
@@ -487,7 +509,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   SplitArgs s = split_args(c, level, OUTSIDE, ih, is_, os_, ws, b1);
   const int64_t rows = (int64_t)B * s.L * s.N;
   const int64_t r0 = OUTSIDE ? B * outside_rows_before(n, level) : B * inside_rows_before(n, level);
-  CL_TRY(compose_gemm_bwd(c, OUTSIDE, r0, rows, W2, ws, bws + c.L.GZ));
+  CL_TRY(compose_gemm_bwd(c, OUTSIDE, level, r0, rows, W2, ws, bws + c.L.GZ));
 
   ScatterArgs sc{};
   sc.s = s;
@@ -1092,6 +1114,10 @@ int cliora_matmul_nn(int M, int N, int K, const float* A, const float* Bm, float
   p.M = M; p.N = N; p.K = K;
   p.accumulate = accumulate;
   return launch_gemm((cudaStream_t)stream, false, p);
+}
+
+void cliora_debug_ptr(int key, void* p) {
+  if (key == 0) lvl::g_level_dbg = static_cast<long long*>(p);
 }
 
 void cliora_debug_set(int key, int value) {

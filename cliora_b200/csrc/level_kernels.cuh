@@ -22,6 +22,7 @@
 #include "tc_gemm.cuh"
 
 namespace cliora {
+extern int g_debug[16];
 namespace lvl {
 
 using tc::fence_barrier_init;
@@ -40,18 +41,21 @@ using tc::umma_idesc_tf32;
 using tc::umma_tf32;
 
 constexpr int kRows = 128;            // split rows per tile = UMMA M
-constexpr int kStages = 3;
+constexpr int kAStages = 4;           // A-operand ring (gathered + transformed by the producer warps), 32 KB per stage
 constexpr int kProdWarps = 8;
 constexpr int kProdWarp0 = 6;
 constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // 448
 constexpr int kMaxCluster = 8;
 constexpr int kMaxUmmaN = 112;
 constexpr int kABytes = kRows * 128;  // one 128 x 32 fp32 operand tile
-constexpr int kXlFloats = 4096;       // region-logit exchange buffer (nc * G * R floats)
-// extras after the pipeline stages: barriers (128 B), b1 (1024 f), b2 (128 f), e, p, nrm, nrm2 (4 x 128 f),
-// three [8][128] exchange buffers, the logit exchange buffer
-constexpr int kExtraFloats = 1024 + 128 + 4 * 128 + 3 * kMaxCluster * 128 + kXlFloats;
-constexpr int kExtraBytes = 128 + 4 * kExtraFloats;
+constexpr int kXlFloats = 2048;       // region-logit exchange buffer (nc * G * R floats)
+// extras after the operand rings: barriers (256 B), b2 (128 f), e, p, nrm, nrm2 (4 x 128 f), three [8][128] exchange
+// buffers, the logit exchange buffer, the global row of every tile row (int64)
+constexpr int kExtraFloats = 128 + 4 * 128 + 3 * kMaxCluster * 128 + kXlFloats;
+constexpr int kExtraBytes = 256 + 4 * kExtraFloats + 8 * 128;
+// W2-slice ring (TMA): three stages when the slice is narrow, two otherwise (shared-memory budget)
+CL_HD int b_stages(int n_umma) { return n_umma <= 80 ? 3 : 2; }
+CL_HD int ring_bytes(int n_umma) { return kAStages * 2 * kABytes + b_stages(n_umma) * 2 * n_umma * 128; }
 
 CL_D uint32_t cluster_ctarank() {
   uint32_t r;
@@ -92,14 +96,37 @@ CL_D void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   //
 CL_D float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 CL_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// value `v` into slot[idx] of every CTA of the cluster, then one arrival on each CTA's barrier
+// Cluster all-gather of small per-row / per-cell values through distributed shared memory.
+// put: lanes 0..nc-1 of the calling warp each store `v` (warp-uniform) into slot[idx] of one CTA.
+CL_D void xchg_put_uniform(float* slot, int idx, float v, int nc, int lane) {
+  if (lane < nc) st_cluster_f32(map_to_cta(smem_u32(slot + idx), (uint32_t)lane), v);
+}
+// put: the calling thread stores its own value into slot[idx] of every CTA of the cluster.
 CL_D void xchg_put(float* slot, int idx, float v, int nc) {
   const uint32_t a = smem_u32(slot + idx);
   for (int c = 0; c < nc; ++c) st_cluster_f32(map_to_cta(a, (uint32_t)c), v);
 }
-CL_D void xchg_arrive(uint64_t* bar, int nc) {
-  const uint32_t a = smem_u32(bar);
-  for (int c = 0; c < nc; ++c) mbar_arrive_cluster(map_to_cta(a, (uint32_t)c));
+// One arrival per warp and destination CTA (barrier count = 4 epilogue warps x nc): every lane fences its remote
+// stores at cluster scope, the warp synchronises, lane c releases on CTA c's barrier.
+CL_D void xchg_arrive_warp(uint64_t* bar, int nc, int lane) {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  __syncwarp();
+  if (lane < nc) mbar_arrive_cluster(map_to_cta(smem_u32(bar), (uint32_t)lane));
+}
+// Only lane 0 spins with cluster-scope acquire (a cluster-scope acquire invalidates L1); __syncwarp orders the rest.
+CL_D void xchg_wait_warp(uint64_t* bar, int lane) {
+  if (lane == 0) mbar_wait_cluster(bar, 0);
+  __syncwarp();
+}
+CL_D long long clock_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+CL_D long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 struct LevelFwdArgs {
@@ -124,6 +151,9 @@ struct LevelFwdArgs {
   float* chart_h; float* chart_s;                     // [B,C,D], [B,C]
   float* q; float* nrm; float* nrm2; float* att;      // saved per cell (q, nrm2, att: R > 0 only)
   const float* obj; const uint8_t* keep;
+  int max_sent;                                       // CLIORA: sentences a tile may span (their region slices are staged in smem)
+  int exp_flags;                                      // timing experiments only (results become wrong): 1 no proxy fence, 2 no Z stores, 4 no transform
+  long long* dbg;                                     // optional in-kernel timeline [ctas][32] (clock64 stamps), or null
 };
 
 struct RowInfo {
@@ -160,11 +190,28 @@ CL_D RowInfo decode_row(const LevelFwdArgs& a, int tile, int cells_here, int r) 
   return ri;
 }
 
+// x = hi + lo exactly with hi = x truncated to tf32 (what the tensor core keeps of an fp32 operand anyway): two
+// instructions per element instead of the four of a round-to-nearest split; lo <= 2^-10 |x|, so the pair still
+// carries 21+ mantissa bits into the 3xTF32 product.
+CL_D void split_trunc(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+
+// zero-filling 16-byte asynchronous copy (src_bytes = 0 writes zeros)
+CL_D void cp_async16_zfill(uint32_t dst_saddr, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(src_bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) {
   pdl_prologue();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // The dynamic shared-memory window starts 1024-byte aligned (no static shared memory in this kernel); deriving every
+  // pointer from the array itself keeps the shared address space visible to the compiler (LDS/STS instead of generic
+  // LD/ST in the transform and finalize loops).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
   const int tile = blockIdx.y;
@@ -172,17 +219,24 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   const int D = a.D;
   const int num_kb = (D + 31) / 32;
   const int b_bytes = a.n_umma * 128;
-  const int stage_bytes = 2 * kABytes + 2 * b_bytes;
+  const int nbs = b_stages(a.n_umma);
+  const int a_stage_bytes = 2 * kABytes, b_stage_bytes = 2 * b_bytes;
+  uint8_t* ringB = smem + kAStages * a_stage_bytes;
   const int cells_here = min(a.G, a.cells - tile * a.G);
+  const int nc = a.nc, ncols = a.ncols, N = a.N;
+  long long* dbg_row = a.dbg ? a.dbg + ((int64_t)blockIdx.y * a.nc + rank) * 64 : nullptr;
+#define LV_STAMP(slot) do { if (dbg_row != nullptr && tid == 128) dbg_row[slot] = clock_now(); } while (0)
+  if (dbg_row && tid == 0) { dbg_row[0] = clock_now(); dbg_row[30] = global_ns(); }
 
-  uint8_t* ex = smem + kStages * stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ex);
-  uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
+  uint8_t* ex = smem + ring_bytes(a.n_umma);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(ex);
+  uint64_t* emptyA = fullA + kAStages;
+  uint64_t* fullB = emptyA + kAStages;
+  uint64_t* emptyB = fullB + 3;
+  uint64_t* tmem_full = emptyB + 3;
   uint64_t* xbar = tmem_full + 1;                 // 4 single-use cluster exchange barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
-  float* s_b1 = reinterpret_cast<float*>(ex + 128);
-  float* s_b2 = s_b1 + 1024;
+  float* s_b2 = reinterpret_cast<float*>(ex + 256);
   float* s_e = s_b2 + 128;
   float* s_p = s_e + 128;
   float* s_nrm = s_p + 128;
@@ -191,17 +245,23 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   float* s_xs = s_xe + kMaxCluster * 128;         // [nc][128] partial |a|^2
   float* s_xs2 = s_xs + kMaxCluster * 128;        // [nc][128] partial |a2|^2
   float* s_xl = s_xs2 + kMaxCluster * 128;        // [nc][G*R] partial region logits
+  long long* s_m = reinterpret_cast<long long*>(s_xl + kXlFloats);   // [128] global row of every tile row, -1 = none
   const uint32_t tmem_cols_alloc = (uint32_t)tc::tmem_cols(2 * a.n_umma);
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmW);
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < kStages; ++i) {
-        mbar_init(&full[i], 1 + kProdWarps);      // the TMA thread's expect_tx arrival + one per producer warp
-        mbar_init(&empty[i], 1);
+      for (int i = 0; i < kAStages; ++i) {
+        mbar_init(&fullA[i], kProdWarps);         // one arrival per producer warp
+        mbar_init(&emptyA[i], 1);
+      }
+      for (int i = 0; i < 3; ++i) {
+        mbar_init(&fullB[i], 1);                  // the TMA thread's expect_tx arrival
+        mbar_init(&emptyB[i], 1);
       }
       mbar_init(tmem_full, 1);
-      for (int i = 0; i < 4; ++i) mbar_init(&xbar[i], (uint32_t)a.nc * 128);
+      mbar_init(&xbar[0], (uint32_t)nc * 4);                  // scores: the four epilogue warps of every CTA
+      for (int i = 1; i < 4; ++i) mbar_init(&xbar[i], (uint32_t)nc * (kThreads / 32));   // cell phases: all warps
       fence_barrier_init();
     }
     __syncwarp();
@@ -210,24 +270,24 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 1024; i += kThreads) s_b1[i] = i < D ? a.b1[i] : 0.f;
-  for (int i = tid; i < 128; i += kThreads) s_b2[i] = (i < a.ncols && n0 + i < D) ? a.b2[n0 + i] : 0.f;
+  for (int i = tid; i < 128; i += kThreads) s_b2[i] = (i < ncols && n0 + i < D) ? a.b2[n0 + i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   cluster_sync_all();          // every CTA's barriers exist before a peer may arrive on them
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg_row && tid == 0) dbg_row[1] = clock_now();
 
   if (warp == 0) {
     // ------------------------------------------------------------ W2 slice: TMA
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(a.mode == 1 ? b_bytes : 2 * b_bytes);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int stage = kb % kStages;
-        const uint32_t phase = (kb / kStages) & 1;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], tx);
-        tma_load_3d(smem + stage * stage_bytes + 2 * kABytes, &tmW, &full[stage], kb * 32, n0, 0);
+        const int sb = kb % nbs;
+        const uint32_t phase = (kb / nbs) & 1;
+        mbar_wait(&emptyB[sb], phase ^ 1);
+        mbar_expect_tx(&fullB[sb], tx);
+        tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kb * 32, n0, 0);
       }
     }
   } else if (warp == 1) {
@@ -236,14 +296,17 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       const uint32_t idesc = umma_idesc_tf32(a.n_umma);
       uint32_t acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int stage = kb % kStages;
-        const uint32_t phase = (kb / kStages) & 1;
-        mbar_wait(&full[stage], phase);
+        const int sA_i = kb % kAStages, sb = kb % nbs;
+        mbar_wait(&fullB[sb], (kb / nbs) & 1);
+        mbar_wait(&fullA[sA_i], (kb / kAStages) & 1);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        if (dbg_row && kb == 0) dbg_row[20] = clock_now();
+        if (dbg_row && kb >= 3 && kb < 7) dbg_row[48 + (kb - 3) * 2] = clock_now();
+        const uint32_t sa = smem_u32(smem + sA_i * a_stage_bytes);
+        const uint32_t sbb = smem_u32(ringB + sb * b_stage_bytes);
         const uint64_t a_hi = umma_desc_k_sw128(sa), a_lo = umma_desc_k_sw128(sa + kABytes);
-        const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * kABytes);
-        const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * kABytes + b_bytes);
+        const uint64_t b_hi = umma_desc_k_sw128(sbb);
+        const uint64_t b_lo = umma_desc_k_sw128(sbb + b_bytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (a.mode == 1) {
@@ -255,12 +318,21 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           }
           acc = 1;
         }
-        umma_commit(&empty[stage]);
+        umma_commit(&emptyA[sA_i]);
+        umma_commit(&emptyB[sb]);
+        if (dbg_row && kb >= 3 && kb < 7) dbg_row[49 + (kb - 3) * 2] = clock_now();
       }
       umma_commit(tmem_full);
+      if (dbg_row) dbg_row[21] = clock_now();
     }
   } else if (warp >= kProdWarp0) {
     // ------------------------------------------------------------ A operand: gather + ReLU + tf32 split
+    // Each thread owns chunk c of rows rbase + 32 i.  The two projection rows of a split are copied asynchronously
+    // (cp.async, L1-bypassing) straight into the stage's hi / lo slots -- kLookahead k-blocks ahead of their use --
+    // and later transformed IN PLACE by the same thread: z = relu(al + ar + b1) -> (hi, lo).
+    // Four A stages, lookahead 2: the copies of k-blocks it and it-1 fly while k-block it-2 is transformed, and the MMAs
+    // of k-block it-2 overlap the next iteration (the stage that iteration refills was consumed one k-block earlier).
+    constexpr int kLookahead = 2;
     const int pt = tid - kProdWarp0 * 32;      // 0..255
     const int c = pt & 7;                      // 16-byte chunk of the 128-byte k-block row
     const int rw = lane >> 3;                  // row within the warp's group of four
@@ -269,13 +341,16 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     const float* pb[4];
     int64_t mrow[4];
     bool ok[4];
+    uint32_t soff[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const RowInfo ri = decode_row(a, tile, cells_here, rbase + 32 * i);
+      const int r = rbase + 32 * i;
+      const RowInfo ri = decode_row(a, tile, cells_here, r);
       ok[i] = ri.ok;
       mrow[i] = ri.m;
       pa[i] = a.P1 + ri.g1 * a.ld1 + a.off_a1 + c * 4;
       pb[i] = a.P2 + ri.g2 * a.ld2 + a.off_a2 + c * 4;
+      soff[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
     }
     const bool write_mask = a.zmask != nullptr && rank == 0;
     uint32_t mw[4][4];
@@ -284,42 +359,53 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
 #pragma unroll
       for (int j = 0; j < 4; ++j) mw[i][j] = 0u;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 xa[4], xb[4];
+    if (dbg_row && pt == 0) dbg_row[22] = clock_now();
+    const uint32_t smem_base = smem_u32(smem);
+    int zturn = 0;                             // k-block kb's Z pair is streamed out by CTA kb % nc
+    for (int it = 0; it < num_kb + kLookahead; ++it) {
+      if (it < num_kb) {
+        // ---- issue the copies of k-block `it`
+        const int stage = it % kAStages;
+        const uint32_t phase = (it / kAStages) & 1;
+        const int kcol = it * 32 + c * 4;
+        mbar_wait(&emptyA[stage], phase ^ 1);
+        if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[32 + (it - 4) * 4] = clock_now();
+        const uint32_t sA = smem_base + (uint32_t)(stage * a_stage_bytes);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool ld = ok[i] && c * 4 < D;
-      xa[i] = ld ? ldcg4(pa[i]) : zero4;
-      xb[i] = ld ? ldcg4(pb[i]) : zero4;
-    }
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int stage = kb % kStages;
-      const uint32_t phase = (kb / kStages) & 1;
-      const int kcol = kb * 32 + c * 4;
-      float4 na[4], nb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {             // next k-block's rows are in flight while this one is processed
-        const bool ld = ok[i] && (kb + 1 < num_kb) && (kcol + 32 < D);
-        na[i] = ld ? ldcg4(pa[i] + (kb + 1) * 32) : zero4;
-        nb[i] = ld ? ldcg4(pb[i] + (kb + 1) * 32) : zero4;
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t nbytes = (ok[i] && kcol < D) ? 16u : 0u;
+          cp_async16_zfill(sA + soff[i], pa[i] + it * 32, nbytes);
+          cp_async16_zfill(sA + kABytes + soff[i], pb[i] + it * 32, nbytes);
+        }
       }
-      const float4 bv = *reinterpret_cast<const float4*>(s_b1 + kcol);
-      mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* sA = smem + stage * stage_bytes;
-      const bool store_z = a.Z != nullptr && (kb % a.nc) == rank && kcol < D;
+      cp_async_commit();                        // (empty groups in the tail keep the group count uniform)
+      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[33 + (it - 4) * 4] = clock_now();
+      const int kb = it - kLookahead;
+      if (kb < 0) continue;
+      cp_async_wait<kLookahead>();              // this thread's copies of k-block kb have landed
+      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[34 + (it - 4) * 4] = clock_now();
+      // ---- transform k-block kb in place
+      const int stage = kb % kAStages;
+      const int kcol = kb * 32 + c * 4;
+      uint8_t* sA = smem + stage * a_stage_bytes;
+      const float4 bv = kcol < D ? __ldg(reinterpret_cast<const float4*>(a.b1 + kcol)) : zero4;
+      const bool store_z = a.Z != nullptr && zturn == rank && kcol < D && !(a.exp_flags & 2);
+      zturn = (zturn + 1 == nc) ? 0 : zturn + 1;
+      if (!(a.exp_flags & 4))
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = rbase + 32 * i;
+        const float4 xa = *reinterpret_cast<const float4*>(sA + soff[i]);
+        const float4 xb = *reinterpret_cast<const float4*>(sA + kABytes + soff[i]);
         float4 o;
-        o.x = fmaxf(xa[i].x + xb[i].x + bv.x, 0.f);
-        o.y = fmaxf(xa[i].y + xb[i].y + bv.y, 0.f);
-        o.z = fmaxf(xa[i].z + xb[i].z + bv.z, 0.f);
-        o.w = fmaxf(xa[i].w + xb[i].w + bv.w, 0.f);
+        o.x = fmaxf(xa.x + xb.x + bv.x, 0.f);
+        o.y = fmaxf(xa.y + xb.y + bv.y, 0.f);
+        o.z = fmaxf(xa.z + xb.z + bv.z, 0.f);
+        o.w = fmaxf(xa.w + xb.w + bv.w, 0.f);
         if (!ok[i] || kcol >= D) o = zero4;
         float4 hi, lo;
-        split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
-        const int off = r * 128 + ((c ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(sA + off) = hi;
-        if (a.mode != 1) *reinterpret_cast<float4*>(sA + kABytes + off) = lo;
+        split_trunc(o.x, hi.x, lo.x); split_trunc(o.y, hi.y, lo.y); split_trunc(o.z, hi.z, lo.z); split_trunc(o.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(sA + soff[i]) = hi;
+        *reinterpret_cast<float4*>(sA + kABytes + soff[i]) = lo;
         if (store_z && ok[i]) {
           st4(a.Z + mrow[i] * D + kcol, hi);
           st4(a.Z + a.z_lo_off + mrow[i] * D + kcol, lo);
@@ -334,9 +420,10 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           mw[i][3] |= ((q3 >> sh) & 0xffu) << up;
         }
       }
-      fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core's async proxy
+      if (!(a.exp_flags & 1)) fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive_local(&full[stage]);
+      if (lane == 0) mbar_arrive_local(&fullA[stage]);
+      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[35 + (it - 4) * 4] = clock_now();
       if (write_mask && ((kb & 3) == 3 || kb == num_kb - 1)) {
         const int t = kb >> 2;                  // 128-column group
 #pragma unroll
@@ -346,34 +433,62 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           mw[i][0] = mw[i][1] = mw[i][2] = mw[i][3] = 0u;
         }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { xa[i] = na[i]; xb[i] = nb[i]; }
     }
+    if (dbg_row && pt == 0) dbg_row[23] = clock_now();
   } else {
-    // ------------------------------------------------------------ warps 2-5: scores, softmax, epilogue, cell finalize
-    const int qd = warp & 3;                    // TMEM lane quarter this warp may read
-    const int r = qd * 32 + lane;               // split row of the tile = TMEM lane
+    // ------------------------------------------------------------ warps 2-5 (thread = split row): scores, softmax
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
     const RowInfo ri = decode_row(a, tile, cells_here, r);
-    const int nc = a.nc, ncols = a.ncols, N = a.N;
-    // (a) partial bilinear score over this CTA's columns, all-gathered over the cluster
-    float part = 0.f;
-    if (ri.ok) {
-      const float* hp = a.h1 + ri.g1 * D + n0;
-      const float* vp = a.P2 + ri.g2 * a.ld2 + a.off_v2 + n0;
-#pragma unroll 5
-      for (int j = 0; j < ncols; j += 4) {
-        if (n0 + j < D) {
-          const float4 hv = ldcg4(hp + j), vv = ldcg4(vp + j);
-          part = fmaf(hv.x, vv.x, part); part = fmaf(hv.y, vv.y, part);
-          part = fmaf(hv.z, vv.z, part); part = fmaf(hv.w, vv.w, part);
+    s_m[r] = ri.ok ? (long long)ri.m : -1ll;
+    LV_STAMP(2);
+    // partial bilinear score over this CTA's columns, all-gathered over the cluster.  Coalesced: eight lanes walk one
+    // row (16 bytes each, chunks c, c+8, ...), four rows per load instruction, two row groups (16 loads) in flight.
+    {
+      const int rr = lane >> 3, c = lane & 7;
+      const int nch = ncols >> 2;                         // 16-byte chunks per row slice
+      const int ok_i = ri.ok ? 1 : 0;
+      const int g1_i = (int)ri.g1, g2_i = (int)ri.g2;     // chart rows fit 32 bits
+#pragma unroll 1
+      for (int grp = 0; grp < 8; grp += 2) {
+        float4 hv[2][4], vv[2][4];
+        bool okr[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int src_lane = (grp + u) * 4 + rr;
+          okr[u] = __shfl_sync(0xffffffffu, ok_i, src_lane) != 0;
+          const int r1 = __shfl_sync(0xffffffffu, g1_i, src_lane), r2 = __shfl_sync(0xffffffffu, g2_i, src_lane);
+          const float* hp = a.h1 + (int64_t)r1 * D + n0;
+          const float* vp = a.P2 + (int64_t)r2 * a.ld2 + a.off_v2 + n0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int ch = c + 8 * t;
+            const bool ld = okr[u] && ch < nch && n0 + ch * 4 < D;
+            hv[u][t] = ld ? ldcg4(hp + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vv[u][t] = ld ? ldcg4(vp + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float part = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            part = fmaf(hv[u][t].x, vv[u][t].x, part); part = fmaf(hv[u][t].y, vv[u][t].y, part);
+            part = fmaf(hv[u][t].z, vv[u][t].z, part); part = fmaf(hv[u][t].w, vv[u][t].w, part);
+          }
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+          if (c == 0) xchg_put(s_xe + rank * 128, qd * 32 + (grp + u) * 4 + rr, part, nc);
         }
       }
     }
-    xchg_put(s_xe + rank * 128, r, part, nc);
-    xchg_arrive(&xbar[0], nc);
     float e = 0.f;
     if (ri.ok) e = a.s1[ri.g1] + a.s2[ri.g2];
-    mbar_wait_cluster(&xbar[0], 0);
+    LV_STAMP(3);
+    xchg_arrive_warp(&xbar[0], nc, lane);
+    xchg_wait_warp(&xbar[0], lane);
+    LV_STAMP(4);
     float dot = 0.f;
     for (int cc = 0; cc < nc; ++cc) dot += s_xe[cc * 128 + r];
     e += dot;
@@ -398,15 +513,28 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
         }
       }
     }
-    // (b) epilogue: y = relu(acc + b2) -> Y row; p * y staged for the per-cell sums
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
-    const int stride = ncols + 4;
-    float* s_stage = reinterpret_cast<float*>(smem);           // pipeline stages are free now
-    float* s_a = s_stage + kRows * stride;                      // [G][ncols]
-    float* yrow = ri.ok ? a.Y + ri.m * D + n0 : nullptr;
+    s_p[r] = p;
+    LV_STAMP(5);
+  }
+
+  // ================================================================ every warp: epilogue + cell finalize
+  mbar_wait(tmem_full, 0);
+  tcgen05_fence_after();
+  __syncthreads();                               // softmax probabilities published; pipeline stages are free
+  LV_STAMP(6);
+  const int stride = ncols + 4;
+  float* s_stage = reinterpret_cast<float*>(smem);            // [128][ncols + 4] p-weighted compose outputs
+  float* s_a = s_stage + kRows * stride;                       // [G][ncols]
+  const int nc4 = ncols >> 2;
+  if (warp >= 2) {
+    // y = relu(acc + b2) -> Y row (saved for backward); p * y staged.  Twelve warps: TMEM lane quarter = warp % 4,
+    // the 16-column chunks of a quarter are dealt to its three warps.
+    const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
+    const long long m = s_m[r];
+    const float p = s_p[r];
+    float* yrow = m >= 0 ? a.Y + m * D + n0 : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < a.n_umma; c0 += 16) {
+    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 48) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);    // warp-collective: no early exit
       if (a.mode != 1) {
@@ -429,158 +557,189 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
         }
       }
     }
-    tcgen05_fence_before();
-    epi_bar_sync();
-    // per-cell sums over the N splits (fixed order: deterministic)
-    const int nc4 = ncols >> 2;
-    for (int item = r; item < cells_here * nc4; item += 128) {
-      const int g = item / nc4, j4 = item - g * nc4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* src = s_stage + (g * N) * stride + j4 * 4;
-      for (int kk = 0; kk < N; ++kk) {
-        const float4 t = ld4(src + kk * stride);
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-      }
-      st4(s_a + g * ncols + j4 * 4, acc);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  LV_STAMP(7);
+  // per-cell sums over the N splits (fixed order: deterministic)
+  for (int item = tid; item < cells_here * nc4; item += kThreads) {
+    const int g = item / nc4, j4 = item - g * nc4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = s_stage + (g * N) * stride + j4 * 4;
+    for (int kk = 0; kk < N; ++kk) {
+      const float4 t = ld4(src + kk * stride);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    epi_bar_sync();
-    int cb = 0, cp = 0;
-    int64_t ccell = 0;
-    if (r < cells_here) {
-      cell_of(a, tile * a.G + r, cb, cp, ccell);
+    st4(s_a + g * ncols + j4 * 4, acc);
+  }
+  __syncthreads();
+  // |a|^2 over this CTA's columns: warp per cell, lanes over columns; all-gathered over the cluster
+  for (int g = warp; g < cells_here; g += kThreads / 32) {
+    float ss = 0.f;
+    for (int j = lane; j < ncols; j += 32) {
+      const float t = s_a[g * ncols + j];
+      ss = fmaf(t, t, ss);
+    }
+    ss = warp_sum(ss);
+    xchg_put_uniform(s_xs + rank * 128, g, ss, nc, lane);
+  }
+  LV_STAMP(8);
+  xchg_arrive_warp(&xbar[1], nc, lane);
+  const bool vl = a.R > 0;
+  const int R = a.R, Rp = a.R | 1;               // odd row pitch: conflict-free column walks
+  const int GRs = a.G * R, GRp = (GRs + 3) & ~3;
+  float* s_att = s_a + kRows * ncols;            // [G][R] logits -> attention weights
+  float* s_patt = s_att + GRp;                   // [G][R] dropout-scaled weights
+  float* s_obj = s_patt + GRp;                   // [max_sent][ncols][Rp]: this CTA's column slice of the tile's images
+  const int b_first = (tile * a.G) / a.L;
+  if (vl) {
+    // stage the region features (transposed) while the norms travel: rows (sentence, region), 16 bytes per thread
+    const int b_last = (tile * a.G + cells_here - 1) / a.L;
+    const int total = (b_last - b_first + 1) * R * nc4;
+    const float* src = a.obj + (int64_t)b_first * R * D + n0;
+    for (int idx = tid; idx < total; idx += kThreads) {
+      const int row = idx / nc4, j4 = idx - row * nc4;        // row = sentence * R + region
+      const int bs = row / R, rr = row - bs * R;
+      const float4 v = (n0 + j4 * 4 < D) ? ldcg4(src + (int64_t)row * D + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* dst = s_obj + ((bs * ncols) + j4 * 4) * Rp + rr;
+      dst[0] = v.x; dst[Rp] = v.y; dst[2 * Rp] = v.z; dst[3 * Rp] = v.w;
+    }
+  }
+  xchg_wait_warp(&xbar[1], lane);
+  LV_STAMP(9);
+  if (tid < cells_here) {
+    int cb, cp;
+    int64_t ccell;
+    cell_of(a, tile * a.G + tid, cb, cp, ccell);
+    float tot = 0.f;
+    for (int cc = 0; cc < nc; ++cc) tot += s_xs[cc * 128 + tid];
+    const float nrm = fmaxf(sqrtf(tot), kTiny);
+    s_nrm[tid] = nrm;
+    if (rank == 0) a.nrm[ccell] = nrm;
+  }
+  __syncthreads();
+  for (int item = tid; item < cells_here * nc4; item += kThreads) {
+    const int g = item / nc4, j4 = item - g * nc4;
+    const float inv = 1.f / s_nrm[g];
+    float4 t = ld4(s_a + g * ncols + j4 * 4);
+    t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+    st4(s_a + g * ncols + j4 * 4, t);
+    if (n0 + j4 * 4 < D) {
+      int b2_, p2_;
+      int64_t cell2;
+      cell_of(a, tile * a.G + g, b2_, p2_, cell2);
+      st4((vl ? a.q : a.chart_h) + cell2 * D + n0 + j4 * 4, t);
+    }
+  }
+  LV_STAMP(10);
+  if (vl) {
+    // region attention of every cell against ITS OWN image only (the reference computes all B x B pairs and
+    // keeps the diagonal, cliora.py:35-42)
+    __syncthreads();
+    for (int item = tid; item < cells_here * R; item += kThreads) {     // partial logits q . obj_r
+      const int g = item / R, rr = item - g * R;
+      const int bs = (tile * a.G + g) / a.L - b_first;
+      const float* op = s_obj + (bs * ncols) * Rp + rr;
+      const float* qp = s_a + g * ncols;
+      float d = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < ncols; ++j) d = fmaf(qp[j], op[j * Rp], d);
+      xchg_put(s_xl + rank * GRs, item, d, nc);
+    }
+    LV_STAMP(12);
+    xchg_arrive_warp(&xbar[2], nc, lane);
+    xchg_wait_warp(&xbar[2], lane);
+    LV_STAMP(13);
+    for (int g = warp; g < cells_here; g += kThreads / 32) {            // softmax over regions: warp per cell
+      int cb, cp;
+      int64_t ccell;
+      cell_of(a, tile * a.G + g, cb, cp, ccell);
+      float lg0 = -INFINITY, lg1 = -INFINITY;
+      if (lane < R) {
+        lg0 = 0.f;
+        for (int cc = 0; cc < nc; ++cc) lg0 += s_xl[cc * GRs + g * R + lane];
+      }
+      if (lane + 32 < R) {
+        lg1 = 0.f;
+        for (int cc = 0; cc < nc; ++cc) lg1 += s_xl[cc * GRs + g * R + lane + 32];
+      }
+      const float mx = warp_max(fmaxf(lg0, lg1));
+      const float e0 = lane < R ? expf(lg0 - mx) : 0.f, e1 = lane + 32 < R ? expf(lg1 - mx) : 0.f;
+      const float inv = 1.f / warp_sum(e0 + e1);
+      if (lane < R) {
+        const float at = e0 * inv;
+        if (rank == 0) a.att[ccell * R + lane] = at;
+        float sc = 1.f;
+        if (a.keep != nullptr) sc = a.keep[ccell * R + lane] ? kKeepScale : 0.f;
+        s_patt[g * R + lane] = at * sc;
+      }
+      if (lane + 32 < R) {
+        const float at = e1 * inv;
+        if (rank == 0) a.att[ccell * R + lane + 32] = at;
+        float sc = 1.f;
+        if (a.keep != nullptr) sc = a.keep[ccell * R + lane + 32] ? kKeepScale : 0.f;
+        s_patt[g * R + lane + 32] = at * sc;
+      }
+    }
+    __syncthreads();
+    LV_STAMP(14);
+    for (int item = tid; item < cells_here * ncols; item += kThreads) {  // a2 = q + sum_r patt_r obj_r
+      const int g = item / ncols, j = item - g * ncols;
+      const int bs = (tile * a.G + g) / a.L - b_first;
+      const float* op = s_obj + (bs * ncols + j) * Rp;
+      const float* wp = s_patt + g * R;
+      float t = s_a[item];
+#pragma unroll 4
+      for (int rr = 0; rr < R; ++rr) t = fmaf(wp[rr], op[rr], t);
+      s_a[item] = t;
+    }
+    __syncthreads();
+    for (int g = warp; g < cells_here; g += kThreads / 32) {
       float ss = 0.f;
-      for (int j = 0; j < ncols; ++j) {
-        const float t = s_a[r * ncols + j];
+      for (int j = lane; j < ncols; j += 32) {
+        const float t = s_a[g * ncols + j];
         ss = fmaf(t, t, ss);
       }
-      xchg_put(s_xs + rank * 128, r, ss, nc);
+      ss = warp_sum(ss);
+      xchg_put_uniform(s_xs2 + rank * 128, g, ss, nc, lane);
     }
-    xchg_arrive(&xbar[1], nc);
-    mbar_wait_cluster(&xbar[1], 0);
-    if (r < cells_here) {
+    LV_STAMP(15);
+    xchg_arrive_warp(&xbar[3], nc, lane);
+    xchg_wait_warp(&xbar[3], lane);
+    LV_STAMP(16);
+    if (tid < cells_here) {
+      int cb, cp;
+      int64_t ccell;
+      cell_of(a, tile * a.G + tid, cb, cp, ccell);
       float tot = 0.f;
-      for (int cc = 0; cc < nc; ++cc) tot += s_xs[cc * 128 + r];
-      const float nrm = fmaxf(sqrtf(tot), kTiny);
-      s_nrm[r] = nrm;
-      if (rank == 0) a.nrm[ccell] = nrm;
+      for (int cc = 0; cc < nc; ++cc) tot += s_xs2[cc * 128 + tid];
+      const float nrm2 = fmaxf(sqrtf(tot), kTiny);
+      s_nrm2[tid] = nrm2;
+      if (rank == 0) a.nrm2[ccell] = nrm2;
     }
-    epi_bar_sync();
-    const bool vl = a.R > 0;
-    for (int item = r; item < cells_here * nc4; item += 128) {
+    __syncthreads();
+    for (int item = tid; item < cells_here * nc4; item += kThreads) {
       const int g = item / nc4, j4 = item - g * nc4;
-      const float inv = 1.f / s_nrm[g];
-      float4 t = ld4(s_a + g * ncols + j4 * 4);
-      t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
-      st4(s_a + g * ncols + j4 * 4, t);
       if (n0 + j4 * 4 < D) {
+        const float inv = 1.f / s_nrm2[g];
+        float4 t = ld4(s_a + g * ncols + j4 * 4);
+        t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
         int b2_, p2_;
         int64_t cell2;
         cell_of(a, tile * a.G + g, b2_, p2_, cell2);
-        st4((vl ? a.q : a.chart_h) + cell2 * D + n0 + j4 * 4, t);
-      }
-    }
-    if (vl) {
-      // region attention of every cell against ITS OWN image only (the reference computes all B x B pairs and
-      // keeps the diagonal, cliora.py:35-42)
-      const int R = a.R, GRs = a.G * R;
-      float* s_att = s_a + kRows * ncols;       // [G][R]
-      float* s_patt = s_att + GRs;              // [G][R]
-      epi_bar_sync();
-      for (int item = r; item < cells_here * R; item += 128) {
-        const int g = item / R, rr = item - g * R;
-        const int bg = (tile * a.G + g) / a.L;
-        const float* op = a.obj + ((int64_t)bg * R + rr) * D + n0;
-        const float* qp = s_a + g * ncols;
-        float d = 0.f;
-#pragma unroll 5
-        for (int j = 0; j < ncols; j += 4) {
-          if (n0 + j < D) {
-            const float4 qv = ld4(qp + j), ov = ldcg4(op + j);
-            d = fmaf(qv.x, ov.x, d); d = fmaf(qv.y, ov.y, d); d = fmaf(qv.z, ov.z, d); d = fmaf(qv.w, ov.w, d);
-          }
-        }
-        xchg_put(s_xl + rank * GRs, item, d, nc);
-      }
-      xchg_arrive(&xbar[2], nc);
-      mbar_wait_cluster(&xbar[2], 0);
-      if (r < cells_here) {
-        float mx = -INFINITY;
-        for (int rr = 0; rr < R; ++rr) {
-          float lg = 0.f;
-          for (int cc = 0; cc < nc; ++cc) lg += s_xl[cc * GRs + r * R + rr];
-          s_att[r * R + rr] = lg;
-          mx = fmaxf(mx, lg);
-        }
-        float sum = 0.f;
-        for (int rr = 0; rr < R; ++rr) {
-          const float ex2 = expf(s_att[r * R + rr] - mx);
-          s_att[r * R + rr] = ex2;
-          sum += ex2;
-        }
-        const float inv = 1.f / sum;
-        for (int rr = 0; rr < R; ++rr) {
-          const float at = s_att[r * R + rr] * inv;
-          if (rank == 0) a.att[ccell * R + rr] = at;
-          float sc = 1.f;
-          if (a.keep != nullptr) sc = a.keep[ccell * R + rr] ? kKeepScale : 0.f;
-          s_patt[r * R + rr] = at * sc;
-        }
-      }
-      epi_bar_sync();
-      for (int item = r; item < cells_here * nc4; item += 128) {
-        const int g = item / nc4, j4 = item - g * nc4;
-        float4 t = ld4(s_a + g * ncols + j4 * 4);
-        if (n0 + j4 * 4 < D) {
-          const int bg = (tile * a.G + g) / a.L;
-          const float* op = a.obj + (int64_t)bg * R * D + n0 + j4 * 4;
-          const float* wp = s_patt + g * R;
-          for (int rr = 0; rr < R; ++rr) {
-            const float w = wp[rr];
-            const float4 ov = ldcg4(op + (int64_t)rr * D);
-            t.x = fmaf(w, ov.x, t.x); t.y = fmaf(w, ov.y, t.y); t.z = fmaf(w, ov.z, t.z); t.w = fmaf(w, ov.w, t.w);
-          }
-        }
-        st4(s_a + g * ncols + j4 * 4, t);
-      }
-      epi_bar_sync();
-      if (r < cells_here) {
-        float ss = 0.f;
-        for (int j = 0; j < ncols; ++j) {
-          const float t = s_a[r * ncols + j];
-          ss = fmaf(t, t, ss);
-        }
-        xchg_put(s_xs2 + rank * 128, r, ss, nc);
-      }
-      xchg_arrive(&xbar[3], nc);
-      mbar_wait_cluster(&xbar[3], 0);
-      if (r < cells_here) {
-        float tot = 0.f;
-        for (int cc = 0; cc < nc; ++cc) tot += s_xs2[cc * 128 + r];
-        const float nrm2 = fmaxf(sqrtf(tot), kTiny);
-        s_nrm2[r] = nrm2;
-        if (rank == 0) a.nrm2[ccell] = nrm2;
-      }
-      epi_bar_sync();
-      for (int item = r; item < cells_here * nc4; item += 128) {
-        const int g = item / nc4, j4 = item - g * nc4;
-        if (n0 + j4 * 4 < D) {
-          const float inv = 1.f / s_nrm2[g];
-          float4 t = ld4(s_a + g * ncols + j4 * 4);
-          t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
-          int b2_, p2_;
-          int64_t cell2;
-          cell_of(a, tile * a.G + g, b2_, p2_, cell2);
-          st4(a.chart_h + cell2 * D + n0 + j4 * 4, t);
-        }
+        st4(a.chart_h + cell2 * D + n0 + j4 * 4, t);
       }
     }
   }
+  LV_STAMP(17);
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols_alloc) : "memory");
   }
   cluster_sync_all();          // no CTA leaves while a peer may still store into its shared memory
+  if (dbg_row && tid == 0) { dbg_row[18] = clock_now(); dbg_row[31] = global_ns(); }
+#undef LV_STAMP
 }
 
 // ---------------------------------------------------------------- host side
@@ -589,33 +748,74 @@ struct LevelGeom {
 };
 inline bool level_geom(int D, LevelGeom& g) {
   if (D < 32 || (D % 4) != 0) return false;
-  int nc = ceil_div(D, 80);
-  if (nc > kMaxCluster) nc = ceil_div(D, kMaxUmmaN);
+  // power-of-two clusters pack the GPCs best (measured: 26 clusters of 5 are co-resident on a B200, 33 of 4)
+  int nc = 1;
+  while (nc <= kMaxCluster && ceil_div(D, nc) > kMaxUmmaN) nc *= 2;
   if (nc > kMaxCluster) return false;
+  if (g_debug[11] > 0 && g_debug[11] <= kMaxCluster && ceil_div(D, g_debug[11]) <= kMaxUmmaN) nc = g_debug[11];
   int ncols = ((ceil_div(D, nc) + 3) / 4) * 4;
   g.nc = nc;
   g.ncols = ncols;
   g.n_umma = ((ncols + 15) / 16) * 16;
   return g.n_umma <= kMaxUmmaN;
 }
-// cells per tile: whole cells only, G*N <= 128; for CLIORA the logit exchange buffer bounds G*R*nc; otherwise spread the
-// level's cells over about one wave of clusters
-inline int level_cells_per_tile(int cells, int N, int R, int nc) {
+// clusters of this shape that can be resident at once (cached per device and shape)
+int max_active_clusters(int nc, size_t smem);
+// cells per tile: whole cells only, G*N <= 128.  CLIORA adds two bounds: the logit exchange buffer (G*R*nc floats) and
+// the shared-memory staging of the region slices of every image a tile can span ((G-1)/L + 2 sentences).  Otherwise the
+// level's cells are spread over about one wave of clusters.
+inline int level_cells_per_tile(int cells, int N, int L, int R, const LevelGeom& g, int target_tiles, int& max_sent) {
   int gmax = kRows / N;
+  max_sent = 0;
   if (R > 0) {
-    const int gv = kXlFloats / (R * nc);
+    const int gv = kXlFloats / (R * g.nc);
     if (gv < gmax) gmax = gv;
   }
   if (gmax < 1) return 0;
-  const int target_tiles = 132 / nc > 0 ? 132 / nc : 1;
+  if (target_tiles < 1) target_tiles = 1;
   int G = ceil_div(cells, target_tiles);
   if (G < 1) G = 1;
   if (G > gmax) G = gmax;
+  if (R > 0) {
+    const int64_t area = (int64_t)ring_bytes(g.n_umma) / 4;     // floats in the operand rings
+    for (; G >= 1; --G) {
+      max_sent = (G - 1) / L + 2;
+      const int64_t need = (int64_t)kRows * (g.ncols + 4) + (int64_t)kRows * g.ncols + 2 * ((G * R + 3) & ~3) +
+                           (int64_t)max_sent * g.ncols * (R | 1);
+      if (need <= area) break;
+    }
+  }
   return G;
 }
-inline size_t level_fwd_smem(int n_umma) { return (size_t)kStages * (2 * kABytes + 2 * n_umma * 128) + kExtraBytes + 1024; }
+inline size_t level_fwd_smem(int n_umma);
+inline int max_active_clusters_query(int nc, size_t smem) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nc, 148, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (func_attr_at_least(reinterpret_cast<const void*>(level_fwd_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, level_fwd_kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 132 / nc;
+  }
+  return n;
+}
+inline size_t level_fwd_smem(int n_umma) { return (size_t)ring_bytes(n_umma) + kExtraBytes; }
 
-inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a, const float* W2pair, const char* tag) {
+extern long long* g_level_dbg;   // debug: timeline buffer handed to the launch selected by g_debug[8] (level + 1) / g_debug[9] (outside)
+
+inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a_in, const float* W2pair, const char* tag) {
+  LevelFwdArgs a = a_in;
+  a.exp_flags = g_debug[12];
+  a.dbg = (g_level_dbg != nullptr && g_debug[8] == a.level + 1 && g_debug[9] == a.outside) ? g_level_dbg : nullptr;
   CUtensorMap tmW;
   CL_TRY(tc::make_pair_map(&tmW, W2pair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
                            a.mode == 1 ? 1 : 2));

@@ -325,6 +325,9 @@ int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_
  * 102  1 = narrow tcgen05 tile allocates 256 TMEM columns       103  narrow tile pipeline depth (2, 3 [default], 4)
  * 104  CTA target of the small-GEMM split-K (default 4 x 148)   105  1 = allow the 128x48 tcgen05 tile */
 void cliora_debug_set(int key, int value);
+/* Development only: hands a device buffer to an instrumented kernel (key 0: int64 [ctas][32] timeline of the fused
+ * level kernel selected by debug keys 8 (level + 1) and 9 (outside)). */
+void cliora_debug_ptr(int key, void* p);
 int cliora_tc_linear(int M, int N, int K, const float* A_pair, const float* W_pair, const float* bias, int act,
                      float* C, cliora_stream_t stream);
 

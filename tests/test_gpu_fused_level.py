@@ -20,6 +20,7 @@ def _run(B, n, D, R, share, fused, train, seed=3):
     else:
         from cliora_b200.net.diora import DioraMLP
     _lib.lib().cliora_debug_set(6, 0 if fused else 1)
+    _lib.lib().cliora_debug_set(10, 1)      # have the fused kernel emit the (optional) ReLU bit masks too
     try:
         P0 = O.init_params(D, share=share, seed=seed)
         g = torch.Generator().manual_seed(seed + 1)
@@ -44,6 +45,7 @@ def _run(B, n, D, R, share, fused, train, seed=3):
         return out, ws, lay
     finally:
         _lib.lib().cliora_debug_set(6, 0)
+        _lib.lib().cliora_debug_set(10, 0)
 
 
 SHAPES = [(4, 10, 400, 36, True, True), (3, 8, 400, 0, False, False), (2, 20, 400, 36, True, True),
@@ -71,13 +73,22 @@ def test_fused_level_forward_matches_unfused_chain(B, n, D, R, share, train):
     for name, off, count, tol in checks:
         if count:
             assert rel_err(seg(ws1, off, count), seg(ws0, off, count)) < tol, name
-    # hidden activations: the very same fp32 adds in both paths -> identical pairs and identical ReLU masks
-    for name, off, count in (('Zin', lay.Zin, 2 * rows_in * D), ('Zout', lay.Zout, 2 * rows_out * D)):
-        if count:
-            assert torch.equal(seg(ws1, off, count), seg(ws0, off, count)), name
+    # hidden activations: same fp32 adds in both paths, but their inputs (the lower levels' cell vectors) already
+    # differ in the last bits between the two paths (summation order of the per-cell reductions), so the pairs agree to
+    # rounding and the ReLU masks everywhere except at pre-activations within rounding of zero
+    for name, off, rows in (('Zin', lay.Zin, rows_in), ('Zout', lay.Zout, rows_out)):
+        if rows:
+            z1 = seg(ws1, off, rows * D) + seg(ws1, off + rows * D, rows * D)
+            z0 = seg(ws0, off, rows * D) + seg(ws0, off + rows * D, rows * D)
+            assert rel_err(z1, z0) < 2e-5, name
+            lo1 = seg(ws1, off + rows * D, rows * D)
+            assert float(lo1.abs().max()) <= 2.0 ** -10 * float(z1.abs().max()) + 1e-30, name + ' lo part'
     if lay.Mbin >= 0:
         for name, off, count in (('Mbin', lay.Mbin, rows_in * 16), ('Mbout', lay.Mbout, rows_out * 16)):
             if count:
-                assert torch.equal(seg(ws1, off, count).view(torch.int32), seg(ws0, off, count).view(torch.int32)), name
+                x = seg(ws1, off, count).view(torch.int32) ^ seg(ws0, off, count).view(torch.int32)
+                x = x.view(-1, 16)[:, :4 * ((D + 127) // 128)]      # words of 128-column groups beyond D are never written
+                flipped = sum(int(((x >> i) & 1).sum()) for i in range(32))
+                assert flipped <= max(2, int(1e-5 * count * 32)), (name, flipped)
     for k in ref:
         assert rel_err(got[k], ref[k]) < 2e-5, k
