@@ -157,6 +157,11 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   L.Hp = take(2 * B * C * D);         // split pair of the chart vectors
   L.CSin = take(B * C * D);           // per-cell sums of the GY rows (zero for cells without splits)
   L.CSout = take(B * C * D);
+  L.GYp_in = take(2 * L.rows_in * D);
+  L.GYp_out = take(2 * L.rows_out * D);
+  L.GA = take(B * C * D);
+  L.CM = take(B * C);
+  L.db2acc = take(2 * D);
   L.bws_floats = o;
   return CLIORA_OK;
 }
@@ -424,7 +429,7 @@ static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g, float* cellsum) {
     return CLIORA_OK;
   }
   CellBwdArgs gb = g;
-  if (g.c.D <= 512 && g.c.E != nullptr && g_debug[4] == 0) gb.cellsum = cellsum;
+  if (g.c.D <= 512 && g.c.E != nullptr && g_debug[4] == 0 && g.ga_out == nullptr) gb.cellsum = cellsum;
   const size_t smem = (size_t)(2 * g.c.D + 3 * g.c.R + 64 + (gb.cellsum ? 8 * g.c.D + 4 : 0)) * sizeof(float);
   launch_k(cell_bwd_kernel<VL>, g.c.B * g.c.L, 256, smem, c.st, gb);
   CL_CHECK_LAUNCH("cell_bwd_kernel");
@@ -438,6 +443,12 @@ static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g) {
   if (!lvl::level_geom(c.d.D, g)) return false;
   if (c.d.D > 1024) return false;
   return true;
+}
+
+// The fused backward needs every level of a pass to qualify (its compose-output gradients live in one buffer per pass)
+static bool fused_bwd_ok(const Ctx& c) {
+  lvl::LevelGeom g;
+  return g_debug[7] == 0 && c.d.n >= 2 && fused_level_ok(c, c.d.n - 1, g);
 }
 
 static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::LevelGeom& geom, const cliora_weights* w,
@@ -501,8 +512,47 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   g.gu = bws + c.L.gu;
   // GE is level-local here: point the kernel at a level block starting at GE[0]
   // (cell_bwd indexes GE with the same row ids as E, relative to the level block).
-  CL_TRY(launch_cell_bwd<VL>(c, g, bws + (OUTSIDE ? c.L.CSout : c.L.CSin)));
+  const bool fused = g.c.E != nullptr && fused_bwd_ok(c);
+  if (fused) {
+    g.ga_out = bws + c.L.GA;
+    g.cm_out = bws + c.L.CM;
+  }
+  CL_TRY(launch_cell_bwd<VL>(c, g, fused ? nullptr : bws + (OUTSIDE ? c.L.CSout : c.L.CSin)));
   if (g.c.E == nullptr) return CLIORA_OK;  // leaf level: no splits
+  if (fused) {
+    lvl::LevelGeom geom;
+    fused_level_ok(c, g.c.N, geom);
+    const bool sh = c.d.share != 0;
+    lvl::LevelBwdArgs b{};
+    lvl::LevelFwdArgs& a = b.geo;
+    a.B = B; a.n = n; a.level = level; a.L = n - level; a.N = g.c.N; a.D = D; a.R = 0;
+    a.cells = B * a.L;
+    a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
+    int max_sent = 0;
+    a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, 148 / geom.nc, max_sent);
+    a.mode = c.tc_mode == 1 ? 1 : 2;
+    a.outside = OUTSIDE ? 1 : 0;
+    a.C = c.C;
+    const int64_t r0 = OUTSIDE ? B * outside_rows_before(n, level) : B * inside_rows_before(n, level);
+    const int ldPin = (int)(c.L.PI * D);
+    b.Y = ws + (OUTSIDE ? c.L.Yout : c.L.Yin) + r0 * D;
+    b.Zhi = ws + (OUTSIDE ? c.L.Zout : c.L.Zin) + r0 * D;
+    b.Pr = ws + (OUTSIDE ? c.L.Prout : c.L.Prin) + r0;
+    b.E = ws + (OUTSIDE ? c.L.Eout : c.L.Ein) + r0;
+    b.GA = bws + c.L.GA; b.CM = bws + c.L.CM;
+    b.Gs = bws + (OUTSIDE ? c.L.Gs_out : c.L.Gs_in);
+    b.h1 = ih;
+    if (!OUTSIDE) { b.P2 = ws + c.L.Pin; b.ld2 = ldPin; b.off_a2 = D; b.off_v2 = 2 * D; b.GP2 = bws + c.L.GP_in; }
+    else { b.P2 = ws + c.L.Pout; b.ld2 = 2 * D; b.off_a2 = 0; b.off_v2 = D; b.GP2 = bws + c.L.GP_out; }
+    b.GP1 = bws + c.L.GP_in; b.ld1 = ldPin; b.off_a1 = (OUTSIDE && !sh) ? 3 * D : 0;
+    b.Gh1 = bws + c.L.Gh_in; b.Gs1 = bws + c.L.Gs_in;
+    b.Gs2 = bws + (OUTSIDE ? c.L.Gs_out : c.L.Gs_in);
+    b.GYp = bws + (OUTSIDE ? c.L.GYp_out : c.L.GYp_in) + r0 * D;
+    b.gy_lo_off = (OUTSIDE ? c.L.rows_out : c.L.rows_in) * D;
+    b.db2 = bws + c.L.db2acc + (OUTSIDE ? D : 0);
+    const float* W2T = ws + (OUTSIDE ? c.L.oW2Tp : c.L.W2Tp);
+    return lvl::launch_level_bwd(c.st, b, W2T, OUTSIDE ? "level_bwd_outside" : "level_bwd_inside");
+  }
 
   const float* W2 = (OUTSIDE && !c.d.share) ? w->oW2 : w->W2;
   const float* b1 = (OUTSIDE && !c.d.share) ? w->ob1 : w->b1;
@@ -731,6 +781,7 @@ int cliora_chart_bwd_begin(const cliora_dims* dims, const float* g_inside_h, con
   CL_CUDA(cudaMemsetAsync(bws + c.L.GP_in, 0, BC * c.L.PI * D * sizeof(float), c.st));
   CL_CUDA(cudaMemsetAsync(bws + c.L.GP_out, 0, BC * 2 * D * sizeof(float), c.st));
   CL_CUDA(cudaMemsetAsync(bws + c.L.CSin, 0, 2 * BC * D * sizeof(float), c.st));   // CSin and CSout are adjacent
+  CL_CUDA(cudaMemsetAsync(bws + c.L.db2acc, 0, 2 * D * sizeof(float), c.st));
   return CLIORA_OK;
 }
 
@@ -766,7 +817,8 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
   float* dW2 = sh ? grads->W2 : grads->oW2;
   float* db2 = sh ? grads->b2 : grads->ob2;
   float* dWb = sh ? grads->Wb : grads->oWb;
-  const float* GY = ws + c.L.Yout;
+  const bool fusedb = fused_bwd_ok(c);
+  const float* GY = fusedb ? bws + c.L.GYp_out : ws + c.L.Yout;
   const float* Z = ws + c.L.Zout;
   const float* GPo = bws + c.L.GP_out;
   const int64_t lo_out = c.use_tc ? c.L.rows_out * D : 0;
@@ -778,7 +830,9 @@ int cliora_outside_bwd(const cliora_dims* dims, const cliora_weights* w, const f
       CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_out, D, D, GY, D, Z, D, dW2, D, 0, scratch, "gemm_wgrad", 0, 0));
     }
   }
-  if (db2) {
+  if (db2 && fusedb) {
+    CL_TRY(colsum(c.st, bws + c.L.db2acc + D, D, 1, D, db2, 0, scratch));
+  } else if (db2) {
     if (cellsum_enabled(c, true)) {
       CL_TRY(colsum(c.st, bws + c.L.CSout, D, BC, D, db2, 0, scratch));
     } else {
@@ -841,7 +895,8 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
   if (grads->b_leaf) CL_TRY(colsum(c.st, gu, D, (int64_t)B * n, D, grads->b_leaf, 0, scratch));
 
   const int acc = (c.d.share && had_outside) ? 1 : 0;
-  const float* GY = ws + c.L.Yin;
+  const bool fusedb = fused_bwd_ok(c);
+  const float* GY = fusedb ? bws + c.L.GYp_in : ws + c.L.Yin;
   const float* Z = ws + c.L.Zin;
   const float* GPi = bws + c.L.GP_in;
   const int ldp = PI * D;
@@ -854,7 +909,9 @@ int cliora_inside_bwd(const cliora_dims* dims, const cliora_weights* w, const fl
       CL_TRY(launch_gemm_tn(c.st, (int)c.L.rows_in, D, D, GY, D, Z, D, grads->W2, D, acc, scratch, "gemm_wgrad", 0, 0));
     }
   }
-  if (grads->b2) {
+  if (grads->b2 && fusedb) {
+    CL_TRY(colsum(c.st, bws + c.L.db2acc, D, 1, D, grads->b2, acc, scratch));
+  } else if (grads->b2) {
     if (cellsum_enabled(c, false)) {
       CL_TRY(colsum(c.st, bws + c.L.CSin, D, BC, D, grads->b2, acc, scratch));
     } else {

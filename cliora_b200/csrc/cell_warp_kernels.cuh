@@ -329,10 +329,18 @@ __global__ __launch_bounds__(kCellThreads) void cell_bwd_warp_kernel(const CellB
         const float gs = g.Gs[cell];
         s_sc[warp * 2] = gs;
         s_sc[warp * 2 + 1] = nrm * ad + a.chart_s[cell] * gs;   // sum_m p_m gp_m
+        if (g.ga_out != nullptr) g.cm_out[cell] = s_sc[warp * 2 + 1];
+      }
+      if (g.ga_out != nullptr) {     // cells-only mode: the fused level kernel does the per-split part
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (j < a.D) st4(g.ga_out + cell * a.D + j, gv[t]);
+        }
       }
     }
   }
-  if (a.E == nullptr) return;   // uniform over the CTA
+  if (a.E == nullptr || g.ga_out != nullptr) return;   // uniform over the CTA
   __syncthreads();
   const int ncell = min(kCellsPerCta, a.L - p0);
   const int items = ncell * a.N;

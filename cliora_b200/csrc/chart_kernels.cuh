@@ -324,6 +324,10 @@ struct CellBwdArgs {
   const float* leaf_t;   // leaf mode: tanh outputs [B*n, D]
   float* gu;             // leaf mode out: gradient wrt the pre-tanh activations [B*n, D]
   float* cellsum;        // [B,C,D] out or null: sum over the cell's splits of the GY rows (colsum of these = db2)
+  // cells-only mode (the fused level backward kernel does the per-split part): when ga_out != null the kernel stores
+  // the gradient wrt the cell's pre-normalisation sum and the softmax constant sum_m p_m gp_m, and stops there
+  float* ga_out;         // [B,C,D]
+  float* cm_out;         // [B,C]
 };
 
 // One block per cell.  Dynamic shared memory: (2D + 3R + 64) floats, + 8D when cellsum != null.
@@ -432,6 +436,11 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
     }
     const float gs = g.Gs[cell];
     const float cm = nrm * ad + a.chart_s[cell] * gs;   // sum_m p_m gp_m
+    if (g.ga_out != nullptr) {     // cells-only mode
+      for (int j = tid * 4; j < a.D; j += blockDim.x * 4) st4(g.ga_out + cell * a.D + j, ld4(s_g + j));
+      if (tid == 0) g.cm_out[cell] = cm;
+      return;
+    }
     // ---- per split: ge, gy ----
     const bool want_sum = g.cellsum != nullptr;     // only offered for D <= 512 (one 4-chunk round per row)
     float4 bacc[4];

@@ -198,11 +198,36 @@ CL_D void split_trunc(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+CL_D void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+CL_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 8 tf32) is read from tensor memory -- lane = row, one
+// 32-bit column per k element -- so the tensor core spends no shared-memory bandwidth on it
+CL_D void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+constexpr uint32_t kTmemA0 = 256;      // first column of the A-operand stages in tensor memory (64 columns per stage)
+
 // zero-filling 16-byte asynchronous copy (src_bytes = 0 writes zeros)
 CL_D void cp_async16_zfill(uint32_t dst_saddr, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(src_bytes) : "memory");
 }
 
+template <bool A_TMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) {
   pdl_prologue();
@@ -246,7 +271,8 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   float* s_xs2 = s_xs + kMaxCluster * 128;        // [nc][128] partial |a2|^2
   float* s_xl = s_xs2 + kMaxCluster * 128;        // [nc][G*R] partial region logits
   long long* s_m = reinterpret_cast<long long*>(s_xl + kXlFloats);   // [128] global row of every tile row, -1 = none
-  const uint32_t tmem_cols_alloc = (uint32_t)tc::tmem_cols(2 * a.n_umma);
+  // A_TMEM: accumulators in columns [0, 2 n_umma), four A-operand stages (hi 32 | lo 32 columns each) from column 256
+  const uint32_t tmem_cols_alloc = A_TMEM ? 512u : (uint32_t)tc::tmem_cols(2 * a.n_umma);
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmW);
   if (warp == 1) {
@@ -307,9 +333,18 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
         const uint64_t a_hi = umma_desc_k_sw128(sa), a_lo = umma_desc_k_sw128(sa + kABytes);
         const uint64_t b_hi = umma_desc_k_sw128(sbb);
         const uint64_t b_lo = umma_desc_k_sw128(sbb + b_bytes);
+        const uint32_t ta_hi = tmem_base + kTmemA0 + (uint32_t)(sA_i * 64), ta_lo = ta_hi + 32;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (a.mode == 1) {
+          if (A_TMEM) {
+            if (a.mode == 1) {
+              umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, acc);
+            } else {
+              umma_tf32_ts(tmem_base + a.n_umma, ta_lo + 8 * k, b_hi + 2 * k, idesc, acc);
+              umma_tf32_ts(tmem_base + a.n_umma, ta_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+              umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, acc);
+            }
+          } else if (a.mode == 1) {
             umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
           } else {
             umma_tf32(tmem_base + a.n_umma, a_lo + 2 * k, b_hi + 2 * k, idesc, acc);
@@ -325,6 +360,100 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       umma_commit(tmem_full);
       if (dbg_row) dbg_row[21] = clock_now();
     }
+  } else if (warp >= kProdWarp0 && A_TMEM) {
+    // ------------------------------------------------------------ A operand -> tensor memory
+    // Copy side (as below): thread owns chunk c of rows rbase + 32 i; cp.async lands the two projection rows of every
+    // split in the raw stage (first 16 KB: first operand, second 16 KB: second operand), 128-byte swizzled.
+    // Transform side: thread = split row r (TMEM lane), the warp's column half h; it reads 16 floats of each raw row,
+    // z = relu(al + ar + b1) -> (hi, lo), and writes them into the TMEM stage with tcgen05.st.  The MMAs then take A
+    // from tensor memory: no shared-memory writes for the pair, no shared-memory reads by the tensor core for A.
+    constexpr int kLookahead = 2;
+    const int pt = tid - kProdWarp0 * 32;      // 0..255
+    const int c = pt & 7;
+    const int rbase = (pt >> 3);
+    const float* pa[4];
+    const float* pb[4];
+    bool ok[4];
+    uint32_t soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rbase + 32 * i;
+      const RowInfo ri = decode_row(a, tile, cells_here, r);
+      ok[i] = ri.ok;
+      pa[i] = a.P1 + ri.g1 * a.ld1 + a.off_a1 + c * 4;
+      pb[i] = a.P2 + ri.g2 * a.ld2 + a.off_a2 + c * 4;
+      soff[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+    }
+    const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;     // TMEM lane quarter, 16-column half of the k-block
+    const int row = qd * 32 + lane;
+    const RowInfo rme = decode_row(a, tile, cells_here, row);
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    if (dbg_row && pt == 0) dbg_row[22] = clock_now();
+    const uint32_t smem_base = smem_u32(smem);
+    int zturn = 0;
+    for (int it = 0; it < num_kb + kLookahead; ++it) {
+      if (it < num_kb) {
+        const int stage = it % kAStages;
+        const int kcol = it * 32 + c * 4;
+        const uint32_t sA = smem_base + (uint32_t)(stage * a_stage_bytes);
+        if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[32 + (it - 4) * 4] = clock_now();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t nbytes = (ok[i] && kcol < D) ? 16u : 0u;
+          cp_async16_zfill(sA + soff[i], pa[i] + it * 32, nbytes);
+          cp_async16_zfill(sA + kABytes + soff[i], pb[i] + it * 32, nbytes);
+        }
+      }
+      cp_async_commit();
+      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[33 + (it - 4) * 4] = clock_now();
+      const int kb = it - kLookahead;
+      if (kb < 0) continue;
+      const int stage = kb % kAStages;
+      mbar_wait(&emptyA[stage], ((kb / kAStages) & 1) ^ 1);      // the MMAs that read this TMEM stage have retired
+      tcgen05_fence_after();
+      cp_async_wait<kLookahead>();
+      asm volatile("bar.sync 3, %0;" ::"r"(kProdWarps * 32) : "memory");   // everybody's copies of k-block kb landed
+      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[34 + (it - 4) * 4] = clock_now();
+      const uint8_t* sA = smem + stage * a_stage_bytes + row * 128;
+      const int k0 = kb * 32 + half * 16;
+      float hi[16], lo[16];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ch = ((half * 4 + t) ^ (row & 7)) << 4;
+        const float4 xa = *reinterpret_cast<const float4*>(sA + ch);
+        const float4 xb = *reinterpret_cast<const float4*>(sA + kABytes + ch);
+        const int kc = k0 + t * 4;
+        const float4 bv = kc < D ? __ldg(reinterpret_cast<const float4*>(a.b1 + kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = fmaxf(xa.x + xb.x + bv.x, 0.f);
+        o.y = fmaxf(xa.y + xb.y + bv.y, 0.f);
+        o.z = fmaxf(xa.z + xb.z + bv.z, 0.f);
+        o.w = fmaxf(xa.w + xb.w + bv.w, 0.f);
+        if (!rme.ok || kc >= D) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        split_trunc(o.x, hi[4 * t], lo[4 * t]); split_trunc(o.y, hi[4 * t + 1], lo[4 * t + 1]);
+        split_trunc(o.z, hi[4 * t + 2], lo[4 * t + 2]); split_trunc(o.w, hi[4 * t + 3], lo[4 * t + 3]);
+      }
+      const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
+      tmem_st16(ta, hi);
+      if (a.mode != 1) tmem_st16(ta + 32, lo);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&fullA[stage]);
+      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[35 + (it - 4) * 4] = clock_now();
+      if (a.Z != nullptr && zturn == rank && rme.ok) {            // this CTA's turn to stream the Z pair out
+        float* zp = a.Z + rme.m * D + k0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (k0 + 4 * t < D) {
+            st4(zp + 4 * t, make_float4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]));
+            st4(zp + a.z_lo_off + 4 * t, make_float4(lo[4 * t], lo[4 * t + 1], lo[4 * t + 2], lo[4 * t + 3]));
+          }
+        }
+      }
+      zturn = (zturn + 1 == nc) ? 0 : zturn + 1;
+    }
+    if (dbg_row && pt == 0) dbg_row[23] = clock_now();
   } else if (warp >= kProdWarp0) {
     // ------------------------------------------------------------ A operand: gather + ReLU + tf32 split
     // Each thread owns chunk c of rows rbase + 32 i.  The two projection rows of a split are copied asynchronously
@@ -742,6 +871,320 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
 #undef LV_STAMP
 }
 
+// ==========================================================================================
+// level_bwd_kernel: the per-split part of a level's backward in one launch (replaces the per-split loop of cell_bwd,
+// the GZ GEMM and split_scatter).  The per-cell part (normalise / attention backward) runs before it in cells-only
+// mode of the cell kernels and leaves GA = d loss / d a (pre-normalisation cell sum) and the softmax constant CM.
+//   per split row (cell c, split k):  gy = p_k * GA_c * [y_k > 0]         (A operand, built by the producer warps)
+//                                     d_k = y_k . GA_c;  ge_k = p_k (gs_c + d_k + e_k gs_c - cm_c)
+//   GZ = (GY W2) * [z > 0]            (tcgen05, W2^T slice by TMA; epilogue masks with the sign of the stored Z)
+//   scatter: GP[first].A += GZ, GP[second].A += GZ, Gh[first] += ge V[second], GP[second].V += ge h[first],
+//            Gs[first] += ge, Gs[second] += ge            (red.global.add, as split_scatter did)
+//   db2 += column sums of GY (warps 2-5 while the MMAs run);  the GY pair is streamed out for the dW2 GEMM.
+// Grid (nc column slices, tiles); no cluster: a CTA needs nothing from its column neighbours.
+// ==========================================================================================
+struct LevelBwdArgs {
+  LevelFwdArgs geo;          // geometry only: B, n, level, L, N, D, G, cells, ncols, n_umma, nc, mode, outside, C
+  const float* Y;            // level block [rows, D]: forward compose outputs
+  const float* Zhi;          // level block [rows, D]: hi part of the hidden activations (its sign is the ReLU mask)
+  const float* Pr; const float* E;       // level blocks [rows]
+  const float* GA; const float* Gs; const float* CM;   // [B,C,D], [B,C], [B,C] of this pass's chart
+  const float* h1;           // chart vectors of `first` [B,C,D]
+  const float* P2; int ld2; int off_a2; int off_v2;    // forward projection row of `second` (V part read here)
+  float* GP1; int ld1; int off_a1;       // projection-gradient row of `first`
+  float* GP2;                            // projection-gradient row of `second` (same pitch / offsets as P2)
+  float* Gh1; float* Gs1; float* Gs2;    // vector / score gradient accumulators of first, score of second
+  float* GYp; int64_t gy_lo_off;         // level block pair out [2][rows, D]
+  float* db2;                            // [D] accumulator
+};
+
+constexpr int kBwdExtraBytes = 256 + 128 * 8 + 4 * (128 * 5 + 128);   // barriers, row ids, p/cell/d0/d1/ge, b-unused
+
+template <int DUMMY>
+__global__ void __launch_bounds__(kThreads, 1)
+level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) {
+  pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  const LevelFwdArgs& a = g.geo;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = blockIdx.x;
+  const int tile = blockIdx.y;
+  const int n0 = rank * a.ncols;
+  const int D = a.D;
+  const int num_kb = (D + 31) / 32;
+  const int b_bytes = a.n_umma * 128;
+  const int nbs = b_stages(a.n_umma);
+  const int a_stage_bytes = 2 * kABytes, b_stage_bytes = 2 * b_bytes;
+  uint8_t* ringB = smem + kAStages * a_stage_bytes;
+  const int cells_here = min(a.G, a.cells - tile * a.G);
+  const int nc = a.nc, ncols = a.ncols;
+
+  uint8_t* ex = smem + ring_bytes(a.n_umma);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(ex);
+  uint64_t* emptyA = fullA + kAStages;
+  uint64_t* fullB = emptyA + kAStages;
+  uint64_t* emptyB = fullB + 3;
+  uint64_t* tmem_full = emptyB + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  long long* s_m = reinterpret_cast<long long*>(ex + 256);          // [128] global row, -1 = none
+  float* s_p = reinterpret_cast<float*>(s_m + 128);                  // [128] softmax probability of the row
+  int* s_cell = reinterpret_cast<int*>(s_p + 128);                   // [128] chart cell (b*C + c) of the row
+  float* s_d = reinterpret_cast<float*>(s_cell + 128);               // [2][128] y . ga, one half of the columns each
+  float* s_ge = s_d + 256;                                           // [128]
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmW);
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kAStages; ++i) {
+        mbar_init(&fullA[i], kProdWarps);
+        mbar_init(&emptyA[i], 1);
+      }
+      for (int i = 0; i < 3; ++i) {
+        mbar_init(&fullB[i], 1);
+        mbar_init(&emptyB[i], 1);
+      }
+      mbar_init(tmem_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < 128) {
+    const RowInfo ri = decode_row(a, tile, cells_here, tid);
+    s_m[tid] = ri.ok ? (long long)ri.m : -1ll;
+    s_p[tid] = ri.ok ? g.Pr[ri.m] : 0.f;
+    s_cell[tid] = (int)ri.cell;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(a.mode == 1 ? b_bytes : 2 * b_bytes);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sb = kb % nbs;
+        mbar_wait(&emptyB[sb], ((kb / nbs) & 1) ^ 1);
+        mbar_expect_tx(&fullB[sb], tx);
+        tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kb * 32, n0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(a.n_umma);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sA_i = kb % kAStages, sb = kb % nbs;
+        mbar_wait(&fullB[sb], (kb / nbs) & 1);
+        mbar_wait(&fullA[sA_i], (kb / kAStages) & 1);
+        tcgen05_fence_after();
+        const uint32_t sbb = smem_u32(ringB + sb * b_stage_bytes);
+        const uint64_t b_hi = umma_desc_k_sw128(sbb), b_lo = umma_desc_k_sw128(sbb + b_bytes);
+        const uint32_t ta_hi = tmem_base + kTmemA0 + (uint32_t)(sA_i * 64), ta_lo = ta_hi + 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (a.mode == 1) {
+            umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, acc);
+          } else {
+            umma_tf32_ts(tmem_base + a.n_umma, ta_lo + 8 * k, b_hi + 2 * k, idesc, acc);
+            umma_tf32_ts(tmem_base + a.n_umma, ta_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+            umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, acc);
+          }
+          acc = 1;
+        }
+        umma_commit(&emptyA[sA_i]);
+        umma_commit(&emptyB[sb]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= kProdWarp0) {
+    // ---- A operand: gy = p * ga * [y > 0] -> tensor memory; d = y . ga on the side
+    constexpr int kLookahead = 2;
+    const int pt = tid - kProdWarp0 * 32;
+    const int c = pt & 7;
+    const int rbase = (pt >> 3);
+    const float* pa[4];
+    const float* pb[4];
+    bool ok[4];
+    uint32_t soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rbase + 32 * i;
+      const long long m = s_m[r];
+      ok[i] = m >= 0;
+      pa[i] = g.Y + (ok[i] ? m : 0) * D + c * 4;
+      pb[i] = g.GA + (int64_t)s_cell[r] * D + c * 4;
+      soff[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+    }
+    const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;
+    const int row = qd * 32 + lane;
+    const long long mrow = s_m[row];
+    const float prow = s_p[row];
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const uint32_t smem_base = smem_u32(smem);
+    float dpart = 0.f;
+    int zturn = 0;
+    for (int it = 0; it < num_kb + kLookahead; ++it) {
+      if (it < num_kb) {
+        const int stage = it % kAStages;
+        const int kcol = it * 32 + c * 4;
+        const uint32_t sA = smem_base + (uint32_t)(stage * a_stage_bytes);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t nbytes = (ok[i] && kcol < D) ? 16u : 0u;
+          cp_async16_zfill(sA + soff[i], pa[i] + it * 32, nbytes);
+          cp_async16_zfill(sA + kABytes + soff[i], pb[i] + it * 32, nbytes);
+        }
+      }
+      cp_async_commit();
+      const int kb = it - kLookahead;
+      if (kb < 0) continue;
+      const int stage = kb % kAStages;
+      mbar_wait(&emptyA[stage], ((kb / kAStages) & 1) ^ 1);
+      tcgen05_fence_after();
+      cp_async_wait<kLookahead>();
+      asm volatile("bar.sync 3, %0;" ::"r"(kProdWarps * 32) : "memory");
+      const uint8_t* sA = smem + stage * a_stage_bytes + row * 128;
+      const int k0 = kb * 32 + half * 16;
+      float hi[16], lo[16];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ch = ((half * 4 + t) ^ (row & 7)) << 4;
+        const float4 y = *reinterpret_cast<const float4*>(sA + ch);
+        const float4 ga = *reinterpret_cast<const float4*>(sA + kABytes + ch);
+        dpart = fmaf(y.x, ga.x, dpart); dpart = fmaf(y.y, ga.y, dpart);
+        dpart = fmaf(y.z, ga.z, dpart); dpart = fmaf(y.w, ga.w, dpart);
+        float4 o;
+        o.x = y.x > 0.f ? prow * ga.x : 0.f;
+        o.y = y.y > 0.f ? prow * ga.y : 0.f;
+        o.z = y.z > 0.f ? prow * ga.z : 0.f;
+        o.w = y.w > 0.f ? prow * ga.w : 0.f;
+        split_trunc(o.x, hi[4 * t], lo[4 * t]); split_trunc(o.y, hi[4 * t + 1], lo[4 * t + 1]);
+        split_trunc(o.z, hi[4 * t + 2], lo[4 * t + 2]); split_trunc(o.w, hi[4 * t + 3], lo[4 * t + 3]);
+      }
+      const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
+      tmem_st16(ta, hi);
+      if (a.mode != 1) tmem_st16(ta + 32, lo);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&fullA[stage]);
+      if (g.GYp != nullptr && zturn == rank && mrow >= 0) {
+        float* zp = g.GYp + mrow * D + k0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (k0 + 4 * t < D) {
+            st4(zp + 4 * t, make_float4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]));
+            st4(zp + g.gy_lo_off + 4 * t, make_float4(lo[4 * t], lo[4 * t + 1], lo[4 * t + 2], lo[4 * t + 3]));
+          }
+        }
+      }
+      zturn = (zturn + 1 == nc) ? 0 : zturn + 1;
+    }
+    s_d[half * 128 + row] = dpart;
+  } else {
+    // ---- warps 2-5 while the MMAs run: db2 += column sums of GY over this tile, for this CTA's columns
+    const int j = tid - 64;            // 0..127
+    if (j < ncols && n0 + j < D && g.db2 != nullptr) {
+      float acc = 0.f;
+      const int rows_here = cells_here * a.N;
+#pragma unroll 4
+      for (int r = 0; r < rows_here; ++r) {
+        const float y = __ldcg(g.Y + s_m[r] * D + n0 + j);
+        const float ga = __ldg(g.GA + (int64_t)s_cell[r] * D + n0 + j);
+        acc += y > 0.f ? s_p[r] * ga : 0.f;
+      }
+      atomicAdd(g.db2 + n0 + j, acc);
+    }
+  }
+
+  // ================================================================ every warp: epilogue + scatter
+  mbar_wait(tmem_full, 0);
+  tcgen05_fence_after();
+  __syncthreads();
+  if (tid < 128) {
+    // ge = p (gs + gp - cm), gp = y . ga + e gs      (softmax-weighted-sum backward)
+    const long long m = s_m[tid];
+    float ge = 0.f;
+    if (m >= 0) {
+      const int cell = s_cell[tid];
+      const float gs = g.Gs[cell];
+      const float gp = s_d[tid] + s_d[128 + tid] + g.E[m] * gs;
+      ge = s_p[tid] * (gs + gp - g.CM[cell]);
+    }
+    s_ge[tid] = ge;
+  }
+  if (warp >= 2) {
+    // GZ = acc * [z > 0]; scattered into the projection-gradient rows of the two cells the split read
+    const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
+    const RowInfo ri = decode_row(a, tile, cells_here, r);
+    const float* zrow = ri.ok ? g.Zhi + ri.m * D + n0 : nullptr;
+    float* d1 = g.GP1 + ri.g1 * g.ld1 + g.off_a1 + n0;
+    float* d2 = g.GP2 + ri.g2 * g.ld2 + g.off_a2 + n0;
+#pragma unroll 1
+    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 48) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
+      if (a.mode != 1) {
+        float x[16];
+        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a.n_umma + c0), x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += x[i];
+      }
+      if (ri.ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int col = c0 + j;
+          if (col < ncols && n0 + col < D) {
+            const float4 z = ldcg4(zrow + col);
+            const float4 o = make_float4(z.x > 0.f ? v[j] : 0.f, z.y > 0.f ? v[j + 1] : 0.f, z.z > 0.f ? v[j + 2] : 0.f,
+                                         z.w > 0.f ? v[j + 3] : 0.f);
+            red_add4(d1 + col, o);
+            red_add4(d2 + col, o);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  {
+    // score path: Gh[first] += ge V[second], GP[second].V += ge h[first] over this CTA's columns; eight lanes per row
+    const int rr = tid >> 3, c = tid & 7;          // 56 rows per pass
+    const int nch = ncols >> 2;
+    for (int r = rr; r < cells_here * a.N; r += kThreads / 8) {
+      const RowInfo ri = decode_row(a, tile, cells_here, r);
+      const float ge = s_ge[r];
+      const float* hp = g.h1 + ri.g1 * D + n0;
+      const float* vp = g.P2 + ri.g2 * g.ld2 + g.off_v2 + n0;
+      float* gh = g.Gh1 + ri.g1 * D + n0;
+      float* gv = g.GP2 + ri.g2 * g.ld2 + g.off_v2 + n0;
+      for (int ch = c; ch < nch; ch += 8) {
+        if (n0 + ch * 4 < D) {
+          const float4 hv = ldcg4(hp + ch * 4), vv = ldcg4(vp + ch * 4);
+          red_add4(gh + ch * 4, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
+          red_add4(gv + ch * 4, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
+        }
+      }
+      if (c == 0 && rank == 0) {
+        atomicAdd(g.Gs1 + ri.g1, ge);
+        atomicAdd(g.Gs2 + ri.g2, ge);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 struct LevelGeom {
   int nc, ncols, n_umma;
@@ -801,8 +1244,8 @@ inline int max_active_clusters_query(int nc, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (func_attr_at_least(reinterpret_cast<const void*>(level_fwd_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-      cudaOccupancyMaxActiveClusters(&n, level_fwd_kernel, &cfg) != cudaSuccess || n < 1) {
+  if (func_attr_at_least(reinterpret_cast<const void*>(level_fwd_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, level_fwd_kernel<true>, &cfg) != cudaSuccess || n < 1) {
     cudaGetLastError();
     n = 132 / nc;
   }
@@ -820,7 +1263,9 @@ inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a_in, const flo
   CL_TRY(tc::make_pair_map(&tmW, W2pair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
                            a.mode == 1 ? 1 : 2));
   const size_t smem = level_fwd_smem(a.n_umma);
-  const void* kern = reinterpret_cast<const void*>(level_fwd_kernel);
+  const bool a_tmem = a.zmask == nullptr && g_debug[13] == 0;      // the bit-mask variant keeps the A pair in shared memory
+  const void* kern = a_tmem ? reinterpret_cast<const void*>(level_fwd_kernel<true>)
+                            : reinterpret_cast<const void*>(level_fwd_kernel<false>);
   CL_CUDA(func_attr_at_least(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (g_carveout >= 0) apply_carveout(kern);
   const int tiles = ceil_div(a.cells, a.G);
@@ -840,8 +1285,28 @@ inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a_in, const flo
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, level_fwd_kernel, tmW, a);
+  if (a_tmem) cudaLaunchKernelEx(&cfg, level_fwd_kernel<true>, tmW, a);
+  else cudaLaunchKernelEx(&cfg, level_fwd_kernel<false>, tmW, a);
   CL_CHECK_LAUNCH("level_fwd_kernel");
+  return CLIORA_OK;
+}
+
+inline size_t level_bwd_smem(int n_umma) { return (size_t)ring_bytes(n_umma) + kBwdExtraBytes; }
+
+inline int launch_level_bwd(cudaStream_t st, const LevelBwdArgs& g, const float* W2Tpair, const char* tag) {
+  const LevelFwdArgs& a = g.geo;
+  CUtensorMap tmW;
+  CL_TRY(tc::make_pair_map(&tmW, W2Tpair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
+                           a.mode == 1 ? 1 : 2));
+  const size_t smem = level_bwd_smem(a.n_umma);
+  const void* kern = reinterpret_cast<const void*>(level_bwd_kernel<0>);
+  CL_CUDA(func_attr_at_least(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (g_carveout >= 0) apply_carveout(kern);
+  const int tiles = ceil_div(a.cells, a.G);
+  const double rows = (double)a.cells * a.N;
+  ProfScope prof(st, tag, 2.0 * rows * a.D * a.D, 4.0 * rows * (9.0 * a.D + 3));
+  launch_k(level_bwd_kernel<0>, dim3(a.nc, tiles, 1), dim3(kThreads, 1, 1), smem, st, tmW, g);
+  CL_CHECK_LAUNCH("level_bwd_kernel");
   return CLIORA_OK;
 }
 

@@ -130,6 +130,12 @@ typedef struct cliora_layout {
   /* forward workspace: ReLU bitmasks of the hidden activations, 16 x uint32 per split row (D <= 512), else -1 */
   int64_t Mbin, Mbout;
   int64_t CSin, CSout;        /* bws: per-cell sums over splits of the compose-output gradients [B,C,D] (-> db2) */
+  /* backward scratch of the fused level kernels: split pairs of the compose-output gradients (the A operand of the
+   * weight-gradient GEMM), per-cell gradients wrt the pre-normalisation sums, per-cell softmax constants, and the
+   * bias-gradient accumulators of both passes */
+  int64_t GYp_in, GYp_out;    /* [2, rows_in, D], [2, rows_out, D] */
+  int64_t GA, CM;             /* [B,C,D], [B,C] */
+  int64_t db2acc;             /* [2, D]: inside, outside */
 } cliora_layout;
 
 int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);
