@@ -436,6 +436,12 @@ static int launch_cell_bwd(const Ctx& c, const CellBwdArgs& g, float* cellsum) {
   return CLIORA_OK;
 }
 
+// Concurrent sentence chains the caller runs (bits 8-11 of cliora_dims.flags; 0 = 1): a hint for tile sizing only
+static int chain_count(const Ctx& c) {
+  const int k = (c.d.flags >> 8) & 15;
+  return k < 1 ? 1 : k;
+}
+
 // One launch for a whole forward level (gather + compose GEMM + softmax-weighted sums + cell finalize): lvl::level_fwd_kernel.
 // Returns false when the shape is outside what the fused kernel covers (the unfused chain then runs).
 static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g) {
@@ -461,8 +467,10 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   a.R = outside ? 0 : c.d.R;
   a.cells = B * a.L;
   a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
+  // sentence chains run their level kernels side by side: each aims at its share of the co-resident clusters
   a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, a.R, geom,
-                                  lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)), a.max_sent);
+                                  lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) / chain_count(c),
+                                  a.max_sent);
   if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
   a.mode = c.tc_mode == 1 ? 1 : 2;
   a.outside = outside ? 1 : 0;
@@ -513,11 +521,12 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   // GE is level-local here: point the kernel at a level block starting at GE[0]
   // (cell_bwd indexes GE with the same row ids as E, relative to the level block).
   const bool fused = g.c.E != nullptr && fused_bwd_ok(c);
+  const bool cells_inline = fused && !VL && g_debug[14] == 0;   // text cells: the fused kernel's prologue does the cell part
   if (fused) {
     g.ga_out = bws + c.L.GA;
     g.cm_out = bws + c.L.CM;
   }
-  CL_TRY(launch_cell_bwd<VL>(c, g, fused ? nullptr : bws + (OUTSIDE ? c.L.CSout : c.L.CSin)));
+  if (!cells_inline) CL_TRY(launch_cell_bwd<VL>(c, g, fused ? nullptr : bws + (OUTSIDE ? c.L.CSout : c.L.CSin)));
   if (g.c.E == nullptr) return CLIORA_OK;  // leaf level: no splits
   if (fused) {
     lvl::LevelGeom geom;
@@ -529,7 +538,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     a.cells = B * a.L;
     a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
     int max_sent = 0;
-    a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, 148 / geom.nc, max_sent);
+    a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, (148 / geom.nc) / chain_count(c), max_sent);
     a.mode = c.tc_mode == 1 ? 1 : 2;
     a.outside = OUTSIDE ? 1 : 0;
     a.C = c.C;
@@ -550,6 +559,10 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     b.GYp = bws + (OUTSIDE ? c.L.GYp_out : c.L.GYp_in) + r0 * D;
     b.gy_lo_off = (OUTSIDE ? c.L.rows_out : c.L.rows_in) * D;
     b.db2 = bws + c.L.db2acc + (OUTSIDE ? D : 0);
+    b.GAw = bws + c.L.GA; b.CMw = bws + c.L.CM;
+    if (cells_inline) {
+      b.cellGh = g.Gh; b.cellH = chart_h; b.cellNrm = g.c.nrm; b.cellS = chart_s;
+    }
     const float* W2T = ws + (OUTSIDE ? c.L.oW2Tp : c.L.W2Tp);
     return lvl::launch_level_bwd(c.st, b, W2T, OUTSIDE ? "level_bwd_outside" : "level_bwd_inside");
   }
@@ -684,7 +697,9 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
   const float* oWb = c.d.share ? w->Wb : w->oWb;
   float* Wcat_in = ws + c.L.Wcat_in;
 
-  CL_CUDA(cudaMemsetAsync(ws + c.L.Pin, 0, (size_t)B * c.C * PI * D * sizeof(float), c.st));
+  // Pin rows start as [0 | b1 | 0 (| 0)]: the bias of the compose MLP's first layer rides on the Ar projection
+  launch_k(init_proj_kernel, 296, 256, 0, c.st, ws + c.L.Pin, (int64_t)B * c.C, PI * D, D, D, w->b1);
+  CL_CHECK_LAUNCH("init_proj_kernel");
   launch_k(pack_weights_kernel, 296, 256, 0, c.st, D, PI, w->W1, w->Wb, oW1, oWb, Wcat_in, ws + c.L.Wcat_out);
   CL_CHECK_LAUNCH("pack_weights_kernel");
   if (c.use_tc) {
@@ -733,7 +748,8 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
   const float* ob2 = c.d.share ? w->b2 : w->ob2;
   float* Wcat_out = ws + c.L.Wcat_out;
 
-  CL_CUDA(cudaMemsetAsync(ws + c.L.Pout, 0, (size_t)B * c.C * 2 * D * sizeof(float), c.st));
+  launch_k(init_proj_kernel, 296, 256, 0, c.st, ws + c.L.Pout, (int64_t)B * c.C, 2 * D, 0, D, ob1);
+  CL_CHECK_LAUNCH("init_proj_kernel");
   launch_k(outside_root_kernel, B, 128, 0, c.st, B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out);
   CL_CHECK_LAUNCH("outside_root_kernel");
   if (n > 1) CL_TRY(project_level(c, n - 1, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
@@ -1145,9 +1161,16 @@ int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float*
   if (B < 1 || n < 1 || n > 512) return CLIORA_ERR_BAD_SHAPE;
   if (n > 1 && !split_scores) return CLIORA_ERR_NULL_POINTER;
   const size_t smem = (size_t)num_cells(n) * sizeof(float);
-  if (smem > 48 * 1024)
-    CL_CUDA(cudaFuncSetAttribute(cky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  launch_k(cky_kernel, B, 64, smem, (cudaStream_t)stream, B, n, split_scores, backptr, best);
+  if (smem <= 200 * 1024) {
+    if (smem > 48 * 1024)
+      CL_CUDA(func_attr_at_least(reinterpret_cast<const void*>(cky_kernel<false>),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_k(cky_kernel<false>, B, kCkyThreads, smem, (cudaStream_t)stream, B, n, split_scores, backptr, best);
+  } else {
+    // sentences whose Viterbi chart does not fit shared memory (n > 319): the chart lives in the caller's `best` rows
+    if (!best) return CLIORA_ERR_UNSUPPORTED;
+    launch_k(cky_kernel<true>, B, kCkyThreads, 0, (cudaStream_t)stream, B, n, split_scores, backptr, best);
+  }
   CL_CHECK_LAUNCH("cky_kernel");
   return CLIORA_OK;
 }

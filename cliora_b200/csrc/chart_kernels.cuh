@@ -31,8 +31,24 @@ __global__ void pack_weights_kernel(int D, int PI, const float* __restrict__ W1,
   }
 }
 
+// Projection buffers start from their bias row instead of zero: P[row, :] = 0 except P[row, boff : boff + D] = bias.
+// Folding b1 into the second operand's projection (Ar = h W1r^T + b1) makes the hidden activation of a split
+// z = relu(Al[first] + Ar[second]) -- one add less per element in the split kernels, and rows that are zero-filled
+// (tile padding) come out as exact zeros without a select.
+__global__ void init_proj_kernel(float* __restrict__ P, int64_t rows, int ld, int boff, int D,
+                                 const float* __restrict__ bias) {
+  pdl_prologue();
+  const int64_t n4 = rows * (ld / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % (ld / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= boff && j < boff + D) v = ld4(bias + (j - boff));
+    st4(P + i * 4, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
-// split_build: per split row, z = relu(Al[first] + Ar[second] + b1), e = h[first].V[second] + s[first] + s[second]
+// split_build: per split row, z = relu(Al[first] + Ar[second]) (b1 is folded into Ar, see init_proj_kernel), e = h[first].V[second] + s[first] + s[second]
 // inside : first = left child (inside chart), second = right child (inside chart)
 // outside: first = sibling (inside chart),    second = parent (outside chart)
 // One warp per row; rows ordered (b,p,k) inside, (b,k,p) outside (the reference's order).
@@ -92,7 +108,7 @@ __global__ __launch_bounds__(256) void split_build_kernel(const SplitArgs a) {
     for (int u = 0; u < 4; ++u) {
       const int j = lane * 4 + (t0 + u) * 128;
       if (j < a.D) {
-        x[u] = ld4(Al + j); y[u] = ld4(Ar + j); bb[u] = ld4(a.b1 + j);
+        x[u] = ld4(Al + j); y[u] = ld4(Ar + j); bb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         hv[u] = ld4(h1 + j); vv[u] = ld4(V + j);
       }
     }

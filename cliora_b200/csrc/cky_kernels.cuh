@@ -7,43 +7,61 @@
 namespace cliora {
 
 // E: raw inside split scores, level blocks [B, L, N] at row offset B * inside_rows_before(n, level).
-// best[l,p] = max_k best[k,p] + best[l-1-k,p+k+1] + (e_k - max_k e_k); leaves = 1; first max wins.
-// Dynamic smem: cells floats.
-__global__ __launch_bounds__(64) void cky_kernel(int B, int n, const float* __restrict__ E,
-                                                 int32_t* __restrict__ backptr, float* __restrict__ best_out) {
+// best[l,p] = max_k best[k,p] + best[l-1-k,p+k+1] + (e_k - max_k e_k); leaves = 1; first max wins (torch.argmax,
+// cky.py:86).  Warp-parallel: one block per sentence, one warp per cell of the current level, lanes over the cell's
+// splits; the per-cell maximum and the first-max argmax are warp-shuffle reductions on (value, split) pairs.  Every
+// candidate is computed with the oracle's own operation order, so scores and backpointers are bit-exact.
+// The Viterbi chart lives in shared memory (GLOBAL_CHART = false: cells floats of dynamic smem) or, for sentences
+// too long for that, in the caller's best_out rows (GLOBAL_CHART = true).
+constexpr int kCkyThreads = 256;
+
+template <bool GLOBAL_CHART>
+__global__ __launch_bounds__(kCkyThreads) void cky_kernel(int B, int n, const float* __restrict__ E,
+                                                          int32_t* __restrict__ backptr, float* __restrict__ best_out) {
   pdl_prologue();
-  extern __shared__ float s_best[];
+  extern __shared__ float s_chart[];
   const int b = blockIdx.x;
   const int C = (int)num_cells(n);
+  float* chart = GLOBAL_CHART ? best_out + (int64_t)b * C : s_chart;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_best[i] = 1.f;
+    chart[i] = 1.f;
     backptr[(int64_t)b * C + i] = -1;
   }
   __syncthreads();
   for (int level = 1; level < n; ++level) {
     const int L = n - level, N = level;
     const int64_t lvl_rows = (int64_t)B * inside_rows_before(n, level);
-    for (int p = threadIdx.x; p < L; p += blockDim.x) {
+    for (int p = warp; p < L; p += nwarps) {
       const float* e = E + lvl_rows + ((int64_t)b * L + p) * N;
-      float mx = e[0];
-      for (int k = 1; k < N; ++k) mx = fmaxf(mx, e[k]);
+      float mx = -INFINITY;
+      for (int k = lane; k < N; k += 32) mx = fmaxf(mx, e[k]);
+      mx = warp_max(mx);
       float bv = -INFINITY;
-      int bk = 0;
-      for (int k = 0; k < N; ++k) {
+      int bk = 0x7fffffff;
+      for (int k = lane; k < N; k += 32) {          // ascending k per lane: a strict > keeps the lane's first maximum
         int l, r;
         inside_children(n, level, p, k, l, r);
-        const float lr = __fadd_rn(s_best[l], s_best[r]);
+        const float lr = __fadd_rn(chart[l], chart[r]);
         const float cand = __fadd_rn(lr, __fsub_rn(e[k], mx));
         if (cand > bv) { bv = cand; bk = k; }
       }
-      const int cell = lvl_off(n, level) + p;
-      s_best[cell] = bv;
-      backptr[(int64_t)b * C + cell] = bk;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {             // first maximum over the warp: larger value, then smaller split
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+      }
+      if (lane == 0) {
+        const int cell = lvl_off(n, level) + p;
+        chart[cell] = bv;
+        backptr[(int64_t)b * C + cell] = bk;
+      }
     }
     __syncthreads();
   }
-  if (best_out != nullptr)
-    for (int i = threadIdx.x; i < C; i += blockDim.x) best_out[(int64_t)b * C + i] = s_best[i];
+  if (!GLOBAL_CHART && best_out != nullptr)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) best_out[(int64_t)b * C + i] = s_chart[i];
 }
 
 // Spans of the CKY tree straight from the backpointer table (replaces the host round trip

@@ -44,7 +44,9 @@ constexpr int kRows = 128;            // split rows per tile = UMMA M
 constexpr int kAStages = 4;           // A-operand ring (gathered + transformed by the producer warps), 32 KB per stage
 constexpr int kProdWarps = 8;
 constexpr int kProdWarp0 = 6;
-constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // 448
+constexpr int kCopyWarp0 = kProdWarp0 + kProdWarps;      // warps 14-17: cp.async gathers of the raw operand rows
+constexpr int kCopyWarps = 4;
+constexpr int kThreads = (kCopyWarp0 + kCopyWarps) * 32;   // 576
 constexpr int kMaxCluster = 8;
 constexpr int kMaxUmmaN = 112;
 constexpr int kABytes = kRows * 128;  // one 128 x 32 fp32 operand tile
@@ -227,6 +229,130 @@ CL_D void cp_async16_zfill(uint32_t dst_saddr, const void* src, uint32_t src_byt
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(src_bytes) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// A-operand pipeline shared by the forward and backward level kernels.
+//   copy warps (kCopyWarp0 .. +4)   thread owns chunk c of rows rbase + 16 i (i < 8): cp.async lands the two raw
+//       128-byte row slices of every tile row in the raw stage (first 16 KB: operand a, second 16 KB: operand b,
+//       128-byte swizzled) and makes the stage's raw_full barrier track their completion.  They run ahead of the
+//       transform by up to kAStages k-blocks and do nothing else, so gather latency never sits in the transform chain.
+//   transform warps (kProdWarp0 .. +8)  thread = tile row (TMEM lane) x 16-column half of the k-block: reads its 16
+//       floats of each raw row, applies xform four elements at a time, splits into tf32 (hi, lo) and writes both into
+//       the tensor-memory stage (tcgen05.st); the raw stage goes back to the copy warps, the TMEM stage to the MMA.
+// offs(r, oa, ob, ok): element offsets of row r's two raw rows relative to base_a / base_b;  xform(xa, xb, kc) -> float4;
+// stream(kb, k0, hi, lo): optional streaming of the 16-float pair to global memory.
+// Barriers: raw_full[s] (count 128 copy threads, cp.async completion), raw_empty[s] (8 transform warps),
+//           fullA[s] (8 transform warps, TMEM stage written), emptyA[s] (tcgen05.commit: TMEM stage consumed).
+// ------------------------------------------------------------------------------------------
+CL_D void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class OffFn, class StoreFn>
+CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int num_kb, int D, const float* base_a,
+                     const float* base_b, OffFn offs, int store_turn0, int store_every, StoreFn store,
+                     long long* dbg = nullptr) {
+  const int gt = threadIdx.x - kCopyWarp0 * 32;          // 0..127
+  const int c = gt & 7, rbase = gt >> 3;
+  uint32_t oa[8], ob[8];
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bool ok;
+    offs(rbase + 16 * i, oa[i], ob[i], ok);
+    oa[i] += c * 4;
+    ob[i] += c * 4;
+    okmask |= ok ? (1u << i) : 0u;
+  }
+  const uint32_t soff0 = (uint32_t)(rbase * 128 + ((c ^ (rbase & 7)) << 4));     // + 2048 i   (16 rows further)
+  const uint32_t smem_base = smem_u32(smem);
+  // The pair of k-block kp (every store_every-th one is this CTA's to stream out) is written from the raw stage by
+  // the thread that copied it, right before the stage is refilled -- coalesced (eight lanes per 128-byte row slice).
+  auto flush = [&](int kp) {
+    if (store_every <= 0 || (kp % store_every) != store_turn0) return;
+    const uint8_t* sA = smem + (kp % kAStages) * 2 * kABytes + soff0;
+    const int kc = kp * 32 + c * 4;
+    if (kc >= D) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if ((okmask >> i) & 1u) {
+        const float4 xa = *reinterpret_cast<const float4*>(sA + i * 2048);
+        const float4 xb = *reinterpret_cast<const float4*>(sA + kABytes + i * 2048);
+        store(rbase + 16 * i, kc, xa, xb);
+      }
+    }
+  };
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const int stage = kb % kAStages;
+    mbar_wait(&raw_empty[stage], ((kb / kAStages) & 1) ^ 1);
+    if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[56 + (kb - 4) * 2] = clock_now();
+    if (kb >= kAStages) {
+      cp_async_wait<kAStages - 1>();                      // this thread's copies of k-block kb - 4 landed long ago
+      flush(kb - kAStages);
+    }
+    const int kcol = kb * 32 + c * 4;
+    const uint32_t sA = smem_base + (uint32_t)(stage * 2 * kABytes) + soff0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t nbytes = (((okmask >> i) & 1u) && kcol < D) ? 16u : 0u;
+      cp_async16_zfill(sA + i * 2048, base_a + oa[i] + kb * 32, nbytes);
+      cp_async16_zfill(sA + kABytes + i * 2048, base_b + ob[i] + kb * 32, nbytes);
+    }
+    cp_async_arrive_noinc(&raw_full[stage]);              // arrives once this thread's copies above have landed
+    cp_async_commit();
+    if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[57 + (kb - 4) * 2] = clock_now();
+  }
+  cp_async_wait_all();
+  for (int kp = (num_kb > kAStages ? num_kb - kAStages : 0); kp < num_kb; ++kp) flush(kp);
+}
+
+template <class XformFn>
+CL_D void transform_a_tmem(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, uint64_t* fullA, uint64_t* emptyA,
+                           uint32_t tmem_base, int num_kb, int mode, XformFn xform, long long* dbg = nullptr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;
+  const int row = qd * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const int stage = kb % kAStages;
+    const uint32_t phase = (kb / kAStages) & 1;
+    const bool st_ = dbg != nullptr && threadIdx.x == kProdWarp0 * 32 && kb >= 4 && kb < 8;
+    if (st_) dbg[32 + (kb - 4) * 6] = clock_now();
+    mbar_wait(&raw_full[stage], phase);                     // the raw rows of k-block kb have landed
+    if (st_) dbg[33 + (kb - 4) * 6] = clock_now();
+    const uint8_t* sA = smem + stage * 2 * kABytes + row * 128;
+    const int k0 = kb * 32 + half * 16;
+    float4 xa[4], xb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ch = ((half * 4 + t) ^ (row & 7)) << 4;
+      xa[t] = *reinterpret_cast<const float4*>(sA + ch);
+      xb[t] = *reinterpret_cast<const float4*>(sA + kABytes + ch);
+    }
+    float hi[16], lo[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float4 o = xform(xa[t], xb[t], k0 + t * 4);
+      split_trunc(o.x, hi[4 * t], lo[4 * t]); split_trunc(o.y, hi[4 * t + 1], lo[4 * t + 1]);
+      split_trunc(o.z, hi[4 * t + 2], lo[4 * t + 2]); split_trunc(o.w, hi[4 * t + 3], lo[4 * t + 3]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(&raw_empty[stage]);   // raw stage read: the copy warps may refill it
+    if (st_) dbg[34 + (kb - 4) * 6] = clock_now();
+    mbar_wait(&emptyA[stage], phase ^ 1);                   // the MMAs that read this TMEM stage have retired
+    tcgen05_fence_after();
+    if (st_) dbg[35 + (kb - 4) * 6] = clock_now();
+    const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
+    tmem_st16(ta, hi);
+    if (mode != 1) tmem_st16(ta + 32, lo);
+    tmem_st_wait();
+    if (st_) dbg[36 + (kb - 4) * 6] = clock_now();
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(&fullA[stage]);
+    if (st_) dbg[37 + (kb - 4) * 6] = clock_now();
+  }
+}
+
 template <bool A_TMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) {
@@ -260,7 +386,9 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   uint64_t* emptyB = fullB + 3;
   uint64_t* tmem_full = emptyB + 3;
   uint64_t* xbar = tmem_full + 1;                 // 4 single-use cluster exchange barriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
+  uint64_t* raw_full = xbar + 4;                  // raw operand rows of a stage landed (cp.async completion)
+  uint64_t* raw_empty = raw_full + kAStages;      // raw stage read by the transform warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kAStages);
   float* s_b2 = reinterpret_cast<float*>(ex + 256);
   float* s_e = s_b2 + 128;
   float* s_p = s_e + 128;
@@ -278,8 +406,10 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < kAStages; ++i) {
-        mbar_init(&fullA[i], kProdWarps);         // one arrival per producer warp
+        mbar_init(&fullA[i], kProdWarps);         // one arrival per producer / transform warp
         mbar_init(&emptyA[i], 1);
+        mbar_init(&raw_full[i], kCopyWarps * 32); // cp.async completion of every copy thread
+        mbar_init(&raw_empty[i], kProdWarps);
       }
       for (int i = 0; i < 3; ++i) {
         mbar_init(&fullB[i], 1);                  // the TMA thread's expect_tx arrival
@@ -360,100 +490,46 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       umma_commit(tmem_full);
       if (dbg_row) dbg_row[21] = clock_now();
     }
+  } else if (warp >= kCopyWarp0) {
+    // ------------------------------------------------------------ raw operand rows: cp.async gathers (TMEM variant)
+    if (A_TMEM) {
+      uint32_t zo[8];                              // element offset of the Z row of this thread's i-th tile row
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        zo[i] = (uint32_t)(decode_row(a, tile, cells_here, ((tid - kCopyWarp0 * 32) >> 3) + 16 * i).m * D);
+      copy_a_raw(
+          smem, raw_full, raw_empty, num_kb, D, a.P1, a.P2,
+          [&](int r, uint32_t& oa, uint32_t& ob, bool& ok) {
+            const RowInfo ri = decode_row(a, tile, cells_here, r);
+            ok = ri.ok;
+            oa = (uint32_t)(ri.g1 * a.ld1 + a.off_a1);
+            ob = (uint32_t)(ri.g2 * a.ld2 + a.off_a2);
+          },
+          // the Z pair of k-block kb (for the dW2 GEMM of the backward pass) is streamed out by CTA kb % nc
+          rank, a.Z != nullptr ? nc : 0,
+          [&](int r, int kc, const float4& xa, const float4& xb) {
+            float4 hi, lo;
+            split_trunc(fmaxf(xa.x + xb.x, 0.f), hi.x, lo.x); split_trunc(fmaxf(xa.y + xb.y, 0.f), hi.y, lo.y);
+            split_trunc(fmaxf(xa.z + xb.z, 0.f), hi.z, lo.z); split_trunc(fmaxf(xa.w + xb.w, 0.f), hi.w, lo.w);
+            float* dst = a.Z + zo[r >> 4] + kc;
+            st4(dst, hi);
+            st4(dst + a.z_lo_off, lo);
+          },
+          dbg_row);
+    }
   } else if (warp >= kProdWarp0 && A_TMEM) {
-    // ------------------------------------------------------------ A operand -> tensor memory
-    // Copy side (as below): thread owns chunk c of rows rbase + 32 i; cp.async lands the two projection rows of every
-    // split in the raw stage (first 16 KB: first operand, second 16 KB: second operand), 128-byte swizzled.
-    // Transform side: thread = split row r (TMEM lane), the warp's column half h; it reads 16 floats of each raw row,
-    // z = relu(al + ar + b1) -> (hi, lo), and writes them into the TMEM stage with tcgen05.st.  The MMAs then take A
-    // from tensor memory: no shared-memory writes for the pair, no shared-memory reads by the tensor core for A.
-    constexpr int kLookahead = 2;
-    const int pt = tid - kProdWarp0 * 32;      // 0..255
-    const int c = pt & 7;
-    const int rbase = (pt >> 3);
-    const float* pa[4];
-    const float* pb[4];
-    bool ok[4];
-    uint32_t soff[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rbase + 32 * i;
-      const RowInfo ri = decode_row(a, tile, cells_here, r);
-      ok[i] = ri.ok;
-      pa[i] = a.P1 + ri.g1 * a.ld1 + a.off_a1 + c * 4;
-      pb[i] = a.P2 + ri.g2 * a.ld2 + a.off_a2 + c * 4;
-      soff[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-    }
-    const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;     // TMEM lane quarter, 16-column half of the k-block
-    const int row = qd * 32 + lane;
-    const RowInfo rme = decode_row(a, tile, cells_here, row);
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    if (dbg_row && pt == 0) dbg_row[22] = clock_now();
-    const uint32_t smem_base = smem_u32(smem);
-    int zturn = 0;
-    for (int it = 0; it < num_kb + kLookahead; ++it) {
-      if (it < num_kb) {
-        const int stage = it % kAStages;
-        const int kcol = it * 32 + c * 4;
-        const uint32_t sA = smem_base + (uint32_t)(stage * a_stage_bytes);
-        if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[32 + (it - 4) * 4] = clock_now();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t nbytes = (ok[i] && kcol < D) ? 16u : 0u;
-          cp_async16_zfill(sA + soff[i], pa[i] + it * 32, nbytes);
-          cp_async16_zfill(sA + kABytes + soff[i], pb[i] + it * 32, nbytes);
-        }
-      }
-      cp_async_commit();
-      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[33 + (it - 4) * 4] = clock_now();
-      const int kb = it - kLookahead;
-      if (kb < 0) continue;
-      const int stage = kb % kAStages;
-      mbar_wait(&emptyA[stage], ((kb / kAStages) & 1) ^ 1);      // the MMAs that read this TMEM stage have retired
-      tcgen05_fence_after();
-      cp_async_wait<kLookahead>();
-      asm volatile("bar.sync 3, %0;" ::"r"(kProdWarps * 32) : "memory");   // everybody's copies of k-block kb landed
-      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[34 + (it - 4) * 4] = clock_now();
-      const uint8_t* sA = smem + stage * a_stage_bytes + row * 128;
-      const int k0 = kb * 32 + half * 16;
-      float hi[16], lo[16];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int ch = ((half * 4 + t) ^ (row & 7)) << 4;
-        const float4 xa = *reinterpret_cast<const float4*>(sA + ch);
-        const float4 xb = *reinterpret_cast<const float4*>(sA + kABytes + ch);
-        const int kc = k0 + t * 4;
-        const float4 bv = kc < D ? __ldg(reinterpret_cast<const float4*>(a.b1 + kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 o;
-        o.x = fmaxf(xa.x + xb.x + bv.x, 0.f);
-        o.y = fmaxf(xa.y + xb.y + bv.y, 0.f);
-        o.z = fmaxf(xa.z + xb.z + bv.z, 0.f);
-        o.w = fmaxf(xa.w + xb.w + bv.w, 0.f);
-        if (!rme.ok || kc >= D) o = make_float4(0.f, 0.f, 0.f, 0.f);
-        split_trunc(o.x, hi[4 * t], lo[4 * t]); split_trunc(o.y, hi[4 * t + 1], lo[4 * t + 1]);
-        split_trunc(o.z, hi[4 * t + 2], lo[4 * t + 2]); split_trunc(o.w, hi[4 * t + 3], lo[4 * t + 3]);
-      }
-      const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
-      tmem_st16(ta, hi);
-      if (a.mode != 1) tmem_st16(ta + 32, lo);
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(&fullA[stage]);
-      if (dbg_row && pt == 0 && it >= 4 && it < 8) dbg_row[35 + (it - 4) * 4] = clock_now();
-      if (a.Z != nullptr && zturn == rank && rme.ok) {            // this CTA's turn to stream the Z pair out
-        float* zp = a.Z + rme.m * D + k0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (k0 + 4 * t < D) {
-            st4(zp + 4 * t, make_float4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]));
-            st4(zp + a.z_lo_off + 4 * t, make_float4(lo[4 * t], lo[4 * t + 1], lo[4 * t + 2], lo[4 * t + 3]));
-          }
-        }
-      }
-      zturn = (zturn + 1 == nc) ? 0 : zturn + 1;
-    }
-    if (dbg_row && pt == 0) dbg_row[23] = clock_now();
+    // ------------------------------------------------------------ A operand -> tensor memory (see transform_a_tmem)
+    // z = relu(Al[first] + Ar[second]); b1 rides on the second operand's projection, padding was zero-filled
+    if (dbg_row && tid == kProdWarp0 * 32) dbg_row[22] = clock_now();
+    transform_a_tmem(
+        smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode,
+        [&](const float4& xa, const float4& xb, int kc) {
+          (void)kc;
+          return make_float4(fmaxf(xa.x + xb.x, 0.f), fmaxf(xa.y + xb.y, 0.f), fmaxf(xa.z + xb.z, 0.f),
+                             fmaxf(xa.w + xb.w, 0.f));
+        },
+        dbg_row);
+    if (dbg_row && tid == kProdWarp0 * 32) dbg_row[23] = clock_now();
   } else if (warp >= kProdWarp0) {
     // ------------------------------------------------------------ A operand: gather + ReLU + tf32 split
     // Each thread owns chunk c of rows rbase + 32 i.  The two projection rows of a split are copied asynchronously
@@ -517,7 +593,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       const int stage = kb % kAStages;
       const int kcol = kb * 32 + c * 4;
       uint8_t* sA = smem + stage * a_stage_bytes;
-      const float4 bv = kcol < D ? __ldg(reinterpret_cast<const float4*>(a.b1 + kcol)) : zero4;
+      const float4 bv = zero4;      // b1 is folded into the second operand's projection (init_proj_kernel)
       const bool store_z = a.Z != nullptr && zturn == rank && kcol < D && !(a.exp_flags & 2);
       zturn = (zturn + 1 == nc) ? 0 : zturn + 1;
       if (!(a.exp_flags & 4))
@@ -658,12 +734,13 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   if (warp >= 2) {
     // y = relu(acc + b2) -> Y row (saved for backward); p * y staged.  Twelve warps: TMEM lane quarter = warp % 4,
     // the 16-column chunks of a quarter are dealt to its three warps.
+    constexpr int kSub = (kThreads / 32 - 2) / 4;          // warps per TMEM lane quarter
     const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
     const long long m = s_m[r];
     const float p = s_p[r];
     float* yrow = m >= 0 ? a.Y + m * D + n0 : nullptr;
 #pragma unroll 1
-    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 48) {
+    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);    // warp-collective: no early exit
       if (a.mode != 1) {
@@ -896,6 +973,10 @@ struct LevelBwdArgs {
   float* Gh1; float* Gs1; float* Gs2;    // vector / score gradient accumulators of first, score of second
   float* GYp; int64_t gy_lo_off;         // level block pair out [2][rows, D]
   float* db2;                            // [D] accumulator
+  // text cells (no region attention): the per-cell normalise backward runs in this kernel's prologue instead of a
+  // separate cells-only launch; null cellGh = GA / CM were prepared by the cell kernel
+  const float* cellGh; const float* cellH; const float* cellNrm; const float* cellS;   // [B,C,D], [B,C,D], [B,C], [B,C]
+  float* GAw; float* CMw;                // writable aliases of GA / CM
 };
 
 constexpr int kBwdExtraBytes = 256 + 128 * 8 + 4 * (128 * 5 + 128);   // barriers, row ids, p/cell/d0/d1/ge, b-unused
@@ -927,7 +1008,9 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   uint64_t* fullB = emptyA + kAStages;
   uint64_t* emptyB = fullB + 3;
   uint64_t* tmem_full = emptyB + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* raw_full = tmem_full + 1;
+  uint64_t* raw_empty = raw_full + kAStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kAStages);
   long long* s_m = reinterpret_cast<long long*>(ex + 256);          // [128] global row, -1 = none
   float* s_p = reinterpret_cast<float*>(s_m + 128);                  // [128] softmax probability of the row
   int* s_cell = reinterpret_cast<int*>(s_p + 128);                   // [128] chart cell (b*C + c) of the row
@@ -940,6 +1023,8 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
       for (int i = 0; i < kAStages; ++i) {
         mbar_init(&fullA[i], kProdWarps);
         mbar_init(&emptyA[i], 1);
+        mbar_init(&raw_full[i], kCopyWarps * 32);
+        mbar_init(&raw_empty[i], kProdWarps);
       }
       for (int i = 0; i < 3; ++i) {
         mbar_init(&fullB[i], 1);
@@ -959,6 +1044,36 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     s_m[tid] = ri.ok ? (long long)ri.m : -1ll;
     s_p[tid] = ri.ok ? g.Pr[ri.m] : 0.f;
     s_cell[tid] = (int)ri.cell;
+  }
+  if (g.cellGh != nullptr) {
+    // per-cell normalise backward (text cells): ga = (g - h (h.g)) / nrm on the live branch, g / eps on the clamped one;
+    // cm = sum_m p_m gp_m = nrm (h . ga) + s gs.  Warp per cell; every column-slice CTA computes the same values.
+    for (int gi = warp; gi < cells_here; gi += kThreads / 32) {
+      int cb, cp;
+      int64_t cell;
+      cell_of(a, tile * a.G + gi, cb, cp, cell);
+      const float* gh = g.cellGh + cell * D;
+      const float* hv = g.cellH + cell * D;
+      const float nrm = g.cellNrm[cell];
+      float hd = 0.f;
+      for (int j = lane * 4; j < D; j += 128) {
+        const float4 x = ldcg4(gh + j), h4 = ldcg4(hv + j);
+        hd = fmaf(h4.x, x.x, hd); hd = fmaf(h4.y, x.y, hd); hd = fmaf(h4.z, x.z, hd); hd = fmaf(h4.w, x.w, hd);
+      }
+      hd = warp_sum(hd);
+      const float coef = unit_bwd_coef(nrm, hd), inv = 1.f / nrm;
+      float ad = 0.f;
+      for (int j = lane * 4; j < D; j += 128) {
+        const float4 x = ldcg4(gh + j), h4 = ldcg4(hv + j);
+        const float4 v = make_float4((x.x - h4.x * coef) * inv, (x.y - h4.y * coef) * inv, (x.z - h4.z * coef) * inv,
+                                     (x.w - h4.w * coef) * inv);
+        ad = fmaf(h4.x, v.x, ad); ad = fmaf(h4.y, v.y, ad); ad = fmaf(h4.z, v.z, ad); ad = fmaf(h4.w, v.w, ad);
+        st4(g.GAw + cell * D + j, v);
+      }
+      ad = warp_sum(ad);
+      if (lane == 0) g.CMw[cell] = nrm * ad + g.cellS[cell] * g.Gs[cell];
+    }
+    __threadfence_block();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1003,90 +1118,40 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
       }
       umma_commit(tmem_full);
     }
+  } else if (warp >= kCopyWarp0) {
+    copy_a_raw(
+        smem, raw_full, raw_empty, num_kb, D, g.Y, g.GA,
+        [&](int r, uint32_t& oa, uint32_t& ob, bool& ok) {
+          const long long m = s_m[r];
+          ok = m >= 0;
+          oa = (uint32_t)((ok ? m : 0) * D);
+          ob = (uint32_t)((int64_t)s_cell[r] * D);
+        },
+        // the GY pair of k-block kb (the A operand of the dW2 GEMM) is streamed out by CTA kb % nc
+        rank, g.GYp != nullptr ? nc : 0,
+        [&](int r, int kc, const float4& y, const float4& ga) {
+          const float pr = s_p[r];
+          float4 hi, lo;
+          split_trunc(y.x > 0.f ? pr * ga.x : 0.f, hi.x, lo.x); split_trunc(y.y > 0.f ? pr * ga.y : 0.f, hi.y, lo.y);
+          split_trunc(y.z > 0.f ? pr * ga.z : 0.f, hi.z, lo.z); split_trunc(y.w > 0.f ? pr * ga.w : 0.f, hi.w, lo.w);
+          float* dst = g.GYp + s_m[r] * D + kc;
+          st4(dst, hi);
+          st4(dst + g.gy_lo_off, lo);
+        });
   } else if (warp >= kProdWarp0) {
-    // ---- A operand: gy = p * ga * [y > 0] -> tensor memory; d = y . ga on the side
-    constexpr int kLookahead = 2;
-    const int pt = tid - kProdWarp0 * 32;
-    const int c = pt & 7;
-    const int rbase = (pt >> 3);
-    const float* pa[4];
-    const float* pb[4];
-    bool ok[4];
-    uint32_t soff[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rbase + 32 * i;
-      const long long m = s_m[r];
-      ok[i] = m >= 0;
-      pa[i] = g.Y + (ok[i] ? m : 0) * D + c * 4;
-      pb[i] = g.GA + (int64_t)s_cell[r] * D + c * 4;
-      soff[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-    }
-    const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;
-    const int row = qd * 32 + lane;
-    const long long mrow = s_m[row];
+    // ---- A operand: gy = p * ga * [y > 0] -> tensor memory (see transform_a_tmem); d = y . ga on the side
+    const int row = (warp & 3) * 32 + lane, half = (warp - kProdWarp0) >> 2;
     const float prow = s_p[row];
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const uint32_t smem_base = smem_u32(smem);
     float dpart = 0.f;
-    int zturn = 0;
-    for (int it = 0; it < num_kb + kLookahead; ++it) {
-      if (it < num_kb) {
-        const int stage = it % kAStages;
-        const int kcol = it * 32 + c * 4;
-        const uint32_t sA = smem_base + (uint32_t)(stage * a_stage_bytes);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t nbytes = (ok[i] && kcol < D) ? 16u : 0u;
-          cp_async16_zfill(sA + soff[i], pa[i] + it * 32, nbytes);
-          cp_async16_zfill(sA + kABytes + soff[i], pb[i] + it * 32, nbytes);
-        }
-      }
-      cp_async_commit();
-      const int kb = it - kLookahead;
-      if (kb < 0) continue;
-      const int stage = kb % kAStages;
-      mbar_wait(&emptyA[stage], ((kb / kAStages) & 1) ^ 1);
-      tcgen05_fence_after();
-      cp_async_wait<kLookahead>();
-      asm volatile("bar.sync 3, %0;" ::"r"(kProdWarps * 32) : "memory");
-      const uint8_t* sA = smem + stage * a_stage_bytes + row * 128;
-      const int k0 = kb * 32 + half * 16;
-      float hi[16], lo[16];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int ch = ((half * 4 + t) ^ (row & 7)) << 4;
-        const float4 y = *reinterpret_cast<const float4*>(sA + ch);
-        const float4 ga = *reinterpret_cast<const float4*>(sA + kABytes + ch);
-        dpart = fmaf(y.x, ga.x, dpart); dpart = fmaf(y.y, ga.y, dpart);
-        dpart = fmaf(y.z, ga.z, dpart); dpart = fmaf(y.w, ga.w, dpart);
-        float4 o;
-        o.x = y.x > 0.f ? prow * ga.x : 0.f;
-        o.y = y.y > 0.f ? prow * ga.y : 0.f;
-        o.z = y.z > 0.f ? prow * ga.z : 0.f;
-        o.w = y.w > 0.f ? prow * ga.w : 0.f;
-        split_trunc(o.x, hi[4 * t], lo[4 * t]); split_trunc(o.y, hi[4 * t + 1], lo[4 * t + 1]);
-        split_trunc(o.z, hi[4 * t + 2], lo[4 * t + 2]); split_trunc(o.w, hi[4 * t + 3], lo[4 * t + 3]);
-      }
-      const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
-      tmem_st16(ta, hi);
-      if (a.mode != 1) tmem_st16(ta + 32, lo);
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(&fullA[stage]);
-      if (g.GYp != nullptr && zturn == rank && mrow >= 0) {
-        float* zp = g.GYp + mrow * D + k0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (k0 + 4 * t < D) {
-            st4(zp + 4 * t, make_float4(hi[4 * t], hi[4 * t + 1], hi[4 * t + 2], hi[4 * t + 3]));
-            st4(zp + g.gy_lo_off + 4 * t, make_float4(lo[4 * t], lo[4 * t + 1], lo[4 * t + 2], lo[4 * t + 3]));
-          }
-        }
-      }
-      zturn = (zturn + 1 == nc) ? 0 : zturn + 1;
-    }
+    transform_a_tmem(
+        smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode,
+        [&](const float4& y, const float4& ga, int kc) {
+          dpart = fmaf(y.x, ga.x, dpart); dpart = fmaf(y.y, ga.y, dpart);
+          dpart = fmaf(y.z, ga.z, dpart); dpart = fmaf(y.w, ga.w, dpart);
+          (void)kc;
+          return make_float4(y.x > 0.f ? prow * ga.x : 0.f, y.y > 0.f ? prow * ga.y : 0.f,
+                             y.z > 0.f ? prow * ga.z : 0.f, y.w > 0.f ? prow * ga.w : 0.f);
+        });
     s_d[half * 128 + row] = dpart;
   } else {
     // ---- warps 2-5 while the MMAs run: db2 += column sums of GY over this tile, for this CTA's columns
@@ -1122,13 +1187,14 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   }
   if (warp >= 2) {
     // GZ = acc * [z > 0]; scattered into the projection-gradient rows of the two cells the split read
+    constexpr int kSub = (kThreads / 32 - 2) / 4;
     const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
     const RowInfo ri = decode_row(a, tile, cells_here, r);
     const float* zrow = ri.ok ? g.Zhi + ri.m * D + n0 : nullptr;
     float* d1 = g.GP1 + ri.g1 * g.ld1 + g.off_a1 + n0;
     float* d2 = g.GP2 + ri.g2 * g.ld2 + g.off_a2 + n0;
 #pragma unroll 1
-    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 48) {
+    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
       if (a.mode != 1) {

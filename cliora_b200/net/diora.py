@@ -172,7 +172,7 @@ class DioraBase(nn.Module):
         chains = self.chains if self.chains is not None else max(1, min(2 if B < 64 else 4, B // 8))
         if self.precision not in ('fp32', 'tf32'):
             raise ValueError("precision must be 'fp32' or 'tf32'")
-        flags = 2 if self.precision == 'tf32' else 0
+        flags = (2 if self.precision == 'tf32' else 0) | ((min(chains, 15) & 15) << 8)   # CLIORA_FLAG_CHAINS
         outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, flags, x_span, obj, keep,
                                    *self._weight_list())
         self._run = run

@@ -74,7 +74,9 @@ def main():
                 print('  %-22s %8.2f us' % (NAMES[k], (row[k].item() - base) / (args.ghz * 1e3)))
         us = lambda k: (row[k].item() - base) / (args.ghz * 1e3)
         for i in range(4):
-            print('  prod it=%d: empty %.2f issued %.2f landed(prev) %.2f transformed %.2f' % (4 + i, us(32 + 4 * i), us(33 + 4 * i), us(34 + 4 * i), us(35 + 4 * i)))
+            print('  xform kb=%d: top %.2f raw_full %.2f math %.2f emptyA %.2f st_done %.2f end %.2f' % tuple([4 + i] + [us(32 + 6 * i + q) for q in range(6)]))
+        for i in range(4):
+            print('  copy kb=%d: raw_empty %.2f issued %.2f' % (4 + i, us(56 + 2 * i), us(57 + 2 * i)))
         for i in range(4):
             print('  mma kb=%d: full %.2f issued %.2f' % (3 + i, us(48 + 2 * i), us(49 + 2 * i)))
 

@@ -100,6 +100,9 @@ typedef struct cliora_dims {
 /* Reduced-precision mode: the tensor-core GEMMs issue one TF32 pass instead of the fp32-accurate three.
  * Stated tolerance 1e-2 of max on chart vectors (measured ~3e-3); CKY trees are NOT guaranteed identical. */
 #define CLIORA_FLAG_TF32_1PASS 2
+/* Bits 8-11: how many sentence chains (independent sub-batches on separate streams) the caller runs concurrently.
+ * A sizing hint only: each chain's fused level kernels then aim at 1/k of the co-resident clusters. */
+#define CLIORA_FLAG_CHAINS(k) (((k) & 15) << 8)
 
 /* Float offsets of every sub-buffer inside the single forward workspace `ws`
  * (saved for backward) and the backward scratch `bws`.  -1 = not present. */
@@ -247,7 +250,9 @@ int cliora_recon_ce_bwd(int rows, int D, int K, const float* cell, const float* 
  * fed by the hook of cliora/analysis/utils.py:78-95).
  *  split_scores = the Ein region of ws (raw inside split scores, all levels)
  *  backptr [B, cells] int32: best split k per cell (first max wins), -1 at leaves
- *  best    [B, cells] fp32 : Viterbi scores (may be NULL)
+ *  best    [B, cells] fp32 : Viterbi scores (may be NULL while the chart fits shared memory, n <= 319; longer
+ *                            sentences keep their chart in these rows: NULL then returns CLIORA_ERR_UNSUPPORTED)
+ * One block per sentence, one warp per cell, lanes over the splits (warp-shuffle max / first-max argmax).
  * ---------------------------------------------------------------------- */
 int cliora_cky(int B, int n, const float* split_scores, int32_t* backptr, float* best, cliora_stream_t stream);
 
