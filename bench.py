@@ -245,6 +245,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sub-records', action='store_true', help='skip the c1/c3/c4/c5 sub-records and gpu_baseline')
     ap.add_argument('--chains', type=int, default=None, help='concurrent sentence sub-batches (default: auto)')
+    ap.add_argument('--fused', default='auto', choices=['auto', 'on', 'off'],
+                    help='fused level kernels (auto: up to batch 32) or the unfused per-level kernel chain')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32', 'bf16'],
                     help="fp32 = fp32-accurate 3xTF32 tensor-core GEMMs (headline); tf32 / bf16 = single-pass reduced precision with their own stated tolerance")
     ap.add_argument('--pdl', type=int, default=None, help='programmatic dependent launch on (1) / off (0)')
@@ -339,6 +341,7 @@ def main():
         if args.chains is not None:
             trainer.net.diora.chains = args.chains
         trainer.net.diora.precision = args.precision
+        trainer.net.diora.fused = {'auto': 'auto', 'on': True, 'off': False}[args.fused]
         sync = None
         if world > 1:
             from cliora_b200.parallel import GradSync

@@ -445,7 +445,7 @@ static int chain_count(const Ctx& c) {
 // One launch for a whole forward level (gather + compose GEMM + softmax-weighted sums + cell finalize): lvl::level_fwd_kernel.
 // Returns false when the shape is outside what the fused kernel covers (the unfused chain then runs).
 static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g) {
-  if (!c.use_tc || g_debug[6] != 0 || N < 1 || N > lvl::kRows) return false;
+  if (!c.use_tc || g_debug[6] != 0 || (c.d.flags & CLIORA_FLAG_UNFUSED) || N < 1 || N > lvl::kRows) return false;
   if (!lvl::level_geom(c.d.D, g)) return false;
   if (c.d.D > 1024) return false;
   return true;

@@ -61,6 +61,11 @@ class DioraBase(nn.Module):
         # 'fp32': tensor-core GEMMs are fp32-accurate (3xTF32, default, <= 1e-4 vs the reference);
         # 'tf32': single TF32 pass, stated tolerance 1e-2 of max, trees not guaranteed identical
         self.precision = 'fp32'
+        # fused level kernels (one launch per level forward, two backward) or the unfused per-level chain: 'auto'
+        # fuses up to batch 32, where per-level latency decides (measured on B200, n=20: +4 % at batch 16, a tie at 32,
+        # -6 % at 48, -13 % at 128: above one wave of clusters the unfused chain's SM time per tile is lower);
+        # True / False force one path; results are the same
+        self.fused = 'auto'
         self.init_parameters()
         self.reset_parameters()
         self.reset()
@@ -172,7 +177,8 @@ class DioraBase(nn.Module):
         chains = self.chains if self.chains is not None else max(1, min(2 if B < 64 else 4, B // 8))
         if self.precision not in ('fp32', 'tf32'):
             raise ValueError("precision must be 'fp32' or 'tf32'")
-        flags = (2 if self.precision == 'tf32' else 0) | ((min(chains, 15) & 15) << 8)   # CLIORA_FLAG_CHAINS
+        fused = (B <= 32) if self.fused == 'auto' else bool(self.fused)
+        flags = (2 if self.precision == 'tf32' else 0) | (0 if fused else 4) | ((min(chains, 15) & 15) << 8)
         outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, flags, x_span, obj, keep,
                                    *self._weight_list())
         self._run = run

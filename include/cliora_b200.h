@@ -100,6 +100,10 @@ typedef struct cliora_dims {
 /* Reduced-precision mode: the tensor-core GEMMs issue one TF32 pass instead of the fp32-accurate three.
  * Stated tolerance 1e-2 of max on chart vectors (measured ~3e-3); CKY trees are NOT guaranteed identical. */
 #define CLIORA_FLAG_TF32_1PASS 2
+/* Run the unfused per-level kernel chain (split_build -> tcgen05 GEMM -> cell kernels -> scatter) instead of the fused
+ * level kernels.  Same results; it is the faster of the two once a level no longer fits one wave of clusters (batches
+ * above ~32 sentences at length 20), where per-tile SM time rather than per-level latency decides. */
+#define CLIORA_FLAG_UNFUSED 4
 /* Bits 8-11: how many sentence chains (independent sub-batches on separate streams) the caller runs concurrently.
  * A sizing hint only: each chain's fused level kernels then aim at 1/k of the co-resident clusters. */
 #define CLIORA_FLAG_CHAINS(k) (((k) & 15) << 8)

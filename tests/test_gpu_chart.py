@@ -292,3 +292,21 @@ def test_multi_chain_backward_vs_oracle(B, n, chains):
     separate streams with per-chain weight-gradient buffers: forward and every gradient against the float64
     oracle with chains > 1, at D=400, R=36 (the last case is the bench workload's chart: B=32, n=20)."""
     test_chart_vs_oracle_live(B, n, 400, 36, True, chains=chains)
+
+
+@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True),
+                                           (5, 11, 132, 7, False), (7, 13, 260, 33, True)])
+def test_unfused_kernel_chain_stays_parity_green(B, n, D, R, share):
+    """The unfused per-level chain (the default above batch 64, CLIORA_FLAG_UNFUSED) against the float64 oracle,
+    forward and every gradient, like the fused default in test_chart_vs_oracle_live."""
+    from cliora_b200.net import diora as diora_mod
+    saved = diora_mod.DioraBase.__init__
+
+    def init(self, *a, **k):
+        saved(self, *a, **k)
+        self.fused = False
+    diora_mod.DioraBase.__init__ = init
+    try:
+        test_chart_vs_oracle_live(B, n, D, R, share)
+    finally:
+        diora_mod.DioraBase.__init__ = saved
