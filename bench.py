@@ -345,7 +345,7 @@ def main():
         sync = None
         if world > 1:
             from cliora_b200.parallel import GradSync
-            sync = trainer.grad_sync = GradSync([p for p in trainer.net.parameters() if p.requires_grad], world)
+            sync = trainer.grad_sync = GradSync.for_module(trainer.net, world)
             trainer.ngpus = world
         rec = {}
         if check and rank == 0:

@@ -42,7 +42,7 @@ _L_FIELDS = ['ws_floats', 'bws_floats', 'rows_in', 'rows_out', 'PI', 'Pin', 'Pou
              'att_in', 'nrm_out', 'leaf_t', 'Zin', 'Yin', 'Ein', 'Prin', 'Zout', 'Yout', 'Eout', 'Prout',
              'Wcat_in', 'Wcat_out', 'Gh_in', 'Gs_in', 'GP_in', 'Gh_out', 'Gs_out', 'GP_out', 'GA2', 'coef',
              'GE', 'GZ', 'splitk', 'gu', 'W2p', 'W2Tp', 'oW2p', 'oW2Tp', 'GPp', 'Hp', 'Mbin', 'Mbout', 'CSin', 'CSout',
-             'GYp_in', 'GYp_out', 'GA', 'CM', 'db2acc']
+             'GYp_in', 'GYp_out', 'GA', 'CM', 'db2acc', 'W2h', 'W2Th', 'oW2h', 'oW2Th']
 
 
 class ProfileRow(Structure):

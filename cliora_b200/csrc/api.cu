@@ -1,5 +1,6 @@
 // extern "C" entry points of libcliora_b200.so (declared in include/cliora_b200.h).
 // Host-side orchestration only: level loops, buffer carving, kernel launches on the caller's stream.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
@@ -128,6 +129,10 @@ static int compute_layout(const cliora_dims& d, cliora_layout& L) {
   L.oW2Tp = d.share ? L.W2Tp : take(2 * D * D);
   L.Mbin = D <= 512 ? take(L.rows_in * 16) : -1;    // ReLU bitmasks of Z (16 x uint32 per split row)
   L.Mbout = D <= 512 ? take(L.rows_out * 16) : -1;
+  L.W2h = take(D * D / 2 + 4);
+  L.W2Th = take(D * D / 2 + 4);
+  L.oW2h = d.share ? L.W2h : take(D * D / 2 + 4);
+  L.oW2Th = d.share ? L.W2Th : take(D * D / 2 + 4);
   L.ws_floats = o;
 
   const int64_t max_rows = B * n * (n - 1) > 0 ? B * n * (n - 1) : 4;
@@ -173,6 +178,7 @@ struct Ctx {
   cudaStream_t st;
   bool use_tc;   // compose GEMMs on tcgen05 (3xTF32 split pairs) instead of the SIMT fp32 kernel
   int tc_mode;   // UMMA accumulation scheme: 2 = fp32-accurate 3xTF32 (default), 1 = single-pass TF32 (CLIORA_FLAG_TF32_1PASS)
+  int lvl_mode;  // mode of the fused level kernels: tc_mode, or 3 = bf16 operands (CLIORA_FLAG_BF16)
 };
 
 static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
@@ -182,7 +188,8 @@ static int make_ctx(const cliora_dims* dims, cliora_stream_t stream, Ctx& c) {
   c.C = num_cells(dims->n);
   c.st = (cudaStream_t)stream;
   c.use_tc = (dims->D >= 32) && (g_debug[1] == 0);
-  c.tc_mode = (dims->flags & CLIORA_FLAG_TF32_1PASS) ? 1 : g_debug[0];
+  c.tc_mode = (dims->flags & (CLIORA_FLAG_TF32_1PASS | CLIORA_FLAG_BF16)) ? 1 : g_debug[0];
+  c.lvl_mode = (dims->flags & CLIORA_FLAG_BF16) ? 3 : (c.tc_mode == 1 ? 1 : 2);
   return CLIORA_OK;
 }
 
@@ -344,6 +351,26 @@ static int compose_gemm_bwd(const Ctx& c, bool outside, int level, int64_t r0, i
   return launch_gemm(c.st, /*nt=*/false, p);
 }
 
+// W [D, D] fp32 -> bf16 copy and bf16 transposed copy (bf16 mode of the fused level kernels)
+__global__ void to_bf16_kernel(const float* __restrict__ W, int D, __nv_bfloat16* __restrict__ out,
+                               __nv_bfloat16* __restrict__ outT) {
+  pdl_prologue();
+  const int64_t n = (int64_t)D * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D), cidx = (int)(i % D);
+    const __nv_bfloat16 v = __float2bfloat16_rn(W[i]);
+    out[i] = v;
+    outT[(int64_t)cidx * D + r] = v;
+  }
+}
+
+static int prepare_w2_bf16(const Ctx& c, const float* W2, float* h, float* hT) {
+  launch_k(to_bf16_kernel, 296, 256, 0, c.st, W2, c.d.D, reinterpret_cast<__nv_bfloat16*>(h),
+           reinterpret_cast<__nv_bfloat16*>(hT));
+  CL_CHECK_LAUNCH("to_bf16_kernel");
+  return CLIORA_OK;
+}
+
 static int prepare_w2_pairs(const Ctx& c, const float* W2, float* pair, float* pairT) {
   const int D = c.d.D;
   const int64_t n = (int64_t)D * D;
@@ -445,7 +472,8 @@ static int chain_count(const Ctx& c) {
 // One launch for a whole forward level (gather + compose GEMM + softmax-weighted sums + cell finalize): lvl::level_fwd_kernel.
 // Returns false when the shape is outside what the fused kernel covers (the unfused chain then runs).
 static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g) {
-  if (!c.use_tc || g_debug[6] != 0 || (c.d.flags & CLIORA_FLAG_UNFUSED) || N < 1 || N > lvl::kRows) return false;
+  const bool unfused = (c.d.flags & CLIORA_FLAG_UNFUSED) && !(c.d.flags & CLIORA_FLAG_BF16);   // bf16 lives in the fused kernels
+  if (!c.use_tc || g_debug[6] != 0 || unfused || N < 1 || N > lvl::kRows) return false;
   if (!lvl::level_geom(c.d.D, g)) return false;
   if (c.d.D > 1024) return false;
   return true;
@@ -472,7 +500,7 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
                                   lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) / chain_count(c),
                                   a.max_sent);
   if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
-  a.mode = c.tc_mode == 1 ? 1 : 2;
+  a.mode = c.lvl_mode;
   a.outside = outside ? 1 : 0;
   a.C = c.C;
   const int ldPin = (int)(c.L.PI * D);
@@ -498,7 +526,7 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   a.nrm2 = (!outside && c.d.R > 0) ? ws + c.L.nrm2_in : nullptr;
   a.att = (!outside && c.d.R > 0) ? ws + c.L.att_in : nullptr;
   a.obj = obj; a.keep = keep;
-  const float* W2pair = ws + (outside ? c.L.oW2p : c.L.W2p);
+  const float* W2pair = c.lvl_mode == 3 ? ws + (outside ? c.L.oW2h : c.L.W2h) : ws + (outside ? c.L.oW2p : c.L.W2p);
   return lvl::launch_level_fwd(c.st, a, W2pair, outside ? "level_fwd_outside" : "level_fwd_inside");
 }
 
@@ -539,7 +567,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
     int max_sent = 0;
     a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, (148 / geom.nc) / chain_count(c), max_sent);
-    a.mode = c.tc_mode == 1 ? 1 : 2;
+    a.mode = c.lvl_mode;
     a.outside = OUTSIDE ? 1 : 0;
     a.C = c.C;
     const int64_t r0 = OUTSIDE ? B * outside_rows_before(n, level) : B * inside_rows_before(n, level);
@@ -563,7 +591,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     if (cells_inline) {
       b.cellGh = g.Gh; b.cellH = chart_h; b.cellNrm = g.c.nrm; b.cellS = chart_s;
     }
-    const float* W2T = ws + (OUTSIDE ? c.L.oW2Tp : c.L.W2Tp);
+    const float* W2T = c.lvl_mode == 3 ? ws + (OUTSIDE ? c.L.oW2Th : c.L.W2Th) : ws + (OUTSIDE ? c.L.oW2Tp : c.L.W2Tp);
     return lvl::launch_level_bwd(c.st, b, W2T, OUTSIDE ? "level_bwd_outside" : "level_bwd_inside");
   }
 
@@ -705,6 +733,10 @@ int cliora_inside_fwd(const cliora_dims* dims, const cliora_weights* w, const fl
   if (c.use_tc) {
     CL_TRY(prepare_w2_pairs(c, w->W2, ws + c.L.W2p, ws + c.L.W2Tp));
     if (!c.d.share) CL_TRY(prepare_w2_pairs(c, w->oW2, ws + c.L.oW2p, ws + c.L.oW2Tp));
+    if (c.lvl_mode == 3) {
+      CL_TRY(prepare_w2_bf16(c, w->W2, ws + c.L.W2h, ws + c.L.W2Th));
+      if (!c.d.share) CL_TRY(prepare_w2_bf16(c, w->oW2, ws + c.L.oW2h, ws + c.L.oW2Th));
+    }
   }
 
   // leaves: t = tanh(W_leaf x + b); h = finalize(t)

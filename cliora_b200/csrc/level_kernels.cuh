@@ -138,7 +138,7 @@ struct LevelFwdArgs {
   int ncols;     // output columns per CTA (multiple of 4)
   int n_umma;    // ncols rounded up to 16 (<= kMaxUmmaN)
   int nc;        // cluster size = column slices
-  int mode;      // 2: fp32-accurate 3xTF32 (main + cross accumulator), 1: single TF32 pass
+  int mode;      // 2: fp32-accurate 3xTF32 (main + cross accumulator), 1: single TF32 pass, 3: bf16 operands (fp32 accumulate)
   int outside;
   int64_t C;
   // first / second operand of a split: inside (left, right) both from the inside chart; outside (sibling from the
@@ -221,6 +221,30 @@ CL_D void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t i
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// bf16 mode (mode 3): D[tmem] (+)= A[tmem, bf16 pairs] * B[smem, bf16], fp32 accumulate (kind::f16, K = 16 per MMA)
+CL_D void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n
+CL_HD uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+// two floats -> one packed bf16x2 word, element `even` in the low half (the order bf16 arrays have in memory)
+CL_D uint32_t pack_bf16x2(float even, float odd) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(odd), "f"(even));
+  return d;
+}
+CL_D void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 constexpr uint32_t kTmemA0 = 256;      // first column of the A-operand stages in tensor memory (64 columns per stage)
 
@@ -341,9 +365,16 @@ CL_D void transform_a_tmem(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empt
     mbar_wait(&emptyA[stage], phase ^ 1);                   // the MMAs that read this TMEM stage have retired
     tcgen05_fence_after();
     if (st_) dbg[35 + (kb - 4) * 6] = clock_now();
-    const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
-    tmem_st16(ta, hi);
-    if (mode != 1) tmem_st16(ta + 32, lo);
+    if (mode == 3) {       // bf16: the 16 values of this half become 8 packed columns (hi + lo restores the value)
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(hi[2 * j] + lo[2 * j], hi[2 * j + 1] + lo[2 * j + 1]);
+      tmem_st8(tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 8), pk);
+    } else {
+      const uint32_t ta = tmem_base + lane_addr + kTmemA0 + (uint32_t)(stage * 64 + half * 16);
+      tmem_st16(ta, hi);
+      if (mode != 1) tmem_st16(ta + 32, lo);
+    }
     tmem_st_wait();
     if (st_) dbg[36 + (kb - 4) * 6] = clock_now();
     tcgen05_fence_before();
@@ -437,13 +468,23 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   if (warp == 0) {
     // ------------------------------------------------------------ W2 slice: TMA
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(a.mode == 1 ? b_bytes : 2 * b_bytes);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int sb = kb % nbs;
-        const uint32_t phase = (kb / nbs) & 1;
-        mbar_wait(&emptyB[sb], phase ^ 1);
-        mbar_expect_tx(&fullB[sb], tx);
-        tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kb * 32, n0, 0);
+      if (a.mode == 3) {
+        // bf16 W2 slice: one 128-byte-swizzled box of 64 k-elements feeds two k-blocks of the A pipeline
+        for (int kq = 0; kq < (num_kb + 1) / 2; ++kq) {
+          const int sb = kq % nbs;
+          mbar_wait(&emptyB[sb], ((kq / nbs) & 1) ^ 1);
+          mbar_expect_tx(&fullB[sb], (uint32_t)b_bytes);
+          tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kq * 64, n0, 0);
+        }
+      } else {
+        const uint32_t tx = (uint32_t)(a.mode == 1 ? b_bytes : 2 * b_bytes);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int sb = kb % nbs;
+          const uint32_t phase = (kb / nbs) & 1;
+          mbar_wait(&emptyB[sb], phase ^ 1);
+          mbar_expect_tx(&fullB[sb], tx);
+          tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kb * 32, n0, 0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -451,6 +492,23 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(a.n_umma);
       uint32_t acc = 0;
+      if (A_TMEM && a.mode == 3) {
+        const uint32_t idesc16 = umma_idesc_bf16(a.n_umma);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int sA_i = kb % kAStages, kq = kb >> 1, sb = kq % nbs;
+          mbar_wait(&fullB[sb], (kq / nbs) & 1);
+          mbar_wait(&fullA[sA_i], (kb / kAStages) & 1);
+          tcgen05_fence_after();
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(ringB + sb * b_stage_bytes)) + (uint64_t)((kb & 1) * 4);
+          const uint32_t ta = tmem_base + kTmemA0 + (uint32_t)(sA_i * 64);
+          umma_bf16_ts(tmem_base, ta, bd, idesc16, acc);              // k elements 0..15 of the k-block
+          umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc16, 1);        // 16..31
+          acc = 1;
+          umma_commit(&emptyA[sA_i]);
+          if ((kb & 1) || kb == num_kb - 1) umma_commit(&emptyB[sb]);
+        }
+        umma_commit(tmem_full);
+      } else {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sA_i = kb % kAStages, sb = kb % nbs;
         mbar_wait(&fullB[sb], (kb / nbs) & 1);
@@ -488,6 +546,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
         if (dbg_row && kb >= 3 && kb < 7) dbg_row[49 + (kb - 3) * 2] = clock_now();
       }
       umma_commit(tmem_full);
+      }
       if (dbg_row) dbg_row[21] = clock_now();
     }
   } else if (warp >= kCopyWarp0) {
@@ -743,7 +802,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);    // warp-collective: no early exit
-      if (a.mode != 1) {
+      if (a.mode == 2) {
         float x[16];
         tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a.n_umma + c0), x);
 #pragma unroll
@@ -1082,18 +1141,44 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(a.mode == 1 ? b_bytes : 2 * b_bytes);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int sb = kb % nbs;
-        mbar_wait(&emptyB[sb], ((kb / nbs) & 1) ^ 1);
-        mbar_expect_tx(&fullB[sb], tx);
-        tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kb * 32, n0, 0);
+      if (a.mode == 3) {
+        // bf16 W2 slice: one 128-byte-swizzled box of 64 k-elements feeds two k-blocks of the A pipeline
+        for (int kq = 0; kq < (num_kb + 1) / 2; ++kq) {
+          const int sb = kq % nbs;
+          mbar_wait(&emptyB[sb], ((kq / nbs) & 1) ^ 1);
+          mbar_expect_tx(&fullB[sb], (uint32_t)b_bytes);
+          tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kq * 64, n0, 0);
+        }
+      } else {
+        const uint32_t tx = (uint32_t)(a.mode == 1 ? b_bytes : 2 * b_bytes);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int sb = kb % nbs;
+          mbar_wait(&emptyB[sb], ((kb / nbs) & 1) ^ 1);
+          mbar_expect_tx(&fullB[sb], tx);
+          tma_load_3d(ringB + sb * b_stage_bytes, &tmW, &fullB[sb], kb * 32, n0, 0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(a.n_umma);
       uint32_t acc = 0;
+      if (a.mode == 3) {
+        const uint32_t idesc16 = umma_idesc_bf16(a.n_umma);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int sA_i = kb % kAStages, kq = kb >> 1, sb = kq % nbs;
+          mbar_wait(&fullB[sb], (kq / nbs) & 1);
+          mbar_wait(&fullA[sA_i], (kb / kAStages) & 1);
+          tcgen05_fence_after();
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(ringB + sb * b_stage_bytes)) + (uint64_t)((kb & 1) * 4);
+          const uint32_t ta = tmem_base + kTmemA0 + (uint32_t)(sA_i * 64);
+          umma_bf16_ts(tmem_base, ta, bd, idesc16, acc);
+          umma_bf16_ts(tmem_base, ta + 8, bd + 2, idesc16, 1);
+          acc = 1;
+          umma_commit(&emptyA[sA_i]);
+          if ((kb & 1) || kb == num_kb - 1) umma_commit(&emptyB[sb]);
+        }
+      } else
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sA_i = kb % kAStages, sb = kb % nbs;
         mbar_wait(&fullB[sb], (kb / nbs) & 1);
@@ -1197,7 +1282,7 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
-      if (a.mode != 1) {
+      if (a.mode == 2) {
         float x[16];
         tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a.n_umma + c0), x);
 #pragma unroll
@@ -1321,15 +1406,35 @@ inline size_t level_fwd_smem(int n_umma) { return (size_t)ring_bytes(n_umma) + k
 
 extern long long* g_level_dbg;   // debug: timeline buffer handed to the launch selected by g_debug[8] (level + 1) / g_debug[9] (outside)
 
+// bf16 matrix [rows, K] (K contiguous) as a 3-D map {K, rows, 1}, box {64, box_rows, 1}, 128-byte swizzle
+inline int make_bf16_map(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (fn == nullptr) return CLIORA_ERR_CUDA;
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, 1};
+  cuuint64_t gstride[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r);
+    return CLIORA_ERR_CUDA;
+  }
+  return CLIORA_OK;
+}
+
 inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a_in, const float* W2pair, const char* tag) {
   LevelFwdArgs a = a_in;
   a.exp_flags = g_debug[12];
   a.dbg = (g_level_dbg != nullptr && g_debug[8] == a.level + 1 && g_debug[9] == a.outside) ? g_level_dbg : nullptr;
   CUtensorMap tmW;
-  CL_TRY(tc::make_pair_map(&tmW, W2pair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
-                           a.mode == 1 ? 1 : 2));
+  if (a.mode == 3) CL_TRY(make_bf16_map(&tmW, W2pair, a.D, a.D, a.n_umma));      // W2pair = the bf16 copy in this mode
+  else
+    CL_TRY(tc::make_pair_map(&tmW, W2pair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
+                             a.mode == 1 ? 1 : 2));
   const size_t smem = level_fwd_smem(a.n_umma);
-  const bool a_tmem = a.zmask == nullptr && g_debug[13] == 0;      // the bit-mask variant keeps the A pair in shared memory
+  const bool a_tmem = (a.zmask == nullptr && g_debug[13] == 0) || a.mode == 3;      // the bit-mask variant keeps the A pair in shared memory
   const void* kern = a_tmem ? reinterpret_cast<const void*>(level_fwd_kernel<true>)
                             : reinterpret_cast<const void*>(level_fwd_kernel<false>);
   CL_CUDA(func_attr_at_least(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1362,8 +1467,10 @@ inline size_t level_bwd_smem(int n_umma) { return (size_t)ring_bytes(n_umma) + k
 inline int launch_level_bwd(cudaStream_t st, const LevelBwdArgs& g, const float* W2Tpair, const char* tag) {
   const LevelFwdArgs& a = g.geo;
   CUtensorMap tmW;
-  CL_TRY(tc::make_pair_map(&tmW, W2Tpair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
-                           a.mode == 1 ? 1 : 2));
+  if (a.mode == 3) CL_TRY(make_bf16_map(&tmW, W2Tpair, a.D, a.D, a.n_umma));
+  else
+    CL_TRY(tc::make_pair_map(&tmW, W2Tpair, a.D, a.D, a.D, (int64_t)a.D * a.D, a.n_umma, CU_TENSOR_MAP_SWIZZLE_128B,
+                             a.mode == 1 ? 1 : 2));
   const size_t smem = level_bwd_smem(a.n_umma);
   const void* kern = reinterpret_cast<const void*>(level_bwd_kernel<0>);
   CL_CUDA(func_attr_at_least(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -60,6 +60,8 @@ class DioraBase(nn.Module):
         self.chains = None     # concurrent sentence sub-batches (None: pick from the batch size)
         # 'fp32': tensor-core GEMMs are fp32-accurate (3xTF32, default, <= 1e-4 vs the reference);
         # 'tf32': single TF32 pass, stated tolerance 1e-2 of max, trees not guaranteed identical
+        # 'bf16': bf16 operands in the compose GEMMs of the fused level kernels (fp32 accumulate), single-pass TF32
+        #         elsewhere; stated tolerance 3e-2 of max on vectors, 1e-2 on scores; trees not guaranteed identical
         self.precision = 'fp32'
         # fused level kernels (one launch per level forward, two backward) or the unfused per-level chain: 'auto'
         # fuses up to batch 32, where per-level latency decides (measured on B200, n=20: +4 % at batch 16, a tie at 32,
@@ -175,10 +177,10 @@ class DioraBase(nn.Module):
         run = ChartRun()
         # measured on B200 (n=20, D=400): 2 chains are best at batch 32 (5034 vs 4910 sent/s with 4), 4 at batch 128
         chains = self.chains if self.chains is not None else max(1, min(2 if B < 64 else 4, B // 8))
-        if self.precision not in ('fp32', 'tf32'):
-            raise ValueError("precision must be 'fp32' or 'tf32'")
+        if self.precision not in ('fp32', 'tf32', 'bf16'):
+            raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
         fused = (B <= 32) if self.fused == 'auto' else bool(self.fused)
-        flags = (2 if self.precision == 'tf32' else 0) | (0 if fused else 4) | ((min(chains, 15) & 15) << 8)
+        flags = {'fp32': 0, 'tf32': 2, 'bf16': 8}[self.precision] | (0 if fused else 4) | ((min(chains, 15) & 15) << 8)
         outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, flags, x_span, obj, keep,
                                    *self._weight_list())
         self._run = run

@@ -28,6 +28,15 @@ class GradSync(object):
         if broadcast and world_size > 1 and dist.is_initialized():
             self.broadcast_parameters(list(buffers))
 
+    @classmethod
+    def for_module(cls, module, world_size, group=None):
+        """Wrap a whole module the way DDP does: trainable parameters are synchronised every step, and EVERYTHING
+        else it owns (frozen parameters such as the word-embedding table, trainer.py:538-541, and buffers) is
+        broadcast from rank 0 once, so replicas that were initialised from different random streams agree."""
+        params = [p for p in module.parameters() if p.requires_grad]
+        rest = [p for p in module.parameters() if not p.requires_grad] + list(module.buffers())
+        return cls(params, world_size, group=group, buffers=rest)
+
     def broadcast_parameters(self, extra=()):
         """Rank 0's values into every replica (what wrapping a module in DDP does, trainer.py:573-574)."""
         with torch.no_grad():

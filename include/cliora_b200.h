@@ -100,6 +100,10 @@ typedef struct cliora_dims {
 /* Reduced-precision mode: the tensor-core GEMMs issue one TF32 pass instead of the fp32-accurate three.
  * Stated tolerance 1e-2 of max on chart vectors (measured ~3e-3); CKY trees are NOT guaranteed identical. */
 #define CLIORA_FLAG_TF32_1PASS 2
+/* bf16-GEMM mode: the compose GEMMs of the fused level kernels take bf16 operands (fp32 accumulate, kind::f16 UMMAs);
+ * every other tensor-core GEMM runs single-pass TF32.  Stated tolerance 3e-2 of max on chart vectors, 1e-2 on scores
+ * (SURVEY.md section 7); CKY trees are NOT guaranteed identical.  Implies the fused level kernels. */
+#define CLIORA_FLAG_BF16 8
 /* Run the unfused per-level kernel chain (split_build -> tcgen05 GEMM -> cell kernels -> scatter) instead of the fused
  * level kernels.  Same results; it is the faster of the two once a level no longer fits one wave of clusters (batches
  * above ~32 sentences at length 20), where per-tile SM time rather than per-level latency decides. */
@@ -143,6 +147,8 @@ typedef struct cliora_layout {
   int64_t GYp_in, GYp_out;    /* [2, rows_in, D], [2, rows_out, D] */
   int64_t GA, CM;             /* [B,C,D], [B,C] */
   int64_t db2acc;             /* [2, D]: inside, outside */
+  /* forward workspace, bf16 mode: bf16 copies of W2 and W2^T (o* alias when share), D*D/2 floats each */
+  int64_t W2h, W2Th, oW2h, oW2Th;
 } cliora_layout;
 
 int cliora_chart_layout(const cliora_dims* dims, cliora_layout* out);

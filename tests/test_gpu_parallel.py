@@ -45,7 +45,7 @@ def _worker(rank, world, port, out):
     cfg = _cfg()
     tr = _trainer(cfg, seed=10 + rank)              # different weights per rank: the broadcast must fix that
     params = [p for p in tr.net.parameters() if p.requires_grad]
-    sync = GradSync(params, world)
+    sync = GradSync.for_module(tr.net, world)      # also broadcasts the frozen embedding table, like DDP
     assert sync.in_sync()
     tr.net.train()
     outp = tr.run_net(_shard(cfg, rank, torch.device('cuda', rank)), None, compute_loss=True)

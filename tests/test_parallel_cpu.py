@@ -73,3 +73,23 @@ def test_gradsync_world1_is_noop():
     sync()
     for a, p in zip(before, m.parameters()):
         assert torch.equal(a, p.grad)
+
+
+def _worker_frozen(rank, world, port):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from cliora_b200.parallel import GradSync
+    m = _model(seed=rank)
+    m[0].weight.requires_grad = False            # a frozen tensor (the word-embedding table in the real net)
+    m.register_buffer('stat', torch.full((3,), float(rank)))
+    GradSync.for_module(m, world)
+    ref = _model(seed=0)
+    assert torch.equal(m[0].weight, ref[0].weight)           # frozen parameters are broadcast too
+    assert torch.equal(m.stat, torch.zeros(3))               # and buffers
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_for_module_broadcasts_frozen_parameters_and_buffers():
+    world, port = 2, _free_port()
+    mp.spawn(_worker_frozen, args=(world, port), nprocs=world, join=True)
