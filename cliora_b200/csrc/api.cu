@@ -254,6 +254,7 @@ static CellArgs cell_args(const Ctx& c, int level, bool outside, float* ws, floa
   const int n = c.d.n;
   a.B = c.d.B; a.n = n; a.level = level; a.D = c.d.D; a.R = outside ? 0 : c.d.R; a.C = c.C;
   a.L = n - level;
+  a.no_norm = (c.d.flags & CLIORA_FLAG_NO_NORMALIZE) ? 1 : 0;
   a.chart_h = chart_h; a.chart_s = chart_s;
   if (!outside) {
     a.N = level == 0 ? 1 : level;
@@ -501,6 +502,7 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
                                   a.max_sent);
   if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
   a.mode = c.lvl_mode;
+  a.no_norm = (c.d.flags & CLIORA_FLAG_NO_NORMALIZE) ? 1 : 0;
   a.outside = outside ? 1 : 0;
   a.C = c.C;
   const int ldPin = (int)(c.L.PI * D);
@@ -568,6 +570,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     int max_sent = 0;
     a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, (148 / geom.nc) / chain_count(c), max_sent);
     a.mode = c.lvl_mode;
+    a.no_norm = (c.d.flags & CLIORA_FLAG_NO_NORMALIZE) ? 1 : 0;
     a.outside = OUTSIDE ? 1 : 0;
     a.C = c.C;
     const int64_t r0 = OUTSIDE ? B * outside_rows_before(n, level) : B * inside_rows_before(n, level);
@@ -782,7 +785,8 @@ int cliora_outside_fwd(const cliora_dims* dims, const cliora_weights* w, const f
 
   launch_k(init_proj_kernel, 296, 256, 0, c.st, ws + c.L.Pout, (int64_t)B * c.C, 2 * D, 0, D, ob1);
   CL_CHECK_LAUNCH("init_proj_kernel");
-  launch_k(outside_root_kernel, B, 128, 0, c.st, B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out);
+  launch_k(outside_root_kernel, B, 128, 0, c.st, B, D, c.C, w->root, outside_h, outside_s, ws + c.L.nrm_out,
+           (c.d.flags & CLIORA_FLAG_NO_NORMALIZE) ? 1 : 0);
   CL_CHECK_LAUNCH("outside_root_kernel");
   if (n > 1) CL_TRY(project_level(c, n - 1, outside_h, Wcat_out, 2 * D, ws + c.L.Pout));
   for (int level = n - 2; level >= 0; --level) {

@@ -146,7 +146,7 @@ __global__ __launch_bounds__(kCellThreads) void cell_fwd_warp_kernel(const CellA
     for (int t = 0; t < kColT; ++t)
       if (lane * 4 + t * 128 < a.D) ss += dot4(acc[t], acc[t]);
     ss = warp_sum(ss);
-    const float nrm = fmaxf(sqrtf(ss), kTiny);
+    const float nrm = a.no_norm ? 1.f : fmaxf(sqrtf(ss), kTiny);
     const float inv_nrm = 1.f / nrm;
 #pragma unroll
     for (int t = 0; t < kColT; ++t) {
@@ -154,7 +154,7 @@ __global__ __launch_bounds__(kCellThreads) void cell_fwd_warp_kernel(const CellA
       q[t] = make_float4(acc[t].x * inv_nrm, acc[t].y * inv_nrm, acc[t].z * inv_nrm, acc[t].w * inv_nrm);
       if (j < a.D) st4((VL ? a.q : a.chart_h) + cell * a.D + j, q[t]);
     }
-    if (lane == 0) a.nrm[cell] = nrm;
+    if (lane == 0) a.nrm[cell] = a.no_norm ? -1.f : nrm;
   }
   if (!VL) return;
   cp_async_wait_all();
@@ -194,7 +194,7 @@ __global__ __launch_bounds__(kCellThreads) void cell_fwd_warp_kernel(const CellA
   for (int t = 0; t < kColT; ++t)
     if (lane * 4 + t * 128 < a.D) ss2 += dot4(q[t], q[t]);
   ss2 = warp_sum(ss2);
-  const float nrm2 = fmaxf(sqrtf(ss2), kTiny);
+  const float nrm2 = a.no_norm ? 1.f : fmaxf(sqrtf(ss2), kTiny);
   const float inv2 = 1.f / nrm2;
 #pragma unroll
   for (int t = 0; t < kColT; ++t) {
@@ -202,7 +202,7 @@ __global__ __launch_bounds__(kCellThreads) void cell_fwd_warp_kernel(const CellA
     if (j < a.D)
       st4(a.chart_h + cell * a.D + j, make_float4(q[t].x * inv2, q[t].y * inv2, q[t].z * inv2, q[t].w * inv2));
   }
-  if (lane == 0) a.nrm2[cell] = nrm2;
+  if (lane == 0) a.nrm2[cell] = a.no_norm ? -1.f : nrm2;
 }
 
 // backward of the above + per-split gradients (same maths as cell_bwd_kernel)
@@ -232,7 +232,8 @@ __global__ __launch_bounds__(kCellThreads) void cell_bwd_warp_kernel(const CellB
   }
   if (active) {
     const int64_t cell = (int64_t)b * a.C + lvl_off(a.n, a.level) + p;
-    const float nrm = a.nrm[cell];
+    const float nrm_raw = a.nrm[cell];
+    const float nrm = fabsf(nrm_raw);
     float4 gv[kColT], hv[kColT], qv[kColT];
     float hd = 0.f;
 #pragma unroll
@@ -248,9 +249,9 @@ __global__ __launch_bounds__(kCellThreads) void cell_bwd_warp_kernel(const CellB
     }
     hd = warp_sum(hd);
     if (VL) {
-      const float nrm2 = a.nrm2[cell];
-      const float coef = unit_bwd_coef(nrm2, hd);
-      const float inv2 = 1.f / nrm2;
+      const float nrm2_raw = a.nrm2[cell];
+      const float coef = unit_bwd_coef(nrm2_raw, hd);
+      const float inv2 = 1.f / fabsf(nrm2_raw);
 #pragma unroll
       for (int t = 0; t < kColT; ++t) {
         const int j = lane * 4 + t * 128;
@@ -298,7 +299,7 @@ __global__ __launch_bounds__(kCellThreads) void cell_bwd_warp_kernel(const CellB
       hd = warp_sum(hd);
     }
     // ga = unit_bwd(gq, q, nrm)
-    const float coef = unit_bwd_coef(nrm, hd);
+    const float coef = unit_bwd_coef(nrm_raw, hd);
     const float inv = 1.f / nrm;
     float ad = 0.f;
 #pragma unroll
@@ -398,7 +399,21 @@ __global__ __launch_bounds__(kCellThreads) void cell_bwd_warp_kernel(const CellB
       d = warp_sum(d);
       if (lane == 0) {
         const float gp = d + ev[u] * gs;
-        g.GE[row[u]] = pk[u] * (gs + gp - cm);
+        g.GE[row[u]] = a.no_norm ? gp : pk[u] * (gs + (gp - cm));
+      }
+    }
+  }
+  if (a.no_norm) {     // exact cancellation of the chosen split (see cell_bwd_kernel)
+    __syncthreads();
+    if (warp < ncell) {
+      const int64_t r0 = (int64_t)b * a.L * a.N + (int64_t)(p0 + warp) * a.sp;
+      const float gs = s_sc[warp * 2];
+      float cm2 = 0.f;
+      for (int k = 0; k < a.N; ++k) cm2 = fmaf(a.Pr[r0 + (int64_t)k * a.sk], g.GE[r0 + (int64_t)k * a.sk], cm2);
+      __syncwarp();
+      for (int k = lane; k < a.N; k += 32) {
+        const int64_t row = r0 + (int64_t)k * a.sk;
+        g.GE[row] = a.Pr[row] * (gs + (g.GE[row] - cm2));
       }
     }
   }

@@ -173,6 +173,7 @@ struct CellArgs {
   float* att;          // [B,C,R] (R > 0)
   const float* obj;    // [B,R,D] (R > 0)
   const uint8_t* keep; // [B,C,R] or nullptr
+  int no_norm;         // --normalize none: norms are the identity; the saved norm is the sentinel -1
 };
 
 template <bool VL>
@@ -235,7 +236,7 @@ __global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
     ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
   }
   ss = block_sum(ss, s_red);
-  const float nrm = fmaxf(sqrtf(ss), kTiny);
+  const float nrm = a.no_norm ? 1.f : fmaxf(sqrtf(ss), kTiny);
   const float inv_nrm = 1.f / nrm;
   // q = a / nrm
   for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
@@ -245,7 +246,7 @@ __global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
     if (VL) st4(a.q + cell * a.D + j, v);
     else st4(a.chart_h + cell * a.D + j, v);
   }
-  if (tid == 0) a.nrm[cell] = nrm;
+  if (tid == 0) a.nrm[cell] = a.no_norm ? -1.f : nrm;
   if (!VL) return;
 
   __syncthreads();
@@ -296,30 +297,31 @@ __global__ __launch_bounds__(128) void cell_aggregate_kernel(const CellArgs a) {
     ss2 += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
   }
   ss2 = block_sum(ss2, s_red);
-  const float nrm2 = fmaxf(sqrtf(ss2), kTiny);
+  const float nrm2 = a.no_norm ? 1.f : fmaxf(sqrtf(ss2), kTiny);
   const float inv2 = 1.f / nrm2;
   for (int j = tid * 4; j < a.D; j += blockDim.x * 4) {
     float4 v = ld4(s_a + j);
     v.x *= inv2; v.y *= inv2; v.z *= inv2; v.w *= inv2;
     st4(a.chart_h + cell * a.D + j, v);
   }
-  if (tid == 0) a.nrm2[cell] = nrm2;
+  if (tid == 0) a.nrm2[cell] = a.no_norm ? -1.f : nrm2;
 }
 
 // outside root: outside_h[:, root] = unit(root_vector), outside_s[:, root] = 0   (diora.py:337-356)
 __global__ void outside_root_kernel(int B, int D, int64_t C, const float* __restrict__ root,
-                                    float* __restrict__ oh, float* __restrict__ os_, float* __restrict__ nrm_out) {
+                                    float* __restrict__ oh, float* __restrict__ os_, float* __restrict__ nrm_out,
+                                    int no_norm) {
   pdl_prologue();
   __shared__ float red[64];
   float ss = 0.f;
   for (int j = threadIdx.x; j < D; j += blockDim.x) ss += root[j] * root[j];
   ss = block_sum(ss, red);
-  const float nrm = fmaxf(sqrtf(ss), kTiny);
+  const float nrm = no_norm ? 1.f : fmaxf(sqrtf(ss), kTiny);
   const int b = blockIdx.x;
   for (int j = threadIdx.x; j < D; j += blockDim.x) oh[((int64_t)b * C + C - 1) * D + j] = root[j] / nrm;
   if (threadIdx.x == 0) {
     os_[(int64_t)b * C + C - 1] = 0.f;
-    nrm_out[(int64_t)b * C + C - 1] = nrm;
+    nrm_out[(int64_t)b * C + C - 1] = no_norm ? -1.f : nrm;
   }
 }
 
@@ -327,7 +329,8 @@ __global__ void outside_root_kernel(int B, int D, int64_t C, const float* __rest
 // backward
 // ==========================================================================================
 
-// d/da of a / clamp(|a|, eps): live branch (g - h (h.g)) / nrm, clamped branch g / eps.
+// d/da of a / clamp(|a|, eps): live branch (g - h (h.g)) / nrm, clamped branch g / eps.  With --normalize none the saved
+// norm is the sentinel -1: the coefficient is 0 and 1 / |nrm| = 1, i.e. the gradient passes through unchanged.
 CL_D float unit_bwd_coef(float nrm, float hdotg) { return (nrm > kTiny) ? hdotg : 0.f; }
 
 struct CellBwdArgs {
@@ -364,7 +367,8 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
   const int64_t row0 = (int64_t)b * a.L * a.N + (int64_t)p * a.sp;
   const float* hvec = a.chart_h + cell * a.D;
   const float* qvec = VL ? a.q + cell * a.D : hvec;
-  const float nrm = a.nrm[cell];
+  const float nrm_raw = a.nrm[cell];
+  const float nrm = fabsf(nrm_raw);
 
   // ---- gradient wrt q (the first-normalised vector) ----
   float hd = 0.f;
@@ -376,9 +380,9 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
   }
   hd = block_sum(hd, s_red);
   if (VL) {
-    const float nrm2 = a.nrm2[cell];
-    const float coef = unit_bwd_coef(nrm2, hd);
-    const float inv2 = 1.f / nrm2;
+    const float nrm2_raw = a.nrm2[cell];
+    const float coef = unit_bwd_coef(nrm2_raw, hd);
+    const float inv2 = 1.f / fabsf(nrm2_raw);
     for (int j = tid; j < a.D; j += blockDim.x) {
       const float v = (s_g[j] - hvec[j] * coef) * inv2;   // ga2
       s_g[j] = v;
@@ -431,7 +435,7 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
   }
   // ---- ga = unit_bwd(gq, q, nrm) ----
   {
-    const float coef = unit_bwd_coef(nrm, hd);
+    const float coef = unit_bwd_coef(nrm_raw, hd);
     const float inv = 1.f / nrm;
     float ad = 0.f;
     for (int j = tid; j < a.D; j += blockDim.x) {
@@ -497,7 +501,22 @@ __global__ __launch_bounds__(256) void cell_bwd_kernel(const CellBwdArgs g) {
       d = warp_sum(d);
       if (lane == 0) {
         const float gp = d + a.E[row] * gs;
-        g.GE[row] = pk * (gs + gp - cm);
+        g.GE[row] = a.no_norm ? gp : pk * (gs + (gp - cm));
+      }
+    }
+    if (a.no_norm) {
+      // Without normalisation the chart grows geometrically and the softmax saturates: cm must cancel gp of the chosen
+      // split exactly, so it is re-summed from the very gp values it is subtracted from (as autograd does).
+      __syncthreads();
+      float cm2 = 0.f;
+      for (int k = 0; k < a.N; ++k) {
+        const int64_t row = row0 + (int64_t)k * a.sk;
+        cm2 = fmaf(a.Pr[row], g.GE[row], cm2);
+      }
+      __syncthreads();
+      for (int k = tid; k < a.N; k += blockDim.x) {
+        const int64_t row = row0 + (int64_t)k * a.sk;
+        g.GE[row] = a.Pr[row] * (gs + (g.GE[row] - cm2));
       }
     }
     if (want_sum) {   // warps -> block: the cell's sum of GY rows
@@ -584,13 +603,14 @@ __global__ void outside_root_bwd_kernel(int B, int D, int64_t C, const float* __
   pdl_prologue();
   __shared__ float red[64];
   const int b = blockIdx.x;
-  const float nrm = nrm_out[(int64_t)b * C + C - 1];
+  const float nrm_raw = nrm_out[(int64_t)b * C + C - 1];
+  const float nrm = fabsf(nrm_raw);
   const float* gh = Gh_out + ((int64_t)b * C + C - 1) * D;
   const float* h = oh + ((int64_t)b * C + C - 1) * D;
   float d = 0.f;
   for (int j = threadIdx.x; j < D; j += blockDim.x) d = fmaf(h[j], gh[j], d);
   d = block_sum(d, red);
-  const float coef = unit_bwd_coef(nrm, d);
+  const float coef = unit_bwd_coef(nrm_raw, d);
   for (int j = threadIdx.x; j < D; j += blockDim.x) atomicAdd(g_root + j, (gh[j] - h[j] * coef) / nrm);
 }
 

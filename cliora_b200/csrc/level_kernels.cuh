@@ -154,6 +154,7 @@ struct LevelFwdArgs {
   float* q; float* nrm; float* nrm2; float* att;      // saved per cell (q, nrm2, att: R > 0 only)
   const float* obj; const uint8_t* keep;
   int max_sent;                                       // CLIORA: sentences a tile may span (their region slices are staged in smem)
+  int no_norm;                                        // --normalize none: norms are the identity, saved norms hold -1
   int exp_flags;                                      // timing experiments only (results become wrong): 1 no proxy fence, 2 no Z stores, 4 no transform
   long long* dbg;                                     // optional in-kernel timeline [ctas][32] (clock64 stamps), or null
 };
@@ -311,7 +312,9 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
     if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[56 + (kb - 4) * 2] = clock_now();
     if (kb >= kAStages) {
       cp_async_wait<kAStages - 1>();                      // this thread's copies of k-block kb - 4 landed long ago
+      if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[64 + (kb - 4) * 4] = clock_now();
       flush(kb - kAStages);
+      if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[65 + (kb - 4) * 4] = clock_now();
     }
     const int kcol = kb * 32 + c * 4;
     const uint32_t sA = smem_base + (uint32_t)(stage * 2 * kABytes) + soff0;
@@ -321,6 +324,7 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
       cp_async16_zfill(sA + i * 2048, base_a + oa[i] + kb * 32, nbytes);
       cp_async16_zfill(sA + kABytes + i * 2048, base_b + ob[i] + kb * 32, nbytes);
     }
+    if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[66 + (kb - 4) * 4] = clock_now();
     cp_async_arrive_noinc(&raw_full[stage]);              // arrives once this thread's copies above have landed
     cp_async_commit();
     if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[57 + (kb - 4) * 2] = clock_now();
@@ -406,7 +410,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   uint8_t* ringB = smem + kAStages * a_stage_bytes;
   const int cells_here = min(a.G, a.cells - tile * a.G);
   const int nc = a.nc, ncols = a.ncols, N = a.N;
-  long long* dbg_row = a.dbg ? a.dbg + ((int64_t)blockIdx.y * a.nc + rank) * 64 : nullptr;
+  long long* dbg_row = a.dbg ? a.dbg + ((int64_t)blockIdx.y * a.nc + rank) * 128 : nullptr;
 #define LV_STAMP(slot) do { if (dbg_row != nullptr && tid == 128) dbg_row[slot] = clock_now(); } while (0)
   if (dbg_row && tid == 0) { dbg_row[0] = clock_now(); dbg_row[30] = global_ns(); }
 
@@ -878,9 +882,9 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     cell_of(a, tile * a.G + tid, cb, cp, ccell);
     float tot = 0.f;
     for (int cc = 0; cc < nc; ++cc) tot += s_xs[cc * 128 + tid];
-    const float nrm = fmaxf(sqrtf(tot), kTiny);
+    const float nrm = a.no_norm ? 1.f : fmaxf(sqrtf(tot), kTiny);
     s_nrm[tid] = nrm;
-    if (rank == 0) a.nrm[ccell] = nrm;
+    if (rank == 0) a.nrm[ccell] = a.no_norm ? -1.f : nrm;
   }
   __syncthreads();
   for (int item = tid; item < cells_here * nc4; item += kThreads) {
@@ -978,9 +982,9 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       cell_of(a, tile * a.G + tid, cb, cp, ccell);
       float tot = 0.f;
       for (int cc = 0; cc < nc; ++cc) tot += s_xs2[cc * 128 + tid];
-      const float nrm2 = fmaxf(sqrtf(tot), kTiny);
+      const float nrm2 = a.no_norm ? 1.f : fmaxf(sqrtf(tot), kTiny);
       s_nrm2[tid] = nrm2;
-      if (rank == 0) a.nrm2[ccell] = nrm2;
+      if (rank == 0) a.nrm2[ccell] = a.no_norm ? -1.f : nrm2;
     }
     __syncthreads();
     for (int item = tid; item < cells_here * nc4; item += kThreads) {
@@ -1113,14 +1117,15 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
       cell_of(a, tile * a.G + gi, cb, cp, cell);
       const float* gh = g.cellGh + cell * D;
       const float* hv = g.cellH + cell * D;
-      const float nrm = g.cellNrm[cell];
+      const float nrm_raw = g.cellNrm[cell];
+      const float nrm = fabsf(nrm_raw);
       float hd = 0.f;
       for (int j = lane * 4; j < D; j += 128) {
         const float4 x = ldcg4(gh + j), h4 = ldcg4(hv + j);
         hd = fmaf(h4.x, x.x, hd); hd = fmaf(h4.y, x.y, hd); hd = fmaf(h4.z, x.z, hd); hd = fmaf(h4.w, x.w, hd);
       }
       hd = warp_sum(hd);
-      const float coef = unit_bwd_coef(nrm, hd), inv = 1.f / nrm;
+      const float coef = unit_bwd_coef(nrm_raw, hd), inv = 1.f / nrm;
       float ad = 0.f;
       for (int j = lane * 4; j < D; j += 128) {
         const float4 x = ldcg4(gh + j), h4 = ldcg4(hv + j);
@@ -1266,9 +1271,21 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
       const int cell = s_cell[tid];
       const float gs = g.Gs[cell];
       const float gp = s_d[tid] + s_d[128 + tid] + g.E[m] * gs;
-      ge = s_p[tid] * (gs + gp - g.CM[cell]);
+      ge = s_p[tid] * (gs + (gp - g.CM[cell]));   // the difference first: gs is tiny next to gp when the chart is not normalised
+      if (a.no_norm) ge = gp;
     }
     s_ge[tid] = ge;
+    if (a.no_norm) {
+      // Without normalisation the chart grows geometrically and the softmax saturates: cm must cancel gp of the chosen
+      // split exactly, so it is re-summed from the very gp values it is subtracted from (as autograd does).
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int base = (tid / a.N) * a.N;
+      float cm2 = 0.f;
+      if (m >= 0)
+        for (int kk = 0; kk < a.N; ++kk) cm2 = fmaf(s_p[base + kk], s_ge[base + kk], cm2);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      s_ge[tid] = m >= 0 ? s_p[tid] * (g.Gs[s_cell[tid]] + (ge - cm2)) : 0.f;
+    }
   }
   if (warp >= 2) {
     // GZ = acc * [z > 0]; scattered into the projection-gradient rows of the two cells the split read

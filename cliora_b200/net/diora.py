@@ -40,12 +40,12 @@ class DioraBase(nn.Module):
     def __init__(self, size, word_mat=None, cate_mat=None, outside=True, normalize='unit', compress=False,
                  share=True):
         super().__init__()
-        if normalize != 'unit':
-            raise NotImplementedError('cliora_b200 implements normalize="unit" (the reference default, '
-                                      'scripts/train.py) only; got %r' % (normalize,))
+        if normalize not in ('unit', 'none'):      # scripts/train.py:341: choices=('none', 'unit')
+            raise ValueError("normalize must be 'unit' or 'none'; got %r" % (normalize,))
         if compress:
             raise NotImplementedError('compress=True is unreachable in the reference (trainer.py:552)')
         self.size = size
+        self.normalize = normalize
         self.share = share
         self.outside = outside
         self.inside_normalize_func = NormalizeFunc(normalize)
@@ -181,6 +181,8 @@ class DioraBase(nn.Module):
             raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
         fused = (B <= 32) if self.fused == 'auto' else bool(self.fused)
         flags = {'fp32': 0, 'tf32': 2, 'bf16': 8}[self.precision] | (0 if fused else 4) | ((min(chains, 15) & 15) << 8)
+        if self.normalize == 'none':
+            flags |= 16        # CLIORA_FLAG_NO_NORMALIZE
         outs = ChartFunction.apply(run, bool(self.share), bool(self.outside), chains, flags, x_span, obj, keep,
                                    *self._weight_list())
         self._run = run

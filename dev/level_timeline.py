@@ -45,7 +45,7 @@ def main():
     x = torch.randn(B, n, D).cuda()
     obj = 0.05 * torch.randn(B, max(R, 1), D).cuda()
     L = _lib.lib()
-    dbg = torch.zeros(4096, 64, dtype=torch.int64, device='cuda')
+    dbg = torch.zeros(4096, 128, dtype=torch.int64, device='cuda')
     for it in range(3):
         if it == 2:
             L.cliora_debug_ptr(0, dbg.data_ptr())
@@ -76,7 +76,8 @@ def main():
         for i in range(4):
             print('  xform kb=%d: top %.2f raw_full %.2f math %.2f emptyA %.2f st_done %.2f end %.2f' % tuple([4 + i] + [us(32 + 6 * i + q) for q in range(6)]))
         for i in range(4):
-            print('  copy kb=%d: raw_empty %.2f issued %.2f' % (4 + i, us(56 + 2 * i), us(57 + 2 * i)))
+            print('  copy kb=%d: raw_empty %.2f waited %.2f flushed %.2f copies %.2f issued %.2f' % (
+                4 + i, us(56 + 2 * i), us(64 + 4 * i), us(65 + 4 * i), us(66 + 4 * i), us(57 + 2 * i)))
         for i in range(4):
             print('  mma kb=%d: full %.2f issued %.2f' % (3 + i, us(48 + 2 * i), us(49 + 2 * i)))
 

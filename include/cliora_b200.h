@@ -100,6 +100,9 @@ typedef struct cliora_dims {
 /* Reduced-precision mode: the tensor-core GEMMs issue one TF32 pass instead of the fp32-accurate three.
  * Stated tolerance 1e-2 of max on chart vectors (measured ~3e-3); CKY trees are NOT guaranteed identical. */
 #define CLIORA_FLAG_TF32_1PASS 2
+/* --normalize none (cliora/net/utils.py:17-27): every unit-normalisation of the chart (leaves, cells, the CLIORA
+ * attention residual, the outside root) becomes the identity.  The saved norms hold the sentinel -1. */
+#define CLIORA_FLAG_NO_NORMALIZE 16
 /* bf16-GEMM mode: the compose GEMMs of the fused level kernels take bf16 operands (fp32 accumulate, kind::f16 UMMAs);
  * every other tensor-core GEMM runs single-pass TF32.  Stated tolerance 3e-2 of max on chart vectors, 1e-2 on scores
  * (SURVEY.md section 7); CKY trees are NOT guaranteed identical.  Implies the fused level kernels. */

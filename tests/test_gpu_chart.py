@@ -116,7 +116,7 @@ def test_alignment_tensors_vs_oracle_odd_shapes(B, n, D, R, train):
     assert rel_err(m.atten_score, O.atten_score(vg)) < TOL
 
 
-def _oracle_run(dt, B, n, D, R, share, seed=8):
+def _oracle_run(dt, B, n, D, R, share, seed=8, mode='unit'):
     from oracle import cliora_oracle as O
     P0 = O.init_params(D, share=share, seed=7)
     g = torch.Generator().manual_seed(seed)
@@ -133,7 +133,7 @@ def _oracle_run(dt, B, n, D, R, share, seed=8):
                 P['outside_' + k[len('inside_'):]] = P[k]
     xo = x.to(dt).requires_grad_()
     oo = obj.to(dt).requires_grad_() if R else None
-    out = O.chart_forward(P, xo, oo, keep)
+    out = O.chart_forward(P, xo, oo, keep, mode=mode)
     sum((getattr(out, k) * ct[k].to(dt)).sum() for k in ct).backward()
     res = {k: getattr(out, k).detach() for k in ct}
     res['grad_x'] = xo.grad
@@ -338,3 +338,40 @@ def test_unfused_kernel_chain_stays_parity_green(B, n, D, R, share):
         test_chart_vs_oracle_live(B, n, D, R, share)
     finally:
         diora_mod.DioraBase.__init__ = saved
+
+
+@pytest.mark.parametrize('B,n,D,R,share,fused', [(3, 5, 64, 4, True, True), (2, 4, 400, 0, False, True),
+                                                 (3, 5, 64, 4, True, False), (4, 6, 132, 0, True, False)])
+def test_normalize_none_vs_oracle(B, n, D, R, share, fused):
+    """--normalize none (scripts/train.py:341, cliora/net/utils.py:17-27): every unit-normalisation is the identity.
+    Forward and gradients against the float64 oracle run in the same mode, on both kernel paths."""
+    if R:
+        from cliora_b200.net.cliora import DioraMLP
+    else:
+        from cliora_b200.net.diora import DioraMLP
+    P0, x, obj, keep, ct, ref = _oracle_run(torch.float64, B, n, D, R, share, mode='none')
+    ref.pop('pre')
+    m = DioraMLP(D, share=share, normalize='none').cuda()
+    m.fused = fused
+    _fill(m, P0)
+    xc = x.cuda().requires_grad_()
+    oc = obj.cuda().requires_grad_() if R else None
+    m.train()
+    if R:
+        m.set_dropout_mask(keep.cuda())
+        m(xc, xc, oc, oc)
+    else:
+        m(xc, xc)
+    for k in ct:
+        assert rel_err(getattr(m, k), ref[k]) < TOL, k
+    sum((getattr(m, k) * ct[k].cuda()).sum() for k in ct).backward()
+    # without normalisation the chart grows geometrically with the level (1e6 ... 1e10 here) and deep gradients lose
+    # digits in float32 on ANY implementation: the budget is the float32 oracle's own distance from float64
+    ref32 = _oracle_run(torch.float32, B, n, D, R, share, mode='none')[-1]
+
+    def tol(key):
+        return max(5e-4, 3 * rel_err(ref32[key], ref[key]))
+    assert rel_err(xc.grad, ref['grad_x']) < tol('grad_x')
+    for k, v in _grads(m).items():
+        if not (share and k.startswith('outside_')) and ref.get('grad:' + k) is not None:
+            assert rel_err(v, ref['grad:' + k]) < tol('grad:' + k), k
