@@ -46,6 +46,8 @@ constexpr int kProdWarps = 8;
 constexpr int kProdWarp0 = 6;
 constexpr int kCopyWarp0 = kProdWarp0 + kProdWarps;      // warps 14-17: cp.async gathers of the raw operand rows
 constexpr int kCopyWarps = 4;
+constexpr int kCopyRowsPerPass = kCopyWarps * 4;         // tile rows one pass of the copy threads covers (8 lanes per row)
+constexpr int kCopyIters = kRows / kCopyRowsPerPass;      // copies per thread, operand and k-block
 constexpr int kThreads = (kCopyWarp0 + kCopyWarps) * 32;   // 576
 constexpr int kMaxCluster = 8;
 constexpr int kMaxUmmaN = 112;
@@ -272,23 +274,23 @@ CL_D void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <class OffFn, class StoreFn>
+template <class OffFn, class StoreFn, class EndFn>
 CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int num_kb, int D, const float* base_a,
-                     const float* base_b, OffFn offs, int store_turn0, int store_every, StoreFn store,
+                     const float* base_b, OffFn offs, int store_turn0, int store_every, StoreFn store, EndFn store_end,
                      long long* dbg = nullptr) {
-  const int gt = threadIdx.x - kCopyWarp0 * 32;          // 0..127
+  const int gt = threadIdx.x - kCopyWarp0 * 32;          // 0 .. 32 kCopyWarps - 1
   const int c = gt & 7, rbase = gt >> 3;
-  uint32_t oa[8], ob[8];
+  uint32_t oa[kCopyIters], ob[kCopyIters];
   uint32_t okmask = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < kCopyIters; ++i) {
     bool ok;
-    offs(rbase + 16 * i, oa[i], ob[i], ok);
+    offs(rbase + kCopyRowsPerPass * i, oa[i], ob[i], ok);
     oa[i] += c * 4;
     ob[i] += c * 4;
     okmask |= ok ? (1u << i) : 0u;
   }
-  const uint32_t soff0 = (uint32_t)(rbase * 128 + ((c ^ (rbase & 7)) << 4));     // + 2048 i   (16 rows further)
+  const uint32_t soff0 = (uint32_t)(rbase * 128 + ((c ^ (rbase & 7)) << 4));     // + 128 kCopyRowsPerPass i
   const uint32_t smem_base = smem_u32(smem);
   // The pair of k-block kp (every store_every-th one is this CTA's to stream out) is written from the raw stage by
   // the thread that copied it, right before the stage is refilled -- coalesced (eight lanes per 128-byte row slice).
@@ -296,22 +298,24 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
     if (store_every <= 0 || (kp % store_every) != store_turn0) return;
     const uint8_t* sA = smem + (kp % kAStages) * 2 * kABytes + soff0;
     const int kc = kp * 32 + c * 4;
-    if (kc >= D) return;
+    const bool live = kc < D;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if ((okmask >> i) & 1u) {
-        const float4 xa = *reinterpret_cast<const float4*>(sA + i * 2048);
-        const float4 xb = *reinterpret_cast<const float4*>(sA + kABytes + i * 2048);
-        store(rbase + 16 * i, kc, xa, xb);
+    for (int i = 0; i < kCopyIters; ++i) {
+      if (live && ((okmask >> i) & 1u)) {
+        const float4 xa = *reinterpret_cast<const float4*>(sA + i * (128 * kCopyRowsPerPass));
+        const float4 xb = *reinterpret_cast<const float4*>(sA + kABytes + i * (128 * kCopyRowsPerPass));
+        store(rbase + kCopyRowsPerPass * i, kc, xa, xb);
       }
     }
+    store_end(kc, live);          // reached by every lane of the warp
   };
   for (int kb = 0; kb < num_kb; ++kb) {
     const int stage = kb % kAStages;
     mbar_wait(&raw_empty[stage], ((kb / kAStages) & 1) ^ 1);
     if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[56 + (kb - 4) * 2] = clock_now();
     if (kb >= kAStages) {
-      cp_async_wait<kAStages - 1>();                      // this thread's copies of k-block kb - 4 landed long ago
+      // raw_empty[stage] implies raw_full[stage] of k-block kb - 4 completed, i.e. every copy of it (this thread's
+      // included) has landed and is visible: no cp.async.wait_group needed before reading the stage back
       if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[64 + (kb - 4) * 4] = clock_now();
       flush(kb - kAStages);
       if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[65 + (kb - 4) * 4] = clock_now();
@@ -319,10 +323,10 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
     const int kcol = kb * 32 + c * 4;
     const uint32_t sA = smem_base + (uint32_t)(stage * 2 * kABytes) + soff0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kCopyIters; ++i) {
       const uint32_t nbytes = (((okmask >> i) & 1u) && kcol < D) ? 16u : 0u;
-      cp_async16_zfill(sA + i * 2048, base_a + oa[i] + kb * 32, nbytes);
-      cp_async16_zfill(sA + kABytes + i * 2048, base_b + ob[i] + kb * 32, nbytes);
+      cp_async16_zfill(sA + i * (128 * kCopyRowsPerPass), base_a + oa[i] + kb * 32, nbytes);
+      cp_async16_zfill(sA + kABytes + i * (128 * kCopyRowsPerPass), base_b + ob[i] + kb * 32, nbytes);
     }
     if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[66 + (kb - 4) * 4] = clock_now();
     cp_async_arrive_noinc(&raw_full[stage]);              // arrives once this thread's copies above have landed
@@ -556,10 +560,10 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   } else if (warp >= kCopyWarp0) {
     // ------------------------------------------------------------ raw operand rows: cp.async gathers (TMEM variant)
     if (A_TMEM) {
-      uint32_t zo[8];                              // element offset of the Z row of this thread's i-th tile row
+      uint32_t zo[kCopyIters];                     // element offset of the Z row of this thread's i-th tile row
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        zo[i] = (uint32_t)(decode_row(a, tile, cells_here, ((tid - kCopyWarp0 * 32) >> 3) + 16 * i).m * D);
+      for (int i = 0; i < kCopyIters; ++i)
+        zo[i] = (uint32_t)(decode_row(a, tile, cells_here, ((tid - kCopyWarp0 * 32) >> 3) + kCopyRowsPerPass * i).m * D);
       copy_a_raw(
           smem, raw_full, raw_empty, num_kb, D, a.P1, a.P2,
           [&](int r, uint32_t& oa, uint32_t& ob, bool& ok) {
@@ -574,11 +578,11 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
             float4 hi, lo;
             split_trunc(fmaxf(xa.x + xb.x, 0.f), hi.x, lo.x); split_trunc(fmaxf(xa.y + xb.y, 0.f), hi.y, lo.y);
             split_trunc(fmaxf(xa.z + xb.z, 0.f), hi.z, lo.z); split_trunc(fmaxf(xa.w + xb.w, 0.f), hi.w, lo.w);
-            float* dst = a.Z + zo[r >> 4] + kc;
+            float* dst = a.Z + zo[r / kCopyRowsPerPass] + kc;
             st4(dst, hi);
             st4(dst + a.z_lo_off, lo);
           },
-          dbg_row);
+          [](int, bool) {}, dbg_row);
     }
   } else if (warp >= kProdWarp0 && A_TMEM) {
     // ------------------------------------------------------------ A operand -> tensor memory (see transform_a_tmem)
@@ -1042,7 +1046,9 @@ struct LevelBwdArgs {
   float* GAw; float* CMw;                // writable aliases of GA / CM
 };
 
-constexpr int kBwdExtraBytes = 256 + 128 * 8 + 4 * (128 * 5 + 128);   // barriers, row ids, p/cell/d0/d1/ge, b-unused
+constexpr int kBwdDb2Floats = kMaxCluster * kMaxUmmaN;   // D <= 896
+// barriers, row ids, p/cell/d0/d1/ge, chart rows of first/second, ReLU bit masks [128][4], db2 partial sums [D]
+constexpr int kBwdExtraBytes = 256 + 128 * 8 + 4 * (128 * 5 + 128) + 4 * 256 + 4 * 512 + 4 * kBwdDb2Floats;
 
 template <int DUMMY>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -1064,6 +1070,9 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   uint8_t* ringB = smem + kAStages * a_stage_bytes;
   const int cells_here = min(a.G, a.cells - tile * a.G);
   const int nc = a.nc, ncols = a.ncols;
+  long long* dbg_row = a.dbg ? a.dbg + ((int64_t)blockIdx.y * a.nc + rank) * 128 : nullptr;
+#define LB_STAMP(slot) do { if (dbg_row != nullptr && tid == 128) dbg_row[slot] = clock_now(); } while (0)
+  if (dbg_row && tid == 0) { dbg_row[0] = clock_now(); dbg_row[30] = global_ns(); }
 
   uint8_t* ex = smem + ring_bytes(a.n_umma);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(ex);
@@ -1079,6 +1088,10 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   int* s_cell = reinterpret_cast<int*>(s_p + 128);                   // [128] chart cell (b*C + c) of the row
   float* s_d = reinterpret_cast<float*>(s_cell + 128);               // [2][128] y . ga, one half of the columns each
   float* s_ge = s_d + 256;                                           // [128]
+  int* s_g1 = reinterpret_cast<int*>(s_ge + 256);                    // [128] chart row (b*C + c) of `first`
+  int* s_g2 = s_g1 + 128;                                            // [128] chart row of `second`
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_g2 + 128);        // [128][4] ReLU bits of this CTA's columns of z
+  float* s_db2 = reinterpret_cast<float*>(s_mask + 512);             // [D] column sums of the GY k-blocks this CTA streams
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmW);
   if (warp == 1) {
@@ -1107,7 +1120,10 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     s_m[tid] = ri.ok ? (long long)ri.m : -1ll;
     s_p[tid] = ri.ok ? g.Pr[ri.m] : 0.f;
     s_cell[tid] = (int)ri.cell;
+    s_g1[tid] = (int)ri.g1;
+    s_g2[tid] = (int)ri.g2;
   }
+  for (int j = tid; j < D; j += kThreads) s_db2[j] = 0.f;
   if (g.cellGh != nullptr) {
     // per-cell normalise backward (text cells): ga = (g - h (h.g)) / nrm on the live branch, g / eps on the clamped one;
     // cm = sum_m p_m gp_m = nrm (h . ga) + s gs.  Warp per cell; every column-slice CTA computes the same values.
@@ -1143,6 +1159,7 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  LB_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1189,6 +1206,8 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
         mbar_wait(&fullB[sb], (kb / nbs) & 1);
         mbar_wait(&fullA[sA_i], (kb / kAStages) & 1);
         tcgen05_fence_after();
+        if (dbg_row && kb == 0) dbg_row[20] = clock_now();
+        if (dbg_row && kb == num_kb - 1) dbg_row[21] = clock_now();
         const uint32_t sbb = smem_u32(ringB + sb * b_stage_bytes);
         const uint64_t b_hi = umma_desc_k_sw128(sbb), b_lo = umma_desc_k_sw128(sbb + b_bytes);
         const uint32_t ta_hi = tmem_base + kTmemA0 + (uint32_t)(sA_i * 64), ta_lo = ta_hi + 32;
@@ -1209,6 +1228,7 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
       umma_commit(tmem_full);
     }
   } else if (warp >= kCopyWarp0) {
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     copy_a_raw(
         smem, raw_full, raw_empty, num_kb, D, g.Y, g.GA,
         [&](int r, uint32_t& oa, uint32_t& ob, bool& ok) {
@@ -1221,12 +1241,29 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
         rank, g.GYp != nullptr ? nc : 0,
         [&](int r, int kc, const float4& y, const float4& ga) {
           const float pr = s_p[r];
+          const float4 o = make_float4(y.x > 0.f ? pr * ga.x : 0.f, y.y > 0.f ? pr * ga.y : 0.f,
+                                       y.z > 0.f ? pr * ga.z : 0.f, y.w > 0.f ? pr * ga.w : 0.f);
+          csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
           float4 hi, lo;
-          split_trunc(y.x > 0.f ? pr * ga.x : 0.f, hi.x, lo.x); split_trunc(y.y > 0.f ? pr * ga.y : 0.f, hi.y, lo.y);
-          split_trunc(y.z > 0.f ? pr * ga.z : 0.f, hi.z, lo.z); split_trunc(y.w > 0.f ? pr * ga.w : 0.f, hi.w, lo.w);
+          split_trunc(o.x, hi.x, lo.x); split_trunc(o.y, hi.y, lo.y);
+          split_trunc(o.z, hi.z, lo.z); split_trunc(o.w, hi.w, lo.w);
           float* dst = g.GYp + s_m[r] * D + kc;
           st4(dst, hi);
           st4(dst + g.gy_lo_off, lo);
+        },
+        // db2 += column sums of GY: this thread's rows of the four columns it streamed, combined in shared memory
+        [&](int kc, bool live) {
+          // the four lanes of a warp that share a chunk (lane, lane ^ 8, lane ^ 16, lane ^ 24) are summed first
+#pragma unroll
+          for (int off = 8; off < 32; off <<= 1) {
+            csum.x += __shfl_xor_sync(0xffffffffu, csum.x, off); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, off);
+            csum.z += __shfl_xor_sync(0xffffffffu, csum.z, off); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, off);
+          }
+          if (live && (threadIdx.x & 31) < 8) {
+            atomicAdd(s_db2 + kc, csum.x); atomicAdd(s_db2 + kc + 1, csum.y);
+            atomicAdd(s_db2 + kc + 2, csum.z); atomicAdd(s_db2 + kc + 3, csum.w);
+          }
+          csum = make_float4(0.f, 0.f, 0.f, 0.f);
         });
   } else if (warp >= kProdWarp0) {
     // ---- A operand: gy = p * ga * [y > 0] -> tensor memory (see transform_a_tmem); d = y . ga on the side
@@ -1244,25 +1281,59 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
         });
     s_d[half * 128 + row] = dpart;
   } else {
-    // ---- warps 2-5 while the MMAs run: db2 += column sums of GY over this tile, for this CTA's columns
-    const int j = tid - 64;            // 0..127
-    if (j < ncols && n0 + j < D && g.db2 != nullptr) {
-      float acc = 0.f;
-      const int rows_here = cells_here * a.N;
-#pragma unroll 4
-      for (int r = 0; r < rows_here; ++r) {
-        const float y = __ldcg(g.Y + s_m[r] * D + n0 + j);
-        const float ga = __ldg(g.GA + (int64_t)s_cell[r] * D + n0 + j);
-        acc += y > 0.f ? s_p[r] * ga : 0.f;
+    // ---- warps 2-5 while the MMAs run (thread = tile row): the ReLU mask of this CTA's columns of the row's z,
+    // four bits per 16-byte chunk, so that the epilogue neither waits on global memory nor re-reads Z
+    const int r = tid - 64;            // 0..127
+    const long long m = s_m[r];
+    const int nch = ncols >> 2;
+    uint32_t mk[4] = {0u, 0u, 0u, 0u};
+    if (m >= 0) {
+      const float* zrow = g.Zhi + m * D + n0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q * 8 < nch) {
+          float4 z[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = q * 8 + u;
+            z[u] = (j < nch && n0 + 4 * j < D) ? ldcg4(zrow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t b = (z[u].x > 0.f ? 1u : 0u) | (z[u].y > 0.f ? 2u : 0u) | (z[u].z > 0.f ? 4u : 0u) |
+                               (z[u].w > 0.f ? 8u : 0u);
+            mk[q] |= b << (4 * u);
+          }
+        }
       }
-      atomicAdd(g.db2 + n0 + j, acc);
     }
+    *reinterpret_cast<uint4*>(s_mask + r * 4) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+    LB_STAMP(2);
   }
 
   // ================================================================ every warp: epilogue + scatter
   mbar_wait(tmem_full, 0);
   tcgen05_fence_after();
   __syncthreads();
+  LB_STAMP(3);
+  // The operand rings are free now: this CTA's slices of h[first] and V[second] (score path) are copied into them
+  // asynchronously while the accumulators are drained, masked and transposed (thread = row -> row-major in shared
+  // memory), so that the scatter below issues coalesced reductions (one row slice per warp instruction) and never waits
+  // on a global load.
+  const int nch = ncols >> 2;
+  const int pitch = (nch & 1) ? ncols : ncols + 4;           // pitch / 4 odd: conflict-free 16-byte row accesses
+  float* s_gz = reinterpret_cast<float*>(smem);              // [128][pitch] masked GZ
+  float* s_h = s_gz + kRows * pitch;                         // [128][pitch] h[first] slice
+  float* s_v = s_h + kRows * pitch;                          // [128][pitch] V[second] slice
+  const int rows_here = cells_here * a.N;
+  for (int idx = tid; idx < rows_here * nch; idx += kThreads) {
+    const int r = idx / nch, ch = idx - r * nch;
+    if (n0 + ch * 4 < D) {
+      cp_async16(s_h + r * pitch + ch * 4, g.h1 + (int64_t)s_g1[r] * D + n0 + ch * 4);
+      cp_async16(s_v + r * pitch + ch * 4, g.P2 + (int64_t)s_g2[r] * g.ld2 + g.off_v2 + n0 + ch * 4);
+    }
+  }
+  cp_async_commit();
   if (tid < 128) {
     // ge = p (gs + gp - cm), gp = y . ga + e gs      (softmax-weighted-sum backward)
     const long long m = s_m[tid];
@@ -1288,13 +1359,11 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     }
   }
   if (warp >= 2) {
-    // GZ = acc * [z > 0]; scattered into the projection-gradient rows of the two cells the split read
+    // GZ = acc * [z > 0] -> shared memory, row-major
     constexpr int kSub = (kThreads / 32 - 2) / 4;
     const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
-    const RowInfo ri = decode_row(a, tile, cells_here, r);
-    const float* zrow = ri.ok ? g.Zhi + ri.m * D + n0 : nullptr;
-    float* d1 = g.GP1 + ri.g1 * g.ld1 + g.off_a1 + n0;
-    float* d2 = g.GP2 + ri.g2 * g.ld2 + g.off_a2 + n0;
+    const uint4 mk4 = *reinterpret_cast<const uint4*>(s_mask + r * 4);
+    const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
 #pragma unroll 1
     for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
@@ -1305,52 +1374,59 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += x[i];
       }
-      if (ri.ok) {
+      const uint32_t word = (c0 >> 5) == 0 ? mk[0] : (c0 >> 5) == 1 ? mk[1] : (c0 >> 5) == 2 ? mk[2] : mk[3];
+      const uint32_t bits16 = (word >> (c0 & 31)) & 0xffffu;      // c0 is a multiple of 16
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const int col = c0 + j;
-          if (col < ncols && n0 + col < D) {
-            const float4 z = ldcg4(zrow + col);
-            const float4 o = make_float4(z.x > 0.f ? v[j] : 0.f, z.y > 0.f ? v[j + 1] : 0.f, z.z > 0.f ? v[j + 2] : 0.f,
-                                         z.w > 0.f ? v[j + 3] : 0.f);
-            red_add4(d1 + col, o);
-            red_add4(d2 + col, o);
-          }
+      for (int j = 0; j < 16; j += 4) {
+        const int col = c0 + j;
+        if (col < ncols) {
+          const uint32_t b = bits16 >> j;
+          st4(s_gz + r * pitch + col, make_float4((b & 1u) ? v[j] : 0.f, (b & 2u) ? v[j + 1] : 0.f,
+                                                  (b & 4u) ? v[j + 2] : 0.f, (b & 8u) ? v[j + 3] : 0.f));
         }
       }
     }
   }
+  cp_async_wait_all();
   tcgen05_fence_before();
   __syncthreads();
-  {
-    // score path: Gh[first] += ge V[second], GP[second].V += ge h[first] over this CTA's columns; eight lanes per row
-    const int rr = tid >> 3, c = tid & 7;          // 56 rows per pass
-    const int nch = ncols >> 2;
-    for (int r = rr; r < cells_here * a.N; r += kThreads / 8) {
-      const RowInfo ri = decode_row(a, tile, cells_here, r);
-      const float ge = s_ge[r];
-      const float* hp = g.h1 + ri.g1 * D + n0;
-      const float* vp = g.P2 + ri.g2 * g.ld2 + g.off_v2 + n0;
-      float* gh = g.Gh1 + ri.g1 * D + n0;
-      float* gv = g.GP2 + ri.g2 * g.ld2 + g.off_v2 + n0;
-      for (int ch = c; ch < nch; ch += 8) {
-        if (n0 + ch * 4 < D) {
-          const float4 hv = ldcg4(hp + ch * 4), vv = ldcg4(vp + ch * 4);
-          red_add4(gh + ch * 4, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
-          red_add4(gv + ch * 4, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
-        }
-      }
-      if (c == 0 && rank == 0) {
-        atomicAdd(g.Gs1 + ri.g1, ge);
-        atomicAdd(g.Gs2 + ri.g2, ge);
+  LB_STAMP(4);
+  // scatter (red.global.add, as split_scatter did): GP[first].A += GZ, GP[second].A += GZ, Gh[first] += ge V[second],
+  // GP[second].V += ge h[first], Gs[first] += ge, Gs[second] += ge.  Warp per row, lanes over the 16-byte chunks.
+  for (int r = warp; r < rows_here; r += kThreads / 32) {
+    const int64_t g1 = s_g1[r], g2 = s_g2[r];
+    const float ge = s_ge[r];
+    float* d1 = g.GP1 + g1 * g.ld1 + g.off_a1 + n0;
+    float* d2 = g.GP2 + g2 * g.ld2 + g.off_a2 + n0;
+    float* gh = g.Gh1 + g1 * D + n0;
+    float* gv = g.GP2 + g2 * g.ld2 + g.off_v2 + n0;
+    for (int ch = lane; ch < nch; ch += 32) {
+      if (n0 + ch * 4 < D) {
+        const float4 gz = ld4(s_gz + r * pitch + ch * 4);
+        const float4 hv = ld4(s_h + r * pitch + ch * 4), vv = ld4(s_v + r * pitch + ch * 4);
+        red_add4(d1 + ch * 4, gz);
+        red_add4(d2 + ch * 4, gz);
+        red_add4(gh + ch * 4, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
+        red_add4(gv + ch * 4, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
       }
     }
+    if (lane == 0 && rank == 0) {
+      atomicAdd(g.Gs1 + g1, ge);
+      atomicAdd(g.Gs2 + g2, ge);
+    }
   }
+  // db2 += the column sums of the GY k-blocks this CTA streamed out
+  if (g.db2 != nullptr && g.GYp != nullptr)
+    for (int j = tid; j < D; j += kThreads)
+      if (((j >> 5) % nc) == rank) atomicAdd(g.db2 + j, s_db2[j]);
   __syncthreads();
+  LB_STAMP(5);
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  if (dbg_row && tid == 0) { dbg_row[18] = clock_now(); dbg_row[31] = global_ns(); }
+#undef LB_STAMP
 }
 
 // ---------------------------------------------------------------- host side
@@ -1481,7 +1557,9 @@ inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a_in, const flo
 
 inline size_t level_bwd_smem(int n_umma) { return (size_t)ring_bytes(n_umma) + kBwdExtraBytes; }
 
-inline int launch_level_bwd(cudaStream_t st, const LevelBwdArgs& g, const float* W2Tpair, const char* tag) {
+inline int launch_level_bwd(cudaStream_t st, const LevelBwdArgs& g_in, const float* W2Tpair, const char* tag) {
+  LevelBwdArgs g = g_in;
+  g.geo.dbg = (g_level_dbg != nullptr && g_debug[8] == g.geo.level + 1 && g_debug[9] == 2 + g.geo.outside) ? g_level_dbg : nullptr;
   const LevelFwdArgs& a = g.geo;
   CUtensorMap tmW;
   if (a.mode == 3) CL_TRY(make_bf16_map(&tmW, W2Tpair, a.D, a.D, a.n_umma));

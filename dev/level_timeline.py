@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--length', type=int, default=20)
     ap.add_argument('--text', action='store_true')
+    ap.add_argument('--bwd', action='store_true')
     ap.add_argument('--ghz', type=float, default=1.965)
     ap.add_argument('--precision', default='fp32')
     ap.add_argument('--debug-set', default='')
@@ -50,9 +51,14 @@ def main():
         if it == 2:
             L.cliora_debug_ptr(0, dbg.data_ptr())
             L.cliora_debug_set(8, args.level + 1)
-            L.cliora_debug_set(9, 1 if args.outside else 0)
-        with torch.no_grad():
-            m(x, x, obj, obj) if R else m(x, x)
+            L.cliora_debug_set(9, (2 if args.bwd else 0) + (1 if args.outside else 0))
+        if args.bwd:
+            xg = x.clone().requires_grad_()
+            m(xg, xg, obj, obj) if R else m(xg, xg)
+            (m.inside_h.sum() + m.outside_h.sum() + m.inside_s.sum() + m.outside_s.sum()).backward()
+        else:
+            with torch.no_grad():
+                m(x, x, obj, obj) if R else m(x, x)
         torch.cuda.synchronize()
     L.cliora_debug_set(8, 0)
     L.cliora_debug_ptr(0, None)
@@ -70,9 +76,14 @@ def main():
         base = row[0].item()
         print('--- cta', cta)
         for k in sorted(NAMES):
-            if row[k].item():
+            if row[k].item() and not args.bwd:
                 print('  %-22s %8.2f us' % (NAMES[k], (row[k].item() - base) / (args.ghz * 1e3)))
         us = lambda k: (row[k].item() - base) / (args.ghz * 1e3)
+        if args.bwd:
+            for k, nm in [(1, 'prologue done'), (20, 'mma first full'), (2, 'db2 sums done'), (21, 'mma last full'), (3, 'tmem_full + sync'),
+                          (4, 'GZ staged in smem'), (5, 'scatter done'), (18, 'exit')]:
+                print('  %-22s %8.2f us' % (nm, us(k)))
+            continue
         for i in range(4):
             print('  xform kb=%d: top %.2f raw_full %.2f math %.2f emptyA %.2f st_done %.2f end %.2f' % tuple([4 + i] + [us(32 + 6 * i + q) for q in range(6)]))
         for i in range(4):

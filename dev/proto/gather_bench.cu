@@ -17,7 +17,10 @@
 
 constexpr int ROWS = 6720, LD = 1200, D = 400;
 constexpr int kStages = 4, kStageBytes = 2 * 128 * 128;
-constexpr int kConsWarps = 8, kCopyThreads = 128;
+#ifndef COPY_THREADS
+#define COPY_THREADS 128
+#endif
+constexpr int kConsWarps = 8, kCopyThreads = COPY_THREADS;
 constexpr int kThreads = (1 + kConsWarps) * 32 + kCopyThreads;   // warp 0 = TMA issuer, 1..8 consumers, then copy threads
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,8 +186,8 @@ __global__ void __launch_bounds__(kThreads, 1) gather_kernel(const __grid_consta
       mbar_wait(&empty[st], ((kb / kStages) & 1) ^ 1);
       const uint32_t sdst = sbase + st * kStageBytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rbase + 16 * i;
+      for (int i = 0; i < 1024 / kCopyThreads; ++i) {
+        const int r = rbase + (kCopyThreads / 8) * i;
         const uint32_t so = (uint32_t)(r * 128 + (((a.swz ? (c ^ (r & 7)) : c)) << 4));
         cp_async16(sdst + so, a.P + (int64_t)s_rows[r] * LD + kb * 32 + c * 4);
         cp_async16(sdst + 16384 + so, a.P + (int64_t)s_rows[128 + r] * LD + D + kb * 32 + c * 4);
