@@ -519,6 +519,8 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   const int64_t mb = outside ? c.L.Mbout : c.L.Mbin;
   // ReLU bit masks are only produced on request: the backward reads the sign of the stored Z pair instead
   a.zmask = (mb >= 0 && g_debug[10] != 0) ? reinterpret_cast<uint32_t*>(ws + mb) + r0 * 16 : nullptr;
+  // the tensor-memory variant leaves the signs as plain bits in the same buffer (64 bytes per row, D <= 512)
+  a.zbits = (mb >= 0 && g_debug[10] == 0 && g_debug[13] == 0) ? reinterpret_cast<uint16_t*>(ws + mb) + r0 * 32 : nullptr;
   a.Y = ws + (outside ? c.L.Yout : c.L.Yin) + r0 * D;
   a.E = ws + (outside ? c.L.Eout : c.L.Ein) + r0;
   a.Pr = ws + (outside ? c.L.Prout : c.L.Prin) + r0;
@@ -577,6 +579,10 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     const int ldPin = (int)(c.L.PI * D);
     b.Y = ws + (OUTSIDE ? c.L.Yout : c.L.Yin) + r0 * D;
     b.Zhi = ws + (OUTSIDE ? c.L.Zout : c.L.Zin) + r0 * D;
+    {
+      const int64_t mb = OUTSIDE ? c.L.Mbout : c.L.Mbin;
+      b.zbits = (mb >= 0 && g_debug[10] == 0 && g_debug[13] == 0) ? reinterpret_cast<const uint16_t*>(ws + mb) + r0 * 32 : nullptr;
+    }
     b.Pr = ws + (OUTSIDE ? c.L.Prout : c.L.Prin) + r0;
     b.E = ws + (OUTSIDE ? c.L.Eout : c.L.Ein) + r0;
     b.GA = bws + c.L.GA; b.CM = bws + c.L.CM;

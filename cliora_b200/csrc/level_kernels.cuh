@@ -151,6 +151,7 @@ struct LevelFwdArgs {
   const float* s1; const float* s2;                   // chart scores of first / second [B,C]
   const float* b1; const float* b2;
   float* Z; int64_t z_lo_off; uint32_t* zmask;        // level blocks: Z pair (hi, lo at +z_lo_off), ReLU bits [rows,16] or null
+  uint16_t* zbits;                                    // level block [rows,32]: bit j of halfword c = [z[16 c + j] > 0], or null
   float* Y; float* E; float* Pr;                      // level blocks [rows,D], [rows], [rows]
   float* chart_h; float* chart_s;                     // [B,C,D], [B,C]
   float* q; float* nrm; float* nrm2; float* att;      // saved per cell (q, nrm2, att: R > 0 only)
@@ -339,7 +340,8 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
 
 template <class XformFn>
 CL_D void transform_a_tmem(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, uint64_t* fullA, uint64_t* emptyA,
-                           uint32_t tmem_base, int num_kb, int mode, XformFn xform, long long* dbg = nullptr) {
+                           uint32_t tmem_base, int num_kb, int mode, XformFn xform, long long* dbg = nullptr,
+                           uint16_t* zb_row = nullptr, int zb_turn0 = 0, int zb_every = 1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;
   const int row = qd * 32 + lane;
@@ -366,6 +368,12 @@ CL_D void transform_a_tmem(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empt
       const float4 o = xform(xa[t], xb[t], k0 + t * 4);
       split_trunc(o.x, hi[4 * t], lo[4 * t]); split_trunc(o.y, hi[4 * t + 1], lo[4 * t + 1]);
       split_trunc(o.z, hi[4 * t + 2], lo[4 * t + 2]); split_trunc(o.w, hi[4 * t + 3], lo[4 * t + 3]);
+    }
+    if (zb_row != nullptr && (kb % zb_every) == zb_turn0) {   // sign bits of this thread's 16 values (CTA kb % nc writes)
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bits |= (hi[j] > 0.f ? 1u : 0u) << j;
+      zb_row[kb * 2 + half] = (uint16_t)bits;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_local(&raw_empty[stage]);   // raw stage read: the copy warps may refill it
@@ -588,6 +596,11 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     // ------------------------------------------------------------ A operand -> tensor memory (see transform_a_tmem)
     // z = relu(Al[first] + Ar[second]); b1 rides on the second operand's projection, padding was zero-filled
     if (dbg_row && tid == kProdWarp0 * 32) dbg_row[22] = clock_now();
+    uint16_t* zb_row = nullptr;
+    if (a.zbits != nullptr) {
+      const RowInfo ri = decode_row(a, tile, cells_here, (warp & 3) * 32 + lane);
+      if (ri.ok) zb_row = a.zbits + ri.m * 32;
+    }
     transform_a_tmem(
         smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode,
         [&](const float4& xa, const float4& xb, int kc) {
@@ -595,7 +608,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           return make_float4(fmaxf(xa.x + xb.x, 0.f), fmaxf(xa.y + xb.y, 0.f), fmaxf(xa.z + xb.z, 0.f),
                              fmaxf(xa.w + xb.w, 0.f));
         },
-        dbg_row);
+        dbg_row, zb_row, rank, nc);
     if (dbg_row && tid == kProdWarp0 * 32) dbg_row[23] = clock_now();
   } else if (warp >= kProdWarp0) {
     // ------------------------------------------------------------ A operand: gather + ReLU + tf32 split
@@ -1031,6 +1044,7 @@ struct LevelBwdArgs {
   LevelFwdArgs geo;          // geometry only: B, n, level, L, N, D, G, cells, ncols, n_umma, nc, mode, outside, C
   const float* Y;            // level block [rows, D]: forward compose outputs
   const float* Zhi;          // level block [rows, D]: hi part of the hidden activations (its sign is the ReLU mask)
+  const uint16_t* zbits;     // level block [rows, 32]: the same signs as bits (written by the forward level kernel), or null
   const float* Pr; const float* E;       // level blocks [rows]
   const float* GA; const float* Gs; const float* CM;   // [B,C,D], [B,C], [B,C] of this pass's chart
   const float* h1;           // chart vectors of `first` [B,C,D]
@@ -1287,7 +1301,16 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     const long long m = s_m[r];
     const int nch = ncols >> 2;
     uint32_t mk[4] = {0u, 0u, 0u, 0u};
-    if (m >= 0) {
+    if (m >= 0 && g.zbits != nullptr) {
+      // 64 bytes of sign bits per row: the bits of columns n0 .. n0 + 127 are funnel-shifted out of five words
+      const uint32_t* wrow = reinterpret_cast<const uint32_t*>(g.zbits + m * 32);
+      const int w0 = n0 >> 5, sh = n0 & 31;
+      uint32_t wv[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) wv[q] = (w0 + q < 16) ? __ldcg(wrow + w0 + q) : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mk[q] = __funnelshift_r(wv[q], wv[q + 1], sh);
+    } else if (m >= 0) {
       const float* zrow = g.Zhi + m * D + n0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
