@@ -581,7 +581,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
             ob = (uint32_t)(ri.g2 * a.ld2 + a.off_a2);
           },
           // the Z pair of k-block kb (for the dW2 GEMM of the backward pass) is streamed out by CTA kb % nc
-          rank, a.Z != nullptr ? nc : 0,
+          rank, (a.Z != nullptr && !(a.exp_flags & 2)) ? nc : 0,
           [&](int r, int kc, const float4& xa, const float4& xb) {
             float4 hi, lo;
             split_trunc(fmaxf(xa.x + xb.x, 0.f), hi.x, lo.x); split_trunc(fmaxf(xa.y + xb.y, 0.f), hi.y, lo.y);
@@ -597,7 +597,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     // z = relu(Al[first] + Ar[second]); b1 rides on the second operand's projection, padding was zero-filled
     if (dbg_row && tid == kProdWarp0 * 32) dbg_row[22] = clock_now();
     uint16_t* zb_row = nullptr;
-    if (a.zbits != nullptr) {
+    if (a.zbits != nullptr && !(a.exp_flags & 8)) {
       const RowInfo ri = decode_row(a, tile, cells_here, (warp & 3) * 32 + lane);
       if (ri.ok) zb_row = a.zbits + ri.m * 32;
     }
@@ -748,7 +748,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int ch = c + 8 * t;
-            const bool ld = okr[u] && ch < nch && n0 + ch * 4 < D;
+            const bool ld = okr[u] && ch < nch && n0 + ch * 4 < D && !(a.exp_flags & 16);
             hv[u][t] = ld ? ldcg4(hp + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             vv[u][t] = ld ? ldcg4(vp + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -807,18 +807,36 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   tcgen05_fence_after();
   __syncthreads();                               // softmax probabilities published; pipeline stages are free
   LV_STAMP(6);
-  const int stride = ncols + 4;
-  float* s_stage = reinterpret_cast<float*>(smem);            // [128][ncols + 4] p-weighted compose outputs
-  float* s_a = s_stage + kRows * stride;                       // [G][ncols]
   const int nc4 = ncols >> 2;
+  const int stride = (nc4 & 1) ? ncols : ncols + 4;            // stride / 4 odd: conflict-free 16-byte accesses by row
+  float* s_stage = reinterpret_cast<float*>(smem);            // [128][stride] compose outputs y
+  float* s_a = s_stage + kRows * stride;                       // [G][ncols]
+  const bool vl = a.R > 0;
+  const int R = a.R;
+  const int GRs = a.G * R, GRp = (GRs + 3) & ~3;
+  float* s_att = s_a + kRows * ncols;            // [G][R] logits -> attention weights
+  float* s_patt = s_att + GRp;                   // [G][R] dropout-scaled weights
+  float* s_keep = s_patt + GRp;                  // [G][R] dropout scale of every (cell, region): 0 or 1 / (1 - p)
+  float* s_obj = s_keep + GRp;                   // [max_sent][R][stride]: this CTA's column slice of the tile's images
+  const int b_first = (tile * a.G) / a.L;
+  if (vl) {
+    // the region features of the sentences this tile spans: asynchronous copies, consumed after the first normalisation
+    const int b_last = (tile * a.G + cells_here - 1) / a.L;
+    const int total = (b_last - b_first + 1) * R * nc4;
+    const float* src = a.obj + (int64_t)b_first * R * D + n0;
+    for (int idx = tid; idx < total; idx += kThreads) {
+      const int row = idx / nc4, j4 = idx - row * nc4;        // row = sentence * R + region
+      float* dst = s_obj + row * stride + j4 * 4;
+      if (n0 + j4 * 4 < D) cp_async16(dst, src + (int64_t)row * D + j4 * 4);
+      else st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    cp_async_commit();
+  }
   if (warp >= 2) {
-    // y = relu(acc + b2) -> Y row (saved for backward); p * y staged.  Twelve warps: TMEM lane quarter = warp % 4,
-    // the 16-column chunks of a quarter are dealt to its three warps.
+    // y = relu(acc + b2), staged row-major.  TMEM lane quarter = warp % 4, the 16-column chunks of a quarter are dealt
+    // to its warps.
     constexpr int kSub = (kThreads / 32 - 2) / 4;          // warps per TMEM lane quarter
     const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
-    const long long m = s_m[r];
-    const float p = s_p[r];
-    float* yrow = m >= 0 ? a.Y + m * D + n0 : nullptr;
 #pragma unroll 1
     for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
@@ -838,8 +856,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           o.x = fmaxf(v[j] + bv.x, 0.f); o.y = fmaxf(v[j + 1] + bv.y, 0.f);
           o.z = fmaxf(v[j + 2] + bv.z, 0.f); o.w = fmaxf(v[j + 3] + bv.w, 0.f);
           if (n0 + col >= D) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          else if (yrow) st4(yrow + col, o);
-          st4(s_stage + r * stride + col, make_float4(p * o.x, p * o.y, p * o.z, p * o.w));
+          st4(s_stage + r * stride + col, o);
         }
       }
     }
@@ -847,14 +864,18 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   tcgen05_fence_before();
   __syncthreads();
   LV_STAMP(7);
-  // per-cell sums over the N splits (fixed order: deterministic)
+  // per-cell softmax-weighted sums over the N splits (fixed order: deterministic); the Y rows (saved for the backward
+  // pass) leave from here, one 16-byte chunk per thread and a row slice per group of consecutive threads
   for (int item = tid; item < cells_here * nc4; item += kThreads) {
     const int g = item / nc4, j4 = item - g * nc4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* src = s_stage + (g * N) * stride + j4 * 4;
+    const bool live = n0 + j4 * 4 < D;
     for (int kk = 0; kk < N; ++kk) {
       const float4 t = ld4(src + kk * stride);
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      const float pk = s_p[g * N + kk];
+      if (live) st4(a.Y + s_m[g * N + kk] * D + n0 + j4 * 4, t);
+      acc.x = fmaf(pk, t.x, acc.x); acc.y = fmaf(pk, t.y, acc.y); acc.z = fmaf(pk, t.z, acc.z); acc.w = fmaf(pk, t.w, acc.w);
     }
     st4(s_a + g * ncols + j4 * 4, acc);
   }
@@ -871,24 +892,14 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   }
   LV_STAMP(8);
   xchg_arrive_warp(&xbar[1], nc, lane);
-  const bool vl = a.R > 0;
-  const int R = a.R, Rp = a.R | 1;               // odd row pitch: conflict-free column walks
-  const int GRs = a.G * R, GRp = (GRs + 3) & ~3;
-  float* s_att = s_a + kRows * ncols;            // [G][R] logits -> attention weights
-  float* s_patt = s_att + GRp;                   // [G][R] dropout-scaled weights
-  float* s_obj = s_patt + GRp;                   // [max_sent][ncols][Rp]: this CTA's column slice of the tile's images
-  const int b_first = (tile * a.G) / a.L;
   if (vl) {
-    // stage the region features (transposed) while the norms travel: rows (sentence, region), 16 bytes per thread
-    const int b_last = (tile * a.G + cells_here - 1) / a.L;
-    const int total = (b_last - b_first + 1) * R * nc4;
-    const float* src = a.obj + (int64_t)b_first * R * D + n0;
-    for (int idx = tid; idx < total; idx += kThreads) {
-      const int row = idx / nc4, j4 = idx - row * nc4;        // row = sentence * R + region
-      const int bs = row / R, rr = row - bs * R;
-      const float4 v = (n0 + j4 * 4 < D) ? ldcg4(src + (int64_t)row * D + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float* dst = s_obj + ((bs * ncols) + j4 * 4) * Rp + rr;
-      dst[0] = v.x; dst[Rp] = v.y; dst[2 * Rp] = v.z; dst[3 * Rp] = v.w;
+    // dropout scale of every (cell, region) of the tile, fetched while the norms travel
+    for (int item = tid; item < cells_here * R; item += kThreads) {
+      const int g = item / R, rr = item - g * R;
+      int cb, cp;
+      int64_t ccell;
+      cell_of(a, tile * a.G + g, cb, cp, ccell);
+      s_keep[item] = a.keep != nullptr ? (a.keep[ccell * R + rr] ? kKeepScale : 0.f) : 1.f;
     }
   }
   xchg_wait_warp(&xbar[1], lane);
@@ -903,6 +914,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     s_nrm[tid] = nrm;
     if (rank == 0) a.nrm[ccell] = a.no_norm ? -1.f : nrm;
   }
+  if (vl) cp_async_wait_all();                   // this thread's region-feature copies have landed
   __syncthreads();
   for (int item = tid; item < cells_here * nc4; item += kThreads) {
     const int g = item / nc4, j4 = item - g * nc4;
@@ -925,12 +937,15 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     for (int item = tid; item < cells_here * R; item += kThreads) {     // partial logits q . obj_r
       const int g = item / R, rr = item - g * R;
       const int bs = (tile * a.G + g) / a.L - b_first;
-      const float* op = s_obj + (bs * ncols) * Rp + rr;
+      const float* op = s_obj + (bs * R + rr) * stride;
       const float* qp = s_a + g * ncols;
-      float d = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < ncols; ++j) d = fmaf(qp[j], op[j * Rp], d);
-      xchg_put(s_xl + rank * GRs, item, d, nc);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll 2
+      for (int j4 = 0; j4 < nc4; ++j4) {
+        const float4 qv = ld4(qp + j4 * 4), ov = ld4(op + j4 * 4);
+        d0 = fmaf(qv.x, ov.x, d0); d1 = fmaf(qv.y, ov.y, d1); d0 = fmaf(qv.z, ov.z, d0); d1 = fmaf(qv.w, ov.w, d1);
+      }
+      xchg_put(s_xl + rank * GRs, item, d0 + d1, nc);
     }
     LV_STAMP(12);
     xchg_arrive_warp(&xbar[2], nc, lane);
@@ -955,29 +970,29 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       if (lane < R) {
         const float at = e0 * inv;
         if (rank == 0) a.att[ccell * R + lane] = at;
-        float sc = 1.f;
-        if (a.keep != nullptr) sc = a.keep[ccell * R + lane] ? kKeepScale : 0.f;
-        s_patt[g * R + lane] = at * sc;
+        s_patt[g * R + lane] = at * s_keep[g * R + lane];
       }
       if (lane + 32 < R) {
         const float at = e1 * inv;
         if (rank == 0) a.att[ccell * R + lane + 32] = at;
-        float sc = 1.f;
-        if (a.keep != nullptr) sc = a.keep[ccell * R + lane + 32] ? kKeepScale : 0.f;
-        s_patt[g * R + lane + 32] = at * sc;
+        s_patt[g * R + lane + 32] = at * s_keep[g * R + lane + 32];
       }
     }
     __syncthreads();
     LV_STAMP(14);
-    for (int item = tid; item < cells_here * ncols; item += kThreads) {  // a2 = q + sum_r patt_r obj_r
-      const int g = item / ncols, j = item - g * ncols;
+    for (int item = tid; item < cells_here * nc4; item += kThreads) {    // a2 = q + sum_r patt_r obj_r
+      const int g = item / nc4, j4 = item - g * nc4;
       const int bs = (tile * a.G + g) / a.L - b_first;
-      const float* op = s_obj + (bs * ncols + j) * Rp;
+      const float* op = s_obj + (bs * R) * stride + j4 * 4;
       const float* wp = s_patt + g * R;
-      float t = s_a[item];
+      float4 t = ld4(s_a + g * ncols + j4 * 4);
 #pragma unroll 4
-      for (int rr = 0; rr < R; ++rr) t = fmaf(wp[rr], op[rr], t);
-      s_a[item] = t;
+      for (int rr = 0; rr < R; ++rr) {
+        const float w = wp[rr];
+        const float4 ov = ld4(op + rr * stride);
+        t.x = fmaf(w, ov.x, t.x); t.y = fmaf(w, ov.y, t.y); t.z = fmaf(w, ov.z, t.z); t.w = fmaf(w, ov.w, t.w);
+      }
+      st4(s_a + g * ncols + j4 * 4, t);
     }
     __syncthreads();
     for (int g = warp; g < cells_here; g += kThreads / 32) {
@@ -1490,8 +1505,8 @@ inline int level_cells_per_tile(int cells, int N, int L, int R, const LevelGeom&
     const int64_t area = (int64_t)ring_bytes(g.n_umma) / 4;     // floats in the operand rings
     for (; G >= 1; --G) {
       max_sent = (G - 1) / L + 2;
-      const int64_t need = (int64_t)kRows * (g.ncols + 4) + (int64_t)kRows * g.ncols + 2 * ((G * R + 3) & ~3) +
-                           (int64_t)max_sent * g.ncols * (R | 1);
+      const int64_t need = (int64_t)kRows * (g.ncols + 4) + (int64_t)kRows * g.ncols + 3 * ((G * R + 3) & ~3) +
+                           (int64_t)max_sent * R * (g.ncols + 4);
       if (need <= area) break;
     }
   }
