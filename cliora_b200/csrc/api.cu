@@ -553,7 +553,17 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   // GE is level-local here: point the kernel at a level block starting at GE[0]
   // (cell_bwd indexes GE with the same row ids as E, relative to the level block).
   const bool fused = g.c.E != nullptr && fused_bwd_ok(c);
-  const bool cells_inline = fused && !VL && g_debug[14] == 0;   // text cells: the fused kernel's prologue does the cell part
+  // the fused kernel's prologue does the cell part: text cells always, CLIORA cells when a tile's images fit the rings
+  lvl::LevelGeom geom0;
+  int G0 = 0, max_sent0 = 0;
+  if (fused) {
+    fused_level_ok(c, g.c.N, geom0);
+    G0 = lvl::level_cells_per_tile(B * (n - level), g.c.N, n - level, 0, geom0, (148 / geom0.nc) / chain_count(c), max_sent0);
+    max_sent0 = G0 > 0 ? (G0 - 1) / (n - level) + 2 : 0;
+  }
+  const bool vl_fits = VL && D <= 128 * kColT && c.d.R <= 64 && (D % 4) == 0 && G0 > 0 &&
+                       (size_t)max_sent0 * c.d.R * D * sizeof(float) <= (size_t)lvl::ring_bytes(geom0.n_umma);
+  const bool cells_inline = fused && (!VL || vl_fits) && g_debug[14] == 0;
   if (fused) {
     g.ga_out = bws + c.L.GA;
     g.cm_out = bws + c.L.CM;
@@ -599,6 +609,10 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     b.GAw = bws + c.L.GA; b.CMw = bws + c.L.CM;
     if (cells_inline) {
       b.cellGh = g.Gh; b.cellH = chart_h; b.cellNrm = g.c.nrm; b.cellS = chart_s;
+      if (VL) {
+        b.vl_obj = obj; b.vl_keep = keep; b.vl_att = g.c.att; b.vl_q = g.c.q; b.vl_nrm2 = g.c.nrm2;
+        b.vl_GA2 = g.GA2; b.vl_coef = g.coef; b.vl_R = c.d.R;
+      }
     }
     const float* W2T = c.lvl_mode == 3 ? ws + (OUTSIDE ? c.L.oW2Th : c.L.W2Th) : ws + (OUTSIDE ? c.L.oW2Tp : c.L.W2Tp);
     return lvl::launch_level_bwd(c.st, b, W2T, OUTSIDE ? "level_bwd_outside" : "level_bwd_inside");

@@ -19,6 +19,7 @@
 //               weight-gradient GEMM of the backward pass)
 #pragma once
 #include "chart_kernels.cuh"
+#include "cell_warp_kernels.cuh"
 #include "tc_gemm.cuh"
 
 namespace cliora {
@@ -1073,6 +1074,11 @@ struct LevelBwdArgs {
   // separate cells-only launch; null cellGh = GA / CM were prepared by the cell kernel
   const float* cellGh; const float* cellH; const float* cellNrm; const float* cellS;   // [B,C,D], [B,C,D], [B,C], [B,C]
   float* GAw; float* CMw;                // writable aliases of GA / CM
+  // CLIORA cells (region attention): the same prologue also runs the attention / second-normalise backward against the
+  // tile's images, staged in the still idle operand rings; null vl_obj = text cells.  Needs D <= 512, R <= 64.
+  const float* vl_obj; const uint8_t* vl_keep; const float* vl_att; const float* vl_q; const float* vl_nrm2;
+  float* vl_GA2; float* vl_coef;         // saved for the region-feature gradient: ga2 [B,C,D], (patt, g_logit) [B,C,2,R]
+  int vl_R;
 };
 
 constexpr int kBwdDb2Floats = kMaxCluster * kMaxUmmaN;   // D <= 896
@@ -1153,7 +1159,119 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     s_g2[tid] = (int)ri.g2;
   }
   for (int j = tid; j < D; j += kThreads) s_db2[j] = 0.f;
-  if (g.cellGh != nullptr) {
+  if (g.cellGh != nullptr && g.vl_obj != nullptr) {
+    // CLIORA cells: second normalise -> region attention -> first normalise, backward (cliora.py:128-157), warp per
+    // cell against the image's regions staged in shared memory; every column-slice CTA computes the same values.
+    const int R = g.vl_R;
+    const int b_first = (tile * a.G) / a.L, b_last = (tile * a.G + cells_here - 1) / a.L;
+    float* s_obj = reinterpret_cast<float*>(smem);             // [sentences of the tile][R][D]
+    const int total4 = (b_last - b_first + 1) * R * D / 4;
+    const float* src = g.vl_obj + (int64_t)b_first * R * D;
+    for (int i = tid; i < total4; i += kThreads) cp_async16(s_obj + i * 4, src + i * 4);
+    cp_async_commit();
+    LB_STAMP(6);
+    for (int base = 0; base < cells_here; base += kThreads / 32) {      // uniform trip count: the barrier below is safe
+      const int gi = base + warp;
+      const bool active = gi < cells_here;
+      int cb = 0, cp = 0;
+      int64_t cell = 0;
+      if (active) cell_of(a, tile * a.G + gi, cb, cp, cell);
+      float4 gv[kColT], qv[kColT];
+      float nrm_raw = 1.f, at0 = 0.f, at1 = 0.f, sc0 = 1.f, sc1 = 1.f;
+      if (active) {
+        // everything that does not need the regions first: ga2 = unit_bwd(g, h, nrm2), the attention weights and masks
+        nrm_raw = g.cellNrm[cell];
+        const float nrm2_raw = g.vl_nrm2[cell];
+        if (lane < R) {
+          at0 = g.vl_att[cell * R + lane];
+          if (g.vl_keep != nullptr) sc0 = g.vl_keep[cell * R + lane] ? kKeepScale : 0.f;
+        }
+        if (lane + 32 < R) {
+          at1 = g.vl_att[cell * R + lane + 32];
+          if (g.vl_keep != nullptr) sc1 = g.vl_keep[cell * R + lane + 32] ? kKeepScale : 0.f;
+        }
+        float4 hv[kColT];
+        float hd = 0.f;
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          gv[t] = hv[t] = qv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < D) {
+            gv[t] = ldcg4(g.cellGh + cell * D + j);
+            hv[t] = ldcg4(g.cellH + cell * D + j);
+            qv[t] = ldcg4(g.vl_q + cell * D + j);
+            hd += dot4(hv[t], gv[t]);
+          }
+        }
+        hd = warp_sum(hd);
+        const float coef2 = unit_bwd_coef(nrm2_raw, hd), inv2 = 1.f / fabsf(nrm2_raw);
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          gv[t] = make_float4((gv[t].x - hv[t].x * coef2) * inv2, (gv[t].y - hv[t].y * coef2) * inv2,
+                              (gv[t].z - hv[t].z * coef2) * inv2, (gv[t].w - hv[t].w * coef2) * inv2);   // ga2
+          if (j < D) st4(g.vl_GA2 + cell * D + j, gv[t]);
+        }
+      }
+      LB_STAMP(7);
+      if (base == 0) {
+        cp_async_wait_all();
+        __syncthreads();                         // the regions of the tile's images are staged
+      }
+      LB_STAMP(8);
+      if (!active) continue;
+      const float* ob = s_obj + (int64_t)(cb - b_first) * R * D;
+      // g_att_r = (ga2 . obj_r) * scale_r, owned by lane r % 32
+      float ga0, ga1;
+      region_dots(gv, ob, R, D, lane, ga0, ga1);
+      if (lane >= R) ga0 = 0.f;
+      if (lane + 32 >= R) ga1 = 0.f;
+      LB_STAMP(9);
+      ga0 *= sc0;
+      ga1 *= sc1;
+      const float dsum = warp_sum(at0 * ga0 + at1 * ga1);
+      const float gl0 = at0 * (ga0 - dsum), gl1 = at1 * (ga1 - dsum);
+      if (lane < R) {
+        g.vl_coef[(cell * 2) * R + lane] = at0 * sc0;
+        g.vl_coef[(cell * 2 + 1) * R + lane] = gl0;
+      }
+      if (lane + 32 < R) {
+        g.vl_coef[(cell * 2) * R + lane + 32] = at1 * sc1;
+        g.vl_coef[(cell * 2 + 1) * R + lane + 32] = gl1;
+      }
+#pragma unroll 4
+      for (int r = 0; r < R; ++r) {   // gq = ga2 + sum_r g_logit_r obj_r
+        const float w = __shfl_sync(0xffffffffu, r < 32 ? gl0 : gl1, r & 31);
+#pragma unroll
+        for (int t = 0; t < kColT; ++t) {
+          const int j = lane * 4 + t * 128;
+          if (j < D) fma4(gv[t], w, ld4(ob + r * D + j));
+        }
+      }
+      float hd = 0.f;
+#pragma unroll
+      for (int t = 0; t < kColT; ++t)
+        if (lane * 4 + t * 128 < D) hd += dot4(qv[t], gv[t]);
+      hd = warp_sum(hd);
+      // ga = unit_bwd(gq, q, nrm)
+      const float coef = unit_bwd_coef(nrm_raw, hd), inv = 1.f / fabsf(nrm_raw);
+      float ad = 0.f;
+#pragma unroll
+      for (int t = 0; t < kColT; ++t) {
+        const int j = lane * 4 + t * 128;
+        gv[t] = make_float4((gv[t].x - qv[t].x * coef) * inv, (gv[t].y - qv[t].y * coef) * inv,
+                            (gv[t].z - qv[t].z * coef) * inv, (gv[t].w - qv[t].w * coef) * inv);
+        if (j < D) {
+          ad += dot4(qv[t], gv[t]);
+          st4(g.GAw + cell * D + j, gv[t]);
+        }
+      }
+      ad = warp_sum(ad);
+      if (lane == 0) g.CMw[cell] = fabsf(nrm_raw) * ad + g.cellS[cell] * g.Gs[cell];
+      LB_STAMP(10);
+    }
+    __threadfence_block();
+  } else if (g.cellGh != nullptr) {
     // per-cell normalise backward (text cells): ga = (g - h (h.g)) / nrm on the live branch, g / eps on the clamped one;
     // cm = sum_m p_m gp_m = nrm (h . ga) + s gs.  Warp per cell; every column-slice CTA computes the same values.
     for (int gi = warp; gi < cells_here; gi += kThreads / 32) {

@@ -80,7 +80,7 @@ def main():
                 print('  %-22s %8.2f us' % (NAMES[k], (row[k].item() - base) / (args.ghz * 1e3)))
         us = lambda k: (row[k].item() - base) / (args.ghz * 1e3)
         if args.bwd:
-            for k, nm in [(1, 'prologue done'), (20, 'mma first full'), (2, 'db2 sums done'), (21, 'mma last full'), (3, 'tmem_full + sync'),
+            for k, nm in [(6, 'vl: staging issued'), (7, 'vl: ga2 done'), (8, 'vl: regions staged'), (9, 'vl: region dots'), (10, 'vl: cell done'), (1, 'prologue done'), (20, 'mma first full'), (2, 'db2 sums done'), (21, 'mma last full'), (3, 'tmem_full + sync'),
                           (4, 'GZ staged in smem'), (5, 'scatter done'), (18, 'exit')]:
                 print('  %-22s %8.2f us' % (nm, us(k)))
             continue
