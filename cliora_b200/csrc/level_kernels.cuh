@@ -53,10 +53,9 @@ constexpr int kThreads = (kCopyWarp0 + kCopyWarps) * 32;   // 576
 constexpr int kMaxCluster = 8;
 constexpr int kMaxUmmaN = 112;
 constexpr int kABytes = kRows * 128;  // one 128 x 32 fp32 operand tile
-constexpr int kXlFloats = 2048;       // region-logit exchange buffer (nc * G * R floats)
 // extras after the operand rings: barriers (256 B), b2 (128 f), e, p, nrm, nrm2 (4 x 128 f), three [8][128] exchange
-// buffers, the logit exchange buffer, the global row of every tile row (int64)
-constexpr int kExtraFloats = 128 + 4 * 128 + 3 * kMaxCluster * 128 + kXlFloats;
+// buffers, the global row of every tile row (int64)
+constexpr int kExtraFloats = 128 + 4 * 128 + 3 * kMaxCluster * 128;
 constexpr int kExtraBytes = 256 + 4 * kExtraFloats + 8 * 128;
 // W2-slice ring (TMA): three stages when the slice is narrow, two otherwise (shared-memory budget)
 CL_HD int b_stages(int n_umma) { return n_umma <= 80 ? 3 : 2; }
@@ -445,8 +444,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   float* s_xe = s_nrm2 + 128;                     // [nc][128] partial scores
   float* s_xs = s_xe + kMaxCluster * 128;         // [nc][128] partial |a|^2
   float* s_xs2 = s_xs + kMaxCluster * 128;        // [nc][128] partial |a2|^2
-  float* s_xl = s_xs2 + kMaxCluster * 128;        // [nc][G*R] partial region logits
-  long long* s_m = reinterpret_cast<long long*>(s_xl + kXlFloats);   // [128] global row of every tile row, -1 = none
+  long long* s_m = reinterpret_cast<long long*>(s_xs2 + kMaxCluster * 128);   // [128] global row of every tile row, -1 = none
   // A_TMEM: accumulators in columns [0, 2 n_umma), four A-operand stages (hi 32 | lo 32 columns each) from column 256
   const uint32_t tmem_cols_alloc = A_TMEM ? 512u : (uint32_t)tc::tmem_cols(2 * a.n_umma);
 
@@ -819,6 +817,9 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   float* s_patt = s_att + GRp;                   // [G][R] dropout-scaled weights
   float* s_keep = s_patt + GRp;                  // [G][R] dropout scale of every (cell, region): 0 or 1 / (1 - p)
   float* s_obj = s_keep + GRp;                   // [max_sent][R][stride]: this CTA's column slice of the tile's images
+  // [nc][G*R] partial region logits, written by the peers after the norm exchange (every CTA's rings are free by then);
+  // same offset in every CTA of the cluster
+  float* s_xl = s_obj + a.max_sent * R * stride;
   const int b_first = (tile * a.G) / a.L;
   if (vl) {
     // the region features of the sentences this tile spans: asynchronous copies, consumed after the first normalisation
@@ -1604,16 +1605,12 @@ inline bool level_geom(int D, LevelGeom& g) {
 }
 // clusters of this shape that can be resident at once (cached per device and shape)
 int max_active_clusters(int nc, size_t smem);
-// cells per tile: whole cells only, G*N <= 128.  CLIORA adds two bounds: the logit exchange buffer (G*R*nc floats) and
-// the shared-memory staging of the region slices of every image a tile can span ((G-1)/L + 2 sentences).  Otherwise the
+// cells per tile: whole cells only, G*N <= 128.  CLIORA adds one bound: the shared-memory staging of the region slices
+// of every image a tile can span ((G-1)/L + 2 sentences) plus the logit exchange buffer (G*R*nc floats).  Otherwise the
 // level's cells are spread over about one wave of clusters.
 inline int level_cells_per_tile(int cells, int N, int L, int R, const LevelGeom& g, int target_tiles, int& max_sent) {
   int gmax = kRows / N;
   max_sent = 0;
-  if (R > 0) {
-    const int gv = kXlFloats / (R * g.nc);
-    if (gv < gmax) gmax = gv;
-  }
   if (gmax < 1) return 0;
   if (target_tiles < 1) target_tiles = 1;
   int G = ceil_div(cells, target_tiles);
@@ -1624,7 +1621,7 @@ inline int level_cells_per_tile(int cells, int N, int L, int R, const LevelGeom&
     for (; G >= 1; --G) {
       max_sent = (G - 1) / L + 2;
       const int64_t need = (int64_t)kRows * (g.ncols + 4) + (int64_t)kRows * g.ncols + 3 * ((G * R + 3) & ~3) +
-                           (int64_t)max_sent * R * (g.ncols + 4);
+                           (int64_t)max_sent * R * (g.ncols + 4) + (int64_t)g.nc * G * R;
       if (need <= area) break;
     }
   }
@@ -1677,6 +1674,8 @@ inline int launch_level_fwd(cudaStream_t st, const LevelFwdArgs& a_in, const flo
   LevelFwdArgs a = a_in;
   a.exp_flags = g_debug[12];
   a.dbg = (g_level_dbg != nullptr && g_debug[8] == a.level + 1 && g_debug[9] == a.outside) ? g_level_dbg : nullptr;
+  if (g_level_dbg != nullptr && g_debug[8] == 99 && g_debug[9] == a.outside)      // every level: 1024 rows of 128 per level
+    a.dbg = g_level_dbg + (int64_t)a.level * 1024 * 128;
   CUtensorMap tmW;
   if (a.mode == 3) CL_TRY(make_bf16_map(&tmW, W2pair, a.D, a.D, a.n_umma));      // W2pair = the bf16 copy in this mode
   else
@@ -1716,6 +1715,8 @@ inline size_t level_bwd_smem(int n_umma) { return (size_t)ring_bytes(n_umma) + k
 inline int launch_level_bwd(cudaStream_t st, const LevelBwdArgs& g_in, const float* W2Tpair, const char* tag) {
   LevelBwdArgs g = g_in;
   g.geo.dbg = (g_level_dbg != nullptr && g_debug[8] == g.geo.level + 1 && g_debug[9] == 2 + g.geo.outside) ? g_level_dbg : nullptr;
+  if (g_level_dbg != nullptr && g_debug[8] == 99 && g_debug[9] == 2 + g.geo.outside)
+    g.geo.dbg = g_level_dbg + (int64_t)g.geo.level * 1024 * 128;
   const LevelFwdArgs& a = g.geo;
   CUtensorMap tmW;
   if (a.mode == 3) CL_TRY(make_bf16_map(&tmW, W2Tpair, a.D, a.D, a.n_umma));

@@ -21,7 +21,7 @@ def timeit(fn, reps=10):
     for _ in range(reps): g.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-for chains in (1, 4):
+for chains in (1, 2):
     for vl in (False, True):
         m = (DioraMLP(D) if vl else TextDiora(D)).cuda(); m.chains = chains; m.train()
         x = torch.randn(B, n, D, device='cuda', requires_grad=True)
