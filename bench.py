@@ -198,7 +198,15 @@ def roofline_of(prof, nprof, pk, traffic_path=None):
                              gbs=v['bytes'] / v['ms'] / 1e6 if v['ms'] else 0, avg_launch_us=per * 1e3)
     if not prof:
         return None, kernels
-    name, v = max(prof.items(), key=lambda kv: kv[1]['ms'])
+    # the dominant KERNEL: the fused level kernels are profiled as four classes (forward / backward x inside / outside
+    # pass) of two kernels -- their classes are merged before the comparison
+    merged = {}
+    for k, v in prof.items():
+        key = 'level_fwd' if k.startswith('level_fwd') else 'level_bwd' if k.startswith('level_bwd') else k
+        m = merged.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for f in ('launches', 'ms', 'flops', 'bytes'):
+            m[f] += v[f]
+    name, v = max(merged.items(), key=lambda kv: kv[1]['ms'])
     traffic, traffic_note = None, None
     if traffic_path and os.path.exists(traffic_path):   # dram__bytes_read+write of one ncu --set full capture
         t = json.load(open(traffic_path)).get(name)

@@ -480,13 +480,25 @@ static bool fused_level_ok(const Ctx& c, int N, lvl::LevelGeom& g) {
   return true;
 }
 
+// A level whose tiles (whole cells, at most 128 split rows each) cannot all be resident at once with the narrow
+// geometry anyway is run with wide column slices instead: half as many CTAs per tile, so half the waves.
+// `slots`: CTAs of the narrow kernel that can be resident for this chain.
+static void widen_if_crowded(const Ctx& c, int cells, int N, int slots, lvl::LevelGeom& g) {
+  if (g_debug[15] == 1 || (g_debug[13] != 0) || g_debug[10] != 0) return;      // 15 = 1: never wide
+  const int gmax = lvl::kRows / N;
+  const int min_tiles = ceil_div(cells, gmax < 1 ? 1 : gmax);
+  if (g_debug[15] != 2 && min_tiles * g.nc <= slots) return;                    // 15 = 2: always wide
+  lvl::LevelGeom w;
+  if (lvl::level_geom(c.d.D, w, /*wide=*/true) && w.nc < g.nc) g = w;
+}
+
 // The fused backward needs every level of a pass to qualify (its compose-output gradients live in one buffer per pass)
 static bool fused_bwd_ok(const Ctx& c) {
   lvl::LevelGeom g;
   return g_debug[7] == 0 && c.d.n >= 2 && fused_level_ok(c, c.d.n - 1, g);
 }
 
-static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::LevelGeom& geom, const cliora_weights* w,
+static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::LevelGeom& geom_in, const cliora_weights* w,
                            const float* ih, const float* is_, const float* os_, float* chart_h, float* chart_s,
                            const float* obj, const uint8_t* keep, float* ws) {
   const int n = c.d.n, D = c.d.D, B = c.d.B;
@@ -495,13 +507,22 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   a.B = B; a.n = n; a.level = level; a.L = n - level; a.N = outside ? n - level - 1 : level; a.D = D;
   a.R = outside ? 0 : c.d.R;
   a.cells = B * a.L;
-  a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
+  lvl::LevelGeom geom = geom_in;
   // sentence chains run their level kernels side by side: each aims at its share of the co-resident clusters
-  a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, a.R, geom,
-                                  lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) / chain_count(c),
-                                  a.max_sent);
+  const int slots = lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) * geom.nc / chain_count(c);
+  widen_if_crowded(c, a.cells, a.N, slots, geom);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, a.R, geom,
+                                    lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) / chain_count(c),
+                                    a.max_sent);
+    if (a.G >= 1 || geom.nc == geom_in.nc) break;
+    geom = geom_in;                                  // the wide tile does not fit this level's staging: narrow again
+  }
   if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
+  a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
   a.mode = c.lvl_mode;
+  a.store_lo = c.lvl_mode == 2 ? 1 : 0;      // modes 1 and 3 never read the lo parts
+  a.single_acc = (a.n_umma > lvl::kNarrowUmmaN) ? 1 : 0;
   a.no_norm = (c.d.flags & CLIORA_FLAG_NO_NORMALIZE) ? 1 : 0;
   a.outside = outside ? 1 : 0;
   a.C = c.C;
@@ -558,6 +579,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   int G0 = 0, max_sent0 = 0;
   if (fused) {
     fused_level_ok(c, g.c.N, geom0);
+    widen_if_crowded(c, B * (n - level), g.c.N, 148 / chain_count(c), geom0);
     G0 = lvl::level_cells_per_tile(B * (n - level), g.c.N, n - level, 0, geom0, (148 / geom0.nc) / chain_count(c), max_sent0);
     max_sent0 = G0 > 0 ? (G0 - 1) / (n - level) + 2 : 0;
   }
@@ -571,14 +593,15 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   if (!cells_inline) CL_TRY(launch_cell_bwd<VL>(c, g, fused ? nullptr : bws + (OUTSIDE ? c.L.CSout : c.L.CSin)));
   if (g.c.E == nullptr) return CLIORA_OK;  // leaf level: no splits
   if (fused) {
-    lvl::LevelGeom geom;
-    fused_level_ok(c, g.c.N, geom);
+    const lvl::LevelGeom geom = geom0;               // narrow, or wide when the level is crowded (see above)
     const bool sh = c.d.share != 0;
     lvl::LevelBwdArgs b{};
     lvl::LevelFwdArgs& a = b.geo;
     a.B = B; a.n = n; a.level = level; a.L = n - level; a.N = g.c.N; a.D = D; a.R = 0;
     a.cells = B * a.L;
     a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
+    a.single_acc = (a.n_umma > lvl::kNarrowUmmaN) ? 1 : 0;
+    a.store_lo = c.lvl_mode == 2 ? 1 : 0;
     int max_sent = 0;
     a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, (148 / geom.nc) / chain_count(c), max_sent);
     a.mode = c.lvl_mode;

@@ -51,15 +51,19 @@ constexpr int kCopyRowsPerPass = kCopyWarps * 4;         // tile rows one pass o
 constexpr int kCopyIters = kRows / kCopyRowsPerPass;      // copies per thread, operand and k-block
 constexpr int kThreads = (kCopyWarp0 + kCopyWarps) * 32;   // 576
 constexpr int kMaxCluster = 8;
-constexpr int kMaxUmmaN = 112;
+constexpr int kMaxUmmaN = 208;          // wide tiles: two column slices of a 400-wide level (single accumulator)
+constexpr int kNarrowUmmaN = 112;       // up to here: main + cross accumulator, four raw stages
+constexpr int kMaxD = 896;
 constexpr int kABytes = kRows * 128;  // one 128 x 32 fp32 operand tile
 // extras after the operand rings: barriers (256 B), b2 (128 f), e, p, nrm, nrm2 (4 x 128 f), three [8][128] exchange
 // buffers, the global row of every tile row (int64)
-constexpr int kExtraFloats = 128 + 4 * 128 + 3 * kMaxCluster * 128;
+constexpr int kExtraFloats = 256 + 4 * 128 + 3 * kMaxCluster * 128;
 constexpr int kExtraBytes = 256 + 4 * kExtraFloats + 8 * 128;
 // W2-slice ring (TMA): three stages when the slice is narrow, two otherwise (shared-memory budget)
 CL_HD int b_stages(int n_umma) { return n_umma <= 80 ? 3 : 2; }
-CL_HD int ring_bytes(int n_umma) { return kAStages * 2 * kABytes + b_stages(n_umma) * 2 * n_umma * 128; }
+// raw-operand stages of the A pipeline (32 KB each): the wide W2 slice leaves room for three
+CL_HD int raw_stages(int n_umma) { return n_umma > kNarrowUmmaN ? 3 : kAStages; }
+CL_HD int ring_bytes(int n_umma) { return raw_stages(n_umma) * 2 * kABytes + b_stages(n_umma) * 2 * n_umma * 128; }
 
 CL_D uint32_t cluster_ctarank() {
   uint32_t r;
@@ -141,6 +145,9 @@ struct LevelFwdArgs {
   int n_umma;    // ncols rounded up to 16 (<= kMaxUmmaN)
   int nc;        // cluster size = column slices
   int mode;      // 2: fp32-accurate 3xTF32 (main + cross accumulator), 1: single TF32 pass, 3: bf16 operands (fp32 accumulate)
+  int store_lo;    // the streamed-out operand pair (Z forward, GY backward) includes its lo part (0: the single-pass modes
+                   // never read it, the plain fp32 value is written -- the tensor core truncates it to tf32 by itself)
+  int single_acc;  // mode 2 with the cross terms accumulated into the main accumulator (wide tiles: 2 x n_umma > 256 columns)
   int outside;
   int64_t C;
   // first / second operand of a split: inside (left, right) both from the inside chart; outside (sibling from the
@@ -278,7 +285,7 @@ CL_D void cp_async_arrive_noinc(uint64_t* bar) {
 template <class OffFn, class StoreFn, class EndFn>
 CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int num_kb, int D, const float* base_a,
                      const float* base_b, OffFn offs, int store_turn0, int store_every, StoreFn store, EndFn store_end,
-                     long long* dbg = nullptr) {
+                     int nraw, long long* dbg = nullptr) {
   const int gt = threadIdx.x - kCopyWarp0 * 32;          // 0 .. 32 kCopyWarps - 1
   const int c = gt & 7, rbase = gt >> 3;
   uint32_t oa[kCopyIters], ob[kCopyIters];
@@ -297,7 +304,7 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
   // the thread that copied it, right before the stage is refilled -- coalesced (eight lanes per 128-byte row slice).
   auto flush = [&](int kp) {
     if (store_every <= 0 || (kp % store_every) != store_turn0) return;
-    const uint8_t* sA = smem + (kp % kAStages) * 2 * kABytes + soff0;
+    const uint8_t* sA = smem + (kp % nraw) * 2 * kABytes + soff0;
     const int kc = kp * 32 + c * 4;
     const bool live = kc < D;
 #pragma unroll
@@ -311,14 +318,14 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
     store_end(kc, live);          // reached by every lane of the warp
   };
   for (int kb = 0; kb < num_kb; ++kb) {
-    const int stage = kb % kAStages;
-    mbar_wait(&raw_empty[stage], ((kb / kAStages) & 1) ^ 1);
+    const int stage = kb % nraw;
+    mbar_wait(&raw_empty[stage], ((kb / nraw) & 1) ^ 1);
     if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[56 + (kb - 4) * 2] = clock_now();
-    if (kb >= kAStages) {
+    if (kb >= nraw) {
       // raw_empty[stage] implies raw_full[stage] of k-block kb - 4 completed, i.e. every copy of it (this thread's
       // included) has landed and is visible: no cp.async.wait_group needed before reading the stage back
       if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[64 + (kb - 4) * 4] = clock_now();
-      flush(kb - kAStages);
+      flush(kb - nraw);
       if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[65 + (kb - 4) * 4] = clock_now();
     }
     const int kcol = kb * 32 + c * 4;
@@ -335,25 +342,26 @@ CL_D void copy_a_raw(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, int
     if (dbg && gt == 0 && kb >= 4 && kb < 8) dbg[57 + (kb - 4) * 2] = clock_now();
   }
   cp_async_wait_all();
-  for (int kp = (num_kb > kAStages ? num_kb - kAStages : 0); kp < num_kb; ++kp) flush(kp);
+  for (int kp = (num_kb > nraw ? num_kb - nraw : 0); kp < num_kb; ++kp) flush(kp);
 }
 
 template <class XformFn>
 CL_D void transform_a_tmem(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empty, uint64_t* fullA, uint64_t* emptyA,
-                           uint32_t tmem_base, int num_kb, int mode, XformFn xform, long long* dbg = nullptr,
+                           uint32_t tmem_base, int num_kb, int mode, int nraw, XformFn xform, long long* dbg = nullptr,
                            uint16_t* zb_row = nullptr, int zb_turn0 = 0, int zb_every = 1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qd = warp & 3, half = (warp - kProdWarp0) >> 2;
   const int row = qd * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
   for (int kb = 0; kb < num_kb; ++kb) {
-    const int stage = kb % kAStages;
+    const int stage = kb % kAStages;                        // tensor-memory stage
     const uint32_t phase = (kb / kAStages) & 1;
+    const int rstage = kb % nraw;                           // raw shared-memory stage
     const bool st_ = dbg != nullptr && threadIdx.x == kProdWarp0 * 32 && kb >= 4 && kb < 8;
     if (st_) dbg[32 + (kb - 4) * 6] = clock_now();
-    mbar_wait(&raw_full[stage], phase);                     // the raw rows of k-block kb have landed
+    mbar_wait(&raw_full[rstage], (kb / nraw) & 1);          // the raw rows of k-block kb have landed
     if (st_) dbg[33 + (kb - 4) * 6] = clock_now();
-    const uint8_t* sA = smem + stage * 2 * kABytes + row * 128;
+    const uint8_t* sA = smem + rstage * 2 * kABytes + row * 128;
     const int k0 = kb * 32 + half * 16;
     float4 xa[4], xb[4];
 #pragma unroll
@@ -376,7 +384,7 @@ CL_D void transform_a_tmem(uint8_t* smem, uint64_t* raw_full, uint64_t* raw_empt
       zb_row[kb * 2 + half] = (uint16_t)bits;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive_local(&raw_empty[stage]);   // raw stage read: the copy warps may refill it
+    if (lane == 0) mbar_arrive_local(&raw_empty[rstage]);  // raw stage read: the copy warps may refill it
     if (st_) dbg[34 + (kb - 4) * 6] = clock_now();
     mbar_wait(&emptyA[stage], phase ^ 1);                   // the MMAs that read this TMEM stage have retired
     tcgen05_fence_after();
@@ -419,7 +427,8 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   const int b_bytes = a.n_umma * 128;
   const int nbs = b_stages(a.n_umma);
   const int a_stage_bytes = 2 * kABytes, b_stage_bytes = 2 * b_bytes;
-  uint8_t* ringB = smem + kAStages * a_stage_bytes;
+  const int nraw = A_TMEM ? raw_stages(a.n_umma) : kAStages;
+  uint8_t* ringB = smem + nraw * a_stage_bytes;
   const int cells_here = min(a.G, a.cells - tile * a.G);
   const int nc = a.nc, ncols = a.ncols, N = a.N;
   long long* dbg_row = a.dbg ? a.dbg + ((int64_t)blockIdx.y * a.nc + rank) * 128 : nullptr;
@@ -437,7 +446,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   uint64_t* raw_empty = raw_full + kAStages;      // raw stage read by the transform warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kAStages);
   float* s_b2 = reinterpret_cast<float*>(ex + 256);
-  float* s_e = s_b2 + 128;
+  float* s_e = s_b2 + 256;
   float* s_p = s_e + 128;
   float* s_nrm = s_p + 128;
   float* s_nrm2 = s_nrm + 128;
@@ -472,7 +481,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 128; i += kThreads) s_b2[i] = (i < ncols && n0 + i < D) ? a.b2[n0 + i] : 0.f;
+  for (int i = tid; i < 256; i += kThreads) s_b2[i] = (i < ncols && n0 + i < D) ? a.b2[n0 + i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -542,6 +551,10 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           if (A_TMEM) {
             if (a.mode == 1) {
               umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, acc);
+            } else if (a.single_acc) {
+              umma_tf32_ts(tmem_base, ta_lo + 8 * k, b_hi + 2 * k, idesc, acc);
+              umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+              umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, 1);
             } else {
               umma_tf32_ts(tmem_base + a.n_umma, ta_lo + 8 * k, b_hi + 2 * k, idesc, acc);
               umma_tf32_ts(tmem_base + a.n_umma, ta_hi + 8 * k, b_lo + 2 * k, idesc, 1);
@@ -582,14 +595,19 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
           // the Z pair of k-block kb (for the dW2 GEMM of the backward pass) is streamed out by CTA kb % nc
           rank, (a.Z != nullptr && !(a.exp_flags & 2)) ? nc : 0,
           [&](int r, int kc, const float4& xa, const float4& xb) {
-            float4 hi, lo;
-            split_trunc(fmaxf(xa.x + xb.x, 0.f), hi.x, lo.x); split_trunc(fmaxf(xa.y + xb.y, 0.f), hi.y, lo.y);
-            split_trunc(fmaxf(xa.z + xb.z, 0.f), hi.z, lo.z); split_trunc(fmaxf(xa.w + xb.w, 0.f), hi.w, lo.w);
+            const float4 o = make_float4(fmaxf(xa.x + xb.x, 0.f), fmaxf(xa.y + xb.y, 0.f), fmaxf(xa.z + xb.z, 0.f),
+                                         fmaxf(xa.w + xb.w, 0.f));
             float* dst = a.Z + zo[r / kCopyRowsPerPass] + kc;
-            st4(dst, hi);
-            st4(dst + a.z_lo_off, lo);
+            if (!a.store_lo) {
+              __stcs(reinterpret_cast<float4*>(dst), o);                 // streamed out once, read by the dW2 GEMM much later
+            } else {
+              float4 hi, lo;
+              split_trunc(o.x, hi.x, lo.x); split_trunc(o.y, hi.y, lo.y); split_trunc(o.z, hi.z, lo.z); split_trunc(o.w, hi.w, lo.w);
+              __stcs(reinterpret_cast<float4*>(dst), hi);
+              __stcs(reinterpret_cast<float4*>(dst + a.z_lo_off), lo);
+            }
           },
-          [](int, bool) {}, dbg_row);
+          [](int, bool) {}, nraw, dbg_row);
     }
   } else if (warp >= kProdWarp0 && A_TMEM) {
     // ------------------------------------------------------------ A operand -> tensor memory (see transform_a_tmem)
@@ -601,7 +619,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       if (ri.ok) zb_row = a.zbits + ri.m * 32;
     }
     transform_a_tmem(
-        smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode,
+        smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode, nraw,
         [&](const float4& xa, const float4& xb, int kc) {
           (void)kc;
           return make_float4(fmaxf(xa.x + xb.x, 0.f), fmaxf(xa.y + xb.y, 0.f), fmaxf(xa.z + xb.z, 0.f),
@@ -735,31 +753,43 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
       const int g1_i = (int)ri.g1, g2_i = (int)ri.g2;     // chart rows fit 32 bits
 #pragma unroll 1
       for (int grp = 0; grp < 8; grp += 2) {
-        float4 hv[2][4], vv[2][4];
+        float parts[2] = {0.f, 0.f};
         bool okr[2];
+        const float* hp[2];
+        const float* vp[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int src_lane = (grp + u) * 4 + rr;
           okr[u] = __shfl_sync(0xffffffffu, ok_i, src_lane) != 0;
           const int r1 = __shfl_sync(0xffffffffu, g1_i, src_lane), r2 = __shfl_sync(0xffffffffu, g2_i, src_lane);
-          const float* hp = a.h1 + (int64_t)r1 * D + n0;
-          const float* vp = a.P2 + (int64_t)r2 * a.ld2 + a.off_v2 + n0;
+          hp[u] = a.h1 + (int64_t)r1 * D + n0;
+          vp[u] = a.P2 + (int64_t)r2 * a.ld2 + a.off_v2 + n0;
+        }
+#pragma unroll 1
+        for (int cb0 = 0; cb0 < nch; cb0 += 32) {         // 32 chunks (128 columns) per batch; wide slices take two
+          float4 hv[2][4], vv[2][4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ch = c + 8 * t;
-            const bool ld = okr[u] && ch < nch && n0 + ch * 4 < D && !(a.exp_flags & 16);
-            hv[u][t] = ld ? ldcg4(hp + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            vv[u][t] = ld ? ldcg4(vp + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int ch = cb0 + c + 8 * t;
+              const bool ld = okr[u] && ch < nch && n0 + ch * 4 < D && !(a.exp_flags & 16);
+              hv[u][t] = ld ? ldcg4(hp[u] + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              vv[u][t] = ld ? ldcg4(vp[u] + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              parts[u] = fmaf(hv[u][t].x, vv[u][t].x, parts[u]); parts[u] = fmaf(hv[u][t].y, vv[u][t].y, parts[u]);
+              parts[u] = fmaf(hv[u][t].z, vv[u][t].z, parts[u]); parts[u] = fmaf(hv[u][t].w, vv[u][t].w, parts[u]);
+            }
           }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          float part = 0.f;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            part = fmaf(hv[u][t].x, vv[u][t].x, part); part = fmaf(hv[u][t].y, vv[u][t].y, part);
-            part = fmaf(hv[u][t].z, vv[u][t].z, part); part = fmaf(hv[u][t].w, vv[u][t].w, part);
-          }
+          float part = parts[u];
           part += __shfl_xor_sync(0xffffffffu, part, 1);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
           part += __shfl_xor_sync(0xffffffffu, part, 4);
@@ -813,7 +843,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
   const bool vl = a.R > 0;
   const int R = a.R;
   const int GRs = a.G * R, GRp = (GRs + 3) & ~3;
-  float* s_att = s_a + kRows * ncols;            // [G][R] logits -> attention weights
+  float* s_att = s_a + a.G * ncols;              // [G][R] logits -> attention weights
   float* s_patt = s_att + GRp;                   // [G][R] dropout-scaled weights
   float* s_keep = s_patt + GRp;                  // [G][R] dropout scale of every (cell, region): 0 or 1 / (1 - p)
   float* s_obj = s_keep + GRp;                   // [max_sent][R][stride]: this CTA's column slice of the tile's images
@@ -843,7 +873,7 @@ level_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelFwdArgs a) 
     for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);    // warp-collective: no early exit
-      if (a.mode == 2) {
+      if (a.mode == 2 && !a.single_acc) {
         float x[16];
         tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a.n_umma + c0), x);
 #pragma unroll
@@ -1082,9 +1112,9 @@ struct LevelBwdArgs {
   int vl_R;
 };
 
-constexpr int kBwdDb2Floats = kMaxCluster * kMaxUmmaN;   // D <= 896
-// barriers, row ids, p/cell/d0/d1/ge, chart rows of first/second, ReLU bit masks [128][4], db2 partial sums [D]
-constexpr int kBwdExtraBytes = 256 + 128 * 8 + 4 * (128 * 5 + 128) + 4 * 256 + 4 * 512 + 4 * kBwdDb2Floats;
+constexpr int kBwdDb2Floats = kMaxD;
+// barriers, row ids, p/cell/d0/d1/ge, chart rows of first/second, ReLU bit masks [128][8], db2 partial sums [D]
+constexpr int kBwdExtraBytes = 256 + 128 * 8 + 4 * (128 * 5 + 128) + 4 * 256 + 4 * 1024 + 4 * kBwdDb2Floats;
 
 template <int DUMMY>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -1103,7 +1133,8 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   const int b_bytes = a.n_umma * 128;
   const int nbs = b_stages(a.n_umma);
   const int a_stage_bytes = 2 * kABytes, b_stage_bytes = 2 * b_bytes;
-  uint8_t* ringB = smem + kAStages * a_stage_bytes;
+  const int nraw = raw_stages(a.n_umma);
+  uint8_t* ringB = smem + nraw * a_stage_bytes;
   const int cells_here = min(a.G, a.cells - tile * a.G);
   const int nc = a.nc, ncols = a.ncols;
   long long* dbg_row = a.dbg ? a.dbg + ((int64_t)blockIdx.y * a.nc + rank) * 128 : nullptr;
@@ -1126,8 +1157,8 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   float* s_ge = s_d + 256;                                           // [128]
   int* s_g1 = reinterpret_cast<int*>(s_ge + 256);                    // [128] chart row (b*C + c) of `first`
   int* s_g2 = s_g1 + 128;                                            // [128] chart row of `second`
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_g2 + 128);        // [128][4] ReLU bits of this CTA's columns of z
-  float* s_db2 = reinterpret_cast<float*>(s_mask + 512);             // [D] column sums of the GY k-blocks this CTA streams
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_g2 + 128);        // [128][8] ReLU bits of this CTA's columns of z
+  float* s_db2 = reinterpret_cast<float*>(s_mask + 1024);             // [D] column sums of the GY k-blocks this CTA streams
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmW);
   if (warp == 1) {
@@ -1363,6 +1394,10 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
         for (int k = 0; k < 4; ++k) {
           if (a.mode == 1) {
             umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, acc);
+          } else if (a.single_acc) {
+            umma_tf32_ts(tmem_base, ta_lo + 8 * k, b_hi + 2 * k, idesc, acc);
+            umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+            umma_tf32_ts(tmem_base, ta_hi + 8 * k, b_hi + 2 * k, idesc, 1);
           } else {
             umma_tf32_ts(tmem_base + a.n_umma, ta_lo + 8 * k, b_hi + 2 * k, idesc, acc);
             umma_tf32_ts(tmem_base + a.n_umma, ta_hi + 8 * k, b_lo + 2 * k, idesc, 1);
@@ -1392,12 +1427,16 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
           const float4 o = make_float4(y.x > 0.f ? pr * ga.x : 0.f, y.y > 0.f ? pr * ga.y : 0.f,
                                        y.z > 0.f ? pr * ga.z : 0.f, y.w > 0.f ? pr * ga.w : 0.f);
           csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
-          float4 hi, lo;
-          split_trunc(o.x, hi.x, lo.x); split_trunc(o.y, hi.y, lo.y);
-          split_trunc(o.z, hi.z, lo.z); split_trunc(o.w, hi.w, lo.w);
           float* dst = g.GYp + s_m[r] * D + kc;
-          st4(dst, hi);
-          st4(dst + g.gy_lo_off, lo);
+          if (!a.store_lo) {
+            __stcs(reinterpret_cast<float4*>(dst), o);
+          } else {
+            float4 hi, lo;
+            split_trunc(o.x, hi.x, lo.x); split_trunc(o.y, hi.y, lo.y);
+            split_trunc(o.z, hi.z, lo.z); split_trunc(o.w, hi.w, lo.w);
+            __stcs(reinterpret_cast<float4*>(dst), hi);
+            __stcs(reinterpret_cast<float4*>(dst + g.gy_lo_off), lo);
+          }
         },
         // db2 += column sums of GY: this thread's rows of the four columns it streamed, combined in shared memory
         [&](int kc, bool live) {
@@ -1412,14 +1451,15 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
             atomicAdd(s_db2 + kc + 2, csum.z); atomicAdd(s_db2 + kc + 3, csum.w);
           }
           csum = make_float4(0.f, 0.f, 0.f, 0.f);
-        });
+        },
+        nraw);
   } else if (warp >= kProdWarp0) {
     // ---- A operand: gy = p * ga * [y > 0] -> tensor memory (see transform_a_tmem); d = y . ga on the side
     const int row = (warp & 3) * 32 + lane, half = (warp - kProdWarp0) >> 2;
     const float prow = s_p[row];
     float dpart = 0.f;
     transform_a_tmem(
-        smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode,
+        smem, raw_full, raw_empty, fullA, emptyA, tmem_base, num_kb, a.mode, nraw,
         [&](const float4& y, const float4& ga, int kc) {
           dpart = fmaf(y.x, ga.x, dpart); dpart = fmaf(y.y, ga.y, dpart);
           dpart = fmaf(y.z, ga.z, dpart); dpart = fmaf(y.w, ga.w, dpart);
@@ -1434,20 +1474,20 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     const int r = tid - 64;            // 0..127
     const long long m = s_m[r];
     const int nch = ncols >> 2;
-    uint32_t mk[4] = {0u, 0u, 0u, 0u};
+    uint32_t mk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     if (m >= 0 && g.zbits != nullptr) {
-      // 64 bytes of sign bits per row: the bits of columns n0 .. n0 + 127 are funnel-shifted out of five words
+      // 64 bytes of sign bits per row: the bits of columns n0 .. n0 + 255 are funnel-shifted out of nine words
       const uint32_t* wrow = reinterpret_cast<const uint32_t*>(g.zbits + m * 32);
       const int w0 = n0 >> 5, sh = n0 & 31;
-      uint32_t wv[5];
+      uint32_t wv[9];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) wv[q] = (w0 + q < 16) ? __ldcg(wrow + w0 + q) : 0u;
+      for (int q = 0; q < 9; ++q) wv[q] = (w0 + q < 16 && q * 32 < ncols + 32) ? __ldcg(wrow + w0 + q) : 0u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) mk[q] = __funnelshift_r(wv[q], wv[q + 1], sh);
+      for (int q = 0; q < 8; ++q) mk[q] = __funnelshift_r(wv[q], wv[q + 1], sh);
     } else if (m >= 0) {
       const float* zrow = g.Zhi + m * D + n0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         if (q * 8 < nch) {
           float4 z[8];
 #pragma unroll
@@ -1464,7 +1504,8 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
         }
       }
     }
-    *reinterpret_cast<uint4*>(s_mask + r * 4) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+    *reinterpret_cast<uint4*>(s_mask + r * 8) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+    *reinterpret_cast<uint4*>(s_mask + r * 8 + 4) = make_uint4(mk[4], mk[5], mk[6], mk[7]);
     LB_STAMP(2);
   }
 
@@ -1478,19 +1519,7 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
   // memory), so that the scatter below issues coalesced reductions (one row slice per warp instruction) and never waits
   // on a global load.
   const int nch = ncols >> 2;
-  const int pitch = (nch & 1) ? ncols : ncols + 4;           // pitch / 4 odd: conflict-free 16-byte row accesses
-  float* s_gz = reinterpret_cast<float*>(smem);              // [128][pitch] masked GZ
-  float* s_h = s_gz + kRows * pitch;                         // [128][pitch] h[first] slice
-  float* s_v = s_h + kRows * pitch;                          // [128][pitch] V[second] slice
   const int rows_here = cells_here * a.N;
-  for (int idx = tid; idx < rows_here * nch; idx += kThreads) {
-    const int r = idx / nch, ch = idx - r * nch;
-    if (n0 + ch * 4 < D) {
-      cp_async16(s_h + r * pitch + ch * 4, g.h1 + (int64_t)s_g1[r] * D + n0 + ch * 4);
-      cp_async16(s_v + r * pitch + ch * 4, g.P2 + (int64_t)s_g2[r] * g.ld2 + g.off_v2 + n0 + ch * 4);
-    }
-  }
-  cp_async_commit();
   if (tid < 128) {
     // ge = p (gs + gp - cm), gp = y . ga + e gs      (softmax-weighted-sum backward)
     const long long m = s_m[tid];
@@ -1515,61 +1544,79 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
       s_ge[tid] = m >= 0 ? s_p[tid] * (g.Gs[s_cell[tid]] + (ge - cm2)) : 0.f;
     }
   }
-  if (warp >= 2) {
-    // GZ = acc * [z > 0] -> shared memory, row-major
-    constexpr int kSub = (kThreads / 32 - 2) / 4;
-    const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
-    const uint4 mk4 = *reinterpret_cast<const uint4*>(s_mask + r * 4);
-    const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
-#pragma unroll 1
-    for (int c0 = sub * 16; c0 < a.n_umma; c0 += 16 * kSub) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
-      if (a.mode == 2) {
-        float x[16];
-        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a.n_umma + c0), x);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += x[i];
+  // Column passes: a narrow slice (<= 112 columns) fits the rings in one pass, a wide one takes two of 112 + the rest.
+  const int pass_cols = ncols > kNarrowUmmaN ? kNarrowUmmaN : ncols;        // multiple of 16 when it is not everything
+  const int pch = pass_cols >> 2;
+  const int pitch = (pch & 1) ? pass_cols : pass_cols + 4;    // pitch / 4 odd: conflict-free 16-byte row accesses
+  float* s_gz = reinterpret_cast<float*>(smem);              // [128][pitch] masked GZ
+  float* s_h = s_gz + kRows * pitch;                         // [128][pitch] h[first] slice
+  float* s_v = s_h + kRows * pitch;                          // [128][pitch] V[second] slice
+  for (int cbeg = 0; cbeg < ncols; cbeg += pass_cols) {
+    const int cw = min(pass_cols, ncols - cbeg), cwch = cw >> 2;
+    if (cbeg > 0) __syncthreads();                           // the previous pass has been scattered
+    for (int idx = tid; idx < rows_here * cwch; idx += kThreads) {
+      const int r = idx / cwch, ch = idx - r * cwch;
+      const int col = cbeg + ch * 4;
+      if (n0 + col < D) {
+        cp_async16(s_h + r * pitch + ch * 4, g.h1 + (int64_t)s_g1[r] * D + n0 + col);
+        cp_async16(s_v + r * pitch + ch * 4, g.P2 + (int64_t)s_g2[r] * g.ld2 + g.off_v2 + n0 + col);
       }
-      const uint32_t word = (c0 >> 5) == 0 ? mk[0] : (c0 >> 5) == 1 ? mk[1] : (c0 >> 5) == 2 ? mk[2] : mk[3];
-      const uint32_t bits16 = (word >> (c0 & 31)) & 0xffffu;      // c0 is a multiple of 16
+    }
+    cp_async_commit();
+    if (warp >= 2) {
+      // GZ = acc * [z > 0] -> shared memory, row-major
+      constexpr int kSub = (kThreads / 32 - 2) / 4;
+      const int qd = warp & 3, r = qd * 32 + lane, sub = (warp - 2) >> 2;
+      const uint32_t* mrow = s_mask + r * 8;
+#pragma unroll 1
+      for (int c0 = cbeg + sub * 16; c0 < min(cbeg + cw, a.n_umma); c0 += 16 * kSub) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
+        if (a.mode == 2 && !a.single_acc) {
+          float x[16];
+          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a.n_umma + c0), x);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const int col = c0 + j;
-        if (col < ncols) {
-          const uint32_t b = bits16 >> j;
-          st4(s_gz + r * pitch + col, make_float4((b & 1u) ? v[j] : 0.f, (b & 2u) ? v[j + 1] : 0.f,
-                                                  (b & 4u) ? v[j + 2] : 0.f, (b & 8u) ? v[j + 3] : 0.f));
+          for (int i = 0; i < 16; ++i) v[i] += x[i];
+        }
+        const uint32_t bits16 = (mrow[c0 >> 5] >> (c0 & 31)) & 0xffffu;      // c0 is a multiple of 16
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int col = c0 + j;
+          if (col < ncols) {
+            const uint32_t b = bits16 >> j;
+            st4(s_gz + r * pitch + col - cbeg, make_float4((b & 1u) ? v[j] : 0.f, (b & 2u) ? v[j + 1] : 0.f,
+                                                           (b & 4u) ? v[j + 2] : 0.f, (b & 8u) ? v[j + 3] : 0.f));
+          }
         }
       }
     }
-  }
-  cp_async_wait_all();
-  tcgen05_fence_before();
-  __syncthreads();
-  LB_STAMP(4);
-  // scatter (red.global.add, as split_scatter did): GP[first].A += GZ, GP[second].A += GZ, Gh[first] += ge V[second],
-  // GP[second].V += ge h[first], Gs[first] += ge, Gs[second] += ge.  Warp per row, lanes over the 16-byte chunks.
-  for (int r = warp; r < rows_here; r += kThreads / 32) {
-    const int64_t g1 = s_g1[r], g2 = s_g2[r];
-    const float ge = s_ge[r];
-    float* d1 = g.GP1 + g1 * g.ld1 + g.off_a1 + n0;
-    float* d2 = g.GP2 + g2 * g.ld2 + g.off_a2 + n0;
-    float* gh = g.Gh1 + g1 * D + n0;
-    float* gv = g.GP2 + g2 * g.ld2 + g.off_v2 + n0;
-    for (int ch = lane; ch < nch; ch += 32) {
-      if (n0 + ch * 4 < D) {
-        const float4 gz = ld4(s_gz + r * pitch + ch * 4);
-        const float4 hv = ld4(s_h + r * pitch + ch * 4), vv = ld4(s_v + r * pitch + ch * 4);
-        red_add4(d1 + ch * 4, gz);
-        red_add4(d2 + ch * 4, gz);
-        red_add4(gh + ch * 4, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
-        red_add4(gv + ch * 4, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
+    cp_async_wait_all();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (cbeg == 0) LB_STAMP(4);
+    // scatter (red.global.add, as split_scatter did): GP[first].A += GZ, GP[second].A += GZ, Gh[first] += ge V[second],
+    // GP[second].V += ge h[first], Gs[first] += ge, Gs[second] += ge.  Warp per row, lanes over the 16-byte chunks.
+    for (int r = warp; r < rows_here; r += kThreads / 32) {
+      const int64_t g1 = s_g1[r], g2 = s_g2[r];
+      const float ge = s_ge[r];
+      float* d1 = g.GP1 + g1 * g.ld1 + g.off_a1 + n0 + cbeg;
+      float* d2 = g.GP2 + g2 * g.ld2 + g.off_a2 + n0 + cbeg;
+      float* gh = g.Gh1 + g1 * D + n0 + cbeg;
+      float* gv = g.GP2 + g2 * g.ld2 + g.off_v2 + n0 + cbeg;
+      for (int ch = lane; ch < cwch; ch += 32) {
+        if (n0 + cbeg + ch * 4 < D) {
+          const float4 gz = ld4(s_gz + r * pitch + ch * 4);
+          const float4 hv = ld4(s_h + r * pitch + ch * 4), vv = ld4(s_v + r * pitch + ch * 4);
+          red_add4(d1 + ch * 4, gz);
+          red_add4(d2 + ch * 4, gz);
+          red_add4(gh + ch * 4, make_float4(ge * vv.x, ge * vv.y, ge * vv.z, ge * vv.w));
+          red_add4(gv + ch * 4, make_float4(ge * hv.x, ge * hv.y, ge * hv.z, ge * hv.w));
+        }
       }
-    }
-    if (lane == 0 && rank == 0) {
-      atomicAdd(g.Gs1 + g1, ge);
-      atomicAdd(g.Gs2 + g2, ge);
+      if (lane == 0 && rank == 0 && cbeg == 0) {
+        atomicAdd(g.Gs1 + g1, ge);
+        atomicAdd(g.Gs2 + g2, ge);
+      }
     }
   }
   // db2 += the column sums of the GY k-blocks this CTA streamed out
@@ -1590,18 +1637,23 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
 struct LevelGeom {
   int nc, ncols, n_umma;
 };
-inline bool level_geom(int D, LevelGeom& g) {
+// wide = false: column slices of <= 112 (latency-optimal: four CTAs share a tile of a 400-wide level);
+// wide = true: slices of <= 208 (half the CTAs and half the replicated operand gathers per tile: for levels that do not
+// fit one wave anyway).  Wide tiles accumulate the 3xTF32 cross terms into the main accumulator (tensor memory:
+// n_umma + 256 operand columns <= 512).
+inline bool level_geom(int D, LevelGeom& g, bool wide = false) {
   if (D < 32 || (D % 4) != 0) return false;
+  const int cap = wide ? kMaxUmmaN : kNarrowUmmaN;
   // power-of-two clusters pack the GPCs best (measured: 26 clusters of 5 are co-resident on a B200, 33 of 4)
   int nc = 1;
-  while (nc <= kMaxCluster && ceil_div(D, nc) > kMaxUmmaN) nc *= 2;
+  while (nc <= kMaxCluster && ceil_div(D, nc) > cap) nc *= 2;
   if (nc > kMaxCluster) return false;
-  if (g_debug[11] > 0 && g_debug[11] <= kMaxCluster && ceil_div(D, g_debug[11]) <= kMaxUmmaN) nc = g_debug[11];
+  if (!wide && g_debug[11] > 0 && g_debug[11] <= kMaxCluster && ceil_div(D, g_debug[11]) <= cap) nc = g_debug[11];
   int ncols = ((ceil_div(D, nc) + 3) / 4) * 4;
   g.nc = nc;
   g.ncols = ncols;
   g.n_umma = ((ncols + 15) / 16) * 16;
-  return g.n_umma <= kMaxUmmaN;
+  return g.n_umma <= cap;
 }
 // clusters of this shape that can be resident at once (cached per device and shape)
 int max_active_clusters(int nc, size_t smem);
@@ -1620,11 +1672,12 @@ inline int level_cells_per_tile(int cells, int N, int L, int R, const LevelGeom&
     const int64_t area = (int64_t)ring_bytes(g.n_umma) / 4;     // floats in the operand rings
     for (; G >= 1; --G) {
       max_sent = (G - 1) / L + 2;
-      const int64_t need = (int64_t)kRows * (g.ncols + 4) + (int64_t)kRows * g.ncols + 3 * ((G * R + 3) & ~3) +
+      const int64_t need = (int64_t)kRows * (g.ncols + 4) + (int64_t)G * g.ncols + 3 * ((G * R + 3) & ~3) +
                            (int64_t)max_sent * R * (g.ncols + 4) + (int64_t)g.nc * G * R;
       if (need <= area) break;
     }
   }
+  if ((int64_t)kRows * (g.ncols + 4) + (int64_t)G * g.ncols > (int64_t)ring_bytes(g.n_umma) / 4) return 0;
   return G;
 }
 inline size_t level_fwd_smem(int n_umma);

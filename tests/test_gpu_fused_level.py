@@ -92,3 +92,18 @@ def test_fused_level_forward_matches_unfused_chain(B, n, D, R, share, train):
                 assert flipped <= max(2, int(1e-5 * count * 32)), (name, flipped)
     for k in ref:
         assert rel_err(got[k], ref[k]) < 2e-5, k
+
+
+@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 6, 132, 4, True),
+                                           (2, 20, 400, 36, True)])
+def test_wide_level_tiles_stay_parity_green(B, n, D, R, share):
+    """Levels that do not fit one wave run with wide column slices (two CTAs per tile at D=400, single tensor-memory
+    accumulator, three raw stages, two-pass backward epilogue).  Forced on for every level here: forward and every
+    gradient against the float64 oracle, exactly like the default geometry."""
+    from cliora_b200 import _lib
+    from test_gpu_chart import test_chart_vs_oracle_live
+    _lib.lib().cliora_debug_set(15, 2)
+    try:
+        test_chart_vs_oracle_live(B, n, D, R, share)
+    finally:
+        _lib.lib().cliora_debug_set(15, 0)
