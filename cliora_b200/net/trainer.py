@@ -273,6 +273,8 @@ class Trainer(object):
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         if self.grad_sync is not None:
+            if hasattr(self.grad_sync, 'unbind_flat') and not torch.cuda.is_current_stream_capturing():
+                self.grad_sync.unbind_flat()      # eager step: fresh gradient tensors, reduced in place
             self.grad_sync()
         self._optimizer_update()
 
@@ -332,12 +334,20 @@ class Trainer(object):
                 self.gradient_update(self._static_loss)
             self._static_out = {k: v.detach() for k, v in out.items() if 'loss' in k}
         self.launches_per_step = _lib.launch_count() - before   # library kernels baked into the graph
+        self._flat_state = None
+        self._graph_grads = [p.grad for p in self.net.parameters() if p.requires_grad]
         if split:
             # no collective here: the captured backward has not run, its gradient tensors hold garbage, and a
-            # rank that captures while its peers replay would pair this call with their real all-reduce
+            # rank that captures while its peers replay would pair this call with their real all-reduce.
+            # The optimizer graph reads the parameters' gradients from ONE flat buffer (views): every replay packs
+            # the backward graph's gradient tensors into it and all-reduces it in a single call (parallel.py).
+            if hasattr(self.grad_sync, 'bind_flat') and os.environ.get('CLIORA_FLAT_ALLREDUCE', '1') != '0' and \
+                    all(g is not None for g in self._graph_grads) and \
+                    len(self._graph_grads) == len(getattr(self.grad_sync, 'params', ())):
+                self.grad_sync.bind_flat(self._graph_grads)
+                self._flat_state = (self.grad_sync._flat, self.grad_sync._flat_src, self.grad_sync._flat_views)
             with torch.cuda.graph(self._graph_opt, **gkw):
                 self._optimizer_update()
-        self._graph_grads = [p.grad for p in self.net.parameters() if p.requires_grad]
         self._static_loss = self._static_loss.detach()     # only its value is read from here on
         return self
 
@@ -348,7 +358,7 @@ class Trainer(object):
 
     # ---- graph replay for a stream of batches whose shape varies (length-bucketed training) ----
     _GRAPH_STATE = ('_static', '_graph', '_graph_opt', '_static_loss', '_static_out', 'launches_per_step',
-                    '_graph_grads')
+                    '_graph_grads', '_flat_state')
 
     @staticmethod
     def _shape_key(batch_map):
@@ -392,8 +402,9 @@ class Trainer(object):
             for k, v in entry.items():
                 setattr(self, k, v)
             params = [p for p in self.net.parameters() if p.requires_grad]
-            for prm, g in zip(params, entry['_graph_grads']):   # the tensors this graph's backward writes and
-                prm.grad = g                                    # the eager all-reduce (data parallel) reads
+            views = entry['_flat_state'][2] if entry.get('_flat_state') is not None else entry['_graph_grads']
+            for prm, g in zip(params, views):     # what this shape's optimizer graph reads: the flat buffer's views
+                prm.grad = g                      # (data parallel) or the tensors its backward graph writes
             self._active_key = key
         return self.step_graphed(batch_map).clone()
 
@@ -435,7 +446,9 @@ class Trainer(object):
                     self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
         if self._graph_opt is not None:
-            self.grad_sync()          # one flat fp32 all-reduce over NVLink (NCCL), then 1/N
+            if getattr(self, '_flat_state', None) is not None:      # this graph's own flat gradient buffer
+                self.grad_sync._flat, self.grad_sync._flat_src, self.grad_sync._flat_views = self._flat_state
+            self.grad_sync()          # pack + ONE fp32 all-reduce (AVG) over NVLink (NCCL)
             self._graph_opt.replay()
         return self._static_loss
 
@@ -495,5 +508,14 @@ def build_net(options, embeddings=None, random_seed=None):
         net.cuda()
         diora.cuda()
     trainer = Trainer(net, k_neg=options.k_neg, ngpus=1, cuda=options.cuda)
+    trainer.rank = getattr(options, 'local_rank', None)                 # trainer.py:578-579
+    trainer.experiment_name = getattr(options, 'experiment_name', None)
+    if getattr(options, 'multigpu', False):
+        # the reference wraps the net in DDP here (trainer.py:528-532,572-574); this package keeps the process group
+        # outside build_net: wrap with cliora_b200.parallel.GradSync.for_module(trainer.net, world) and set
+        # trainer.grad_sync -- say so instead of silently training unsynchronised replicas
+        import warnings
+        warnings.warn('options.multigpu is set: install trainer.grad_sync = GradSync.for_module(trainer.net, world_size) '
+                      '(cliora_b200.parallel) after init_process_group; build_net does not create process groups')
     trainer.init_optimizer(optim.Adam, dict(lr=options.lr, betas=(0.9, 0.999), eps=1e-8))
     return trainer

@@ -9,9 +9,10 @@ What DDP does and this mirrors:
   * every step, gradients are averaged over ranks before clip + Adam (trainer.py:450-455 run on identical
     gradients on every rank, so no further collective is needed).
 
-The all-reduce is one coalesced (ncclGroupStart/End) call over the gradient tensors IN PLACE: no flat staging
-buffer, no copy passes, the 1/N folded into the collective (ReduceOp.AVG).  Gradient tensors keep their addresses,
-so the call can sit between, or inside, CUDA graphs.
+Eager steps: one coalesced (ncclGroupStart/End) call over the gradient tensors IN PLACE, the 1/N folded into the
+collective (ReduceOp.AVG).  Graph replay (``bind_flat``): the parameters' ``.grad`` are views of one flat buffer, the
+backward graph's gradient tensors are packed into it by one multi-tensor copy, ONE all-reduce follows and clip + Adam
+read the views -- one copy pass, no copy back, no separate scaling.
 """
 import torch
 import torch.distributed as dist
@@ -49,8 +50,37 @@ class GradSync(object):
                 p.grad = torch.zeros_like(p)
         return [p.grad for p in self.params]
 
+    def bind_flat(self, src_grads):
+        """Graph replay: the backward graph always leaves its gradients in the same tensors ``src_grads``.  Give the
+        parameters ONE flat fp32 buffer instead: ``p.grad`` becomes a view of it (so clip + Adam read the reduced
+        values in place), each step packs ``src_grads`` into it with one multi-tensor copy and issues a SINGLE
+        all-reduce -- a grouped call over ~40 small tensors pays their latencies one after the other (measured at
+        8 GPUs: +0.37 ms per step against +0.1 ms for one 14.7 MB all-reduce).  Returns the views."""
+        assert len(src_grads) == len(self.params)
+        n = sum(g.numel() for g in src_grads)
+        self._flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._flat_src = list(src_grads)
+        self._flat_views, off = [], 0
+        for g in src_grads:
+            self._flat_views.append(self._flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        for p, v in zip(self.params, self._flat_views):
+            p.grad = v
+        return self._flat_views
+
+    def unbind_flat(self):
+        self._flat = self._flat_src = self._flat_views = None
+
     def __call__(self):
         if self.world <= 1:
+            return
+        if getattr(self, '_flat', None) is not None:
+            torch._foreach_copy_(self._flat_views, self._flat_src)
+            if self._avg:
+                dist.all_reduce(self._flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+                self._flat.mul_(1.0 / self.world)
             return
         grads = self._grads()
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM

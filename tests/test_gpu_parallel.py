@@ -59,6 +59,35 @@ def _worker(rank, world, port, out):
     for i in range(3):
         tr.step(_shard(cfg, rank + 2 * i, torch.device('cuda', rank)), train=True, sync_result=False)
     assert sync.in_sync()
+    # graph replay (flat gradient buffer + ONE all-reduce, parallel.GradSync.bind_flat) == eager data-parallel steps
+    import copy
+    from conftest import rel_err
+    trg, tr2 = _trainer(cfg, seed=98), _trainer(cfg, seed=99)      # fresh trainers (never stepped on the legacy stream)
+    for t in (trg, tr2):
+        t.net.load_state_dict(copy.deepcopy(tr.net.state_dict()))
+        t.init_optimizer()
+        t.grad_sync = GradSync.for_module(t.net, world)
+    dev = torch.device('cuda', rank)
+    batches = [_shard(cfg, 40 + rank + 2 * i, dev) for i in range(3)]
+    trg.capture(batches[0])                          # three real data-parallel warm-up steps on batches[0], then capture
+    assert trg._graph_opt is not None and trg._flat_state is not None
+    for _ in range(3):
+        tr2.step(batches[0], train=True, sync_result=False)
+    for i, b in enumerate(batches):
+        trg.step_graphed(b)
+        tr2.step(b, train=True, sync_result=False)
+        torch.cuda.synchronize()
+        # the averaged gradients clip + Adam consumed: flat-buffer views (graph) vs in-place reduced tensors (eager).
+        # (Weights alone would not show a wrong scale: Adam is scale-invariant.)  The two trainers' weights differ by
+        # the summation-order noise of earlier steps, amplified by Adam on noise-level entries (measured 1.2e-3), hence 1e-2; a missing 1/N would read 1.0.
+        g_graph = trg.grad_sync._flat_views
+        g_eager = [p.grad for p in tr2.net.parameters() if p.requires_grad]
+        worst = max(rel_err(a, b_) for a, b_ in zip(g_graph, g_eager))
+        assert worst < 1e-2, (i, worst)
+    errs = {k: rel_err(a, b) for (k, a), (_, b) in zip(trg.net.state_dict().items(), tr2.net.state_dict().items())}
+    assert max(errs.values()) < 5e-3, {k: v for k, v in errs.items() if v >= 5e-3}
+    assert trg.grad_sync.in_sync() and tr2.grad_sync.in_sync()
+    assert sync.in_sync()
     dist.barrier()
     dist.destroy_process_group()
 
