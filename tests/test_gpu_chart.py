@@ -146,7 +146,8 @@ def _oracle_run(dt, B, n, D, R, share, seed=8, mode='unit'):
     return P0, x, obj, keep, ct, res
 
 
-@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True)])
+@pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True),
+                                           (2, 6, 512, 4, True), (2, 5, 768, 0, False)])
 def test_chart_vs_oracle_live(B, n, D, R, share, chains=None):
     """Same seeded inputs through the CUDA path and the CPU oracle, fwd + bwd, at the real hidden size.
 
