@@ -107,3 +107,33 @@ def test_wide_level_tiles_stay_parity_green(B, n, D, R, share):
         test_chart_vs_oracle_live(B, n, D, R, share)
     finally:
         _lib.lib().cliora_debug_set(15, 0)
+
+
+@pytest.mark.parametrize('R,wide', [(36, False), (0, False), (36, True), (0, True)])
+def test_fused_forward_is_stable_across_runs(R, wide):
+    """Every shared-memory stage of the level kernels is handed over through mbarriers.  The same input must give the
+    same chart on every run up to the reordering noise of the projection GEMMs' split-K atomics (1e-7 per GEMM): a
+    race in one of those hand-overs would show as a wrong element, not as last-bit noise."""
+    from cliora_b200 import _lib
+    if R:
+        from cliora_b200.net.cliora import DioraMLP
+    else:
+        from cliora_b200.net.diora import DioraMLP
+    B, n, D = 8, 12, 400
+    torch.manual_seed(5)
+    m = DioraMLP(D).cuda().eval()
+    m.chains = 1
+    x = torch.randn(B, n, D, device='cuda')
+    obj = 0.05 * torch.randn(B, max(R, 1), D, device='cuda')
+    _lib.lib().cliora_debug_set(15, 2 if wide else 1)
+    try:
+        outs = []
+        for _ in range(6):
+            with torch.no_grad():
+                m(x, x, obj, obj) if R else m(x, x)
+            outs.append([t.clone() for t in (m.inside_h, m.inside_s, m.outside_h, m.outside_s)])
+        for o in outs[1:]:
+            for a, b in zip(outs[0], o):
+                assert rel_err(a, b) < 1e-5
+    finally:
+        _lib.lib().cliora_debug_set(15, 0)
