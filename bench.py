@@ -463,6 +463,19 @@ def main():
                   unit='sentences/s', steps=sub_steps)
         r5.pop('kernels', None)
         subs['c5'] = r5
+        if world == 1 and args.precision == 'fp32':
+            # the bf16-GEMM path (north_star: "a bf16-GEMM path with its own stated tolerance"): a separate record,
+            # never the headline
+            args.precision = 'bf16'
+            rb = train_record(cfg, sub_steps, 3, False)
+            args.precision = 'fp32'
+            rb.update(config={'workload': workload, 'global_batch': cfg['B'], 'parallelism': 'dp1'}, unit='sentences/s',
+                      steps=sub_steps, dtype='bf16',
+                      tolerance='bf16 operands in the compose GEMMs of the level kernels (fp32 accumulate), single-pass TF32 '
+                                'elsewhere: 3e-2 of max on chart vectors, 1e-2 on scores, 1e-1 on weight gradients '
+                                '(tests/test_gpu_chart.py::test_bf16_gemm_mode_has_its_own_tolerance); CKY trees not guaranteed')
+            rb.pop('kernels', None)
+            subs['c2_bf16'] = rb
         if world == 1 and rank == 0:
             subs.update(other_configs(sub_steps, pk))
 
