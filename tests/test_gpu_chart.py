@@ -147,7 +147,8 @@ def _oracle_run(dt, B, n, D, R, share, seed=8, mode='unit'):
 
 
 @pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 20, 400, 36, True),
-                                           (2, 6, 512, 4, True), (2, 5, 768, 0, False)])
+                                           (2, 6, 512, 4, True), (2, 5, 768, 0, False), (2, 4, 800, 4, True),
+                                           (2, 4, 896, 0, True), (3, 5, 36, 0, True), (2, 4, 1024, 0, True)])
 def test_chart_vs_oracle_live(B, n, D, R, share, chains=None):
     """Same seeded inputs through the CUDA path and the CPU oracle, fwd + bwd, at the real hidden size.
 

@@ -95,7 +95,8 @@ def test_fused_level_forward_matches_unfused_chain(B, n, D, R, share, train):
 
 
 @pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 6, 132, 4, True),
-                                           (2, 20, 400, 36, True), (2, 6, 512, 4, True), (2, 5, 768, 0, False)])
+                                           (2, 20, 400, 36, True), (2, 6, 512, 4, True), (2, 5, 768, 0, False), (2, 4, 800, 4, True),
+                                           (2, 4, 896, 0, True), (3, 5, 36, 0, True), (2, 4, 1024, 0, True)])
 def test_wide_level_tiles_stay_parity_green(B, n, D, R, share):
     """Levels that do not fit one wave run with wide column slices (two CTAs per tile at D=400, single tensor-memory
     accumulator, three raw stages, two-pass backward epilogue).  Forced on for every level here: forward and every
