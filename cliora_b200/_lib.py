@@ -23,6 +23,12 @@ _lock = threading.Lock()
 _lib = None
 
 
+class LevelPlan(Structure):
+    _fields_ = [('fused', c_int32), ('splits', c_int32), ('cells', c_int32), ('column_slices', c_int32),
+                ('slice_cols', c_int32), ('umma_n', c_int32), ('cells_per_tile', c_int32), ('tiles', c_int32),
+                ('max_sentences_per_tile', c_int32), ('ring_bytes', c_int32), ('smem_bytes', c_int64)]
+
+
 class Dims(Structure):
     _fields_ = [('B', c_int), ('n', c_int), ('D', c_int), ('R', c_int), ('share', c_int), ('flags', c_int)]
 
@@ -114,6 +120,7 @@ def _declare(lib):
     lib.cliora_split_row_offset.restype = c_int64
     lib.cliora_split_row_offset.argtypes = [c_int, c_int, c_int, c_int]
     lib.cliora_chart_layout.argtypes = [POINTER(Dims), POINTER(Layout)]
+    lib.cliora_level_plan_query.argtypes = [POINTER(Dims), c_int, c_int, c_int, POINTER(LevelPlan)]
     lib.cliora_inside_fwd.argtypes = [POINTER(Dims), POINTER(Weights), vp, vp, vp, vp, vp, vp, st]
     lib.cliora_outside_fwd.argtypes = [POINTER(Dims), POINTER(Weights), vp, vp, vp, vp, vp, st]
     lib.cliora_chart_bwd_begin.argtypes = [POINTER(Dims), vp, vp, vp, vp, vp, st]
@@ -183,7 +190,7 @@ EXPORTS = ['cliora_status_string', 'cliora_last_cuda_error', 'cliora_abi_version
            'cliora_matmul_nn', 'cliora_matmul_tn_scratch_floats', 'cliora_matmul_tn', 'cliora_launch_count',
            'cliora_profile_start', 'cliora_profile_stop', 'cliora_split_tf32', 'cliora_tc_linear', 'cliora_debug_set',
            'cliora_tc_matmul_tn_scratch_floats', 'cliora_tc_matmul_tn', 'cliora_tc_atten_max_fwd', 'cliora_recon_ce_fwd', 'cliora_recon_ce_bwd', 'cliora_tree_spans', 'cliora_span_f1', 'cliora_grounding_eval', 'cliora_gather_regions', 'cliora_adam_table_bytes',
-           'cliora_adam_table_fill', 'cliora_adam_step', 'cliora_debug_ptr']
+           'cliora_adam_table_fill', 'cliora_adam_step', 'cliora_debug_ptr', 'cliora_level_plan_query']
 
 
 def lib():
@@ -235,6 +242,15 @@ def layout(B, n, D, R, share) -> Layout:
     d = Dims(B, n, D, R, 1 if share else 0, 0)
     out = Layout()
     check(lib().cliora_chart_layout(ctypes.byref(d), ctypes.byref(out)), 'cliora_chart_layout')
+    return out
+
+
+def level_plan(B, n, D, R, level, outside=False, backward=False, share=True, flags=0) -> LevelPlan:
+    """Tile plan of one chart level of the fused level kernels (include/cliora_b200.h: cliora_level_plan_query)."""
+    d = Dims(B, n, D, R, 1 if share else 0, flags)
+    out = LevelPlan()
+    check(lib().cliora_level_plan_query(ctypes.byref(d), level, 1 if outside else 0, 1 if backward else 0,
+                                        ctypes.byref(out)), 'cliora_level_plan_query')
     return out
 
 

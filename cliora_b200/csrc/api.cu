@@ -498,6 +498,37 @@ static bool fused_bwd_ok(const Ctx& c) {
   return g_debug[7] == 0 && c.d.n >= 2 && fused_level_ok(c, c.d.n - 1, g);
 }
 
+// Tile plan of one level (shared by the launches and by cliora_level_plan_query): column slices (narrow, or wide when
+// the level cannot be resident in one wave anyway), cells per tile, sentences a tile may span.
+static bool plan_level_fwd(const Ctx& c, int level, bool outside, lvl::LevelGeom& geom, int& G, int& max_sent) {
+  const int n = c.d.n, L = n - level, N = outside ? n - level - 1 : level, R = outside ? 0 : c.d.R;
+  const int cells = c.d.B * L;
+  lvl::LevelGeom narrow;
+  if (!fused_level_ok(c, N, narrow)) return false;
+  geom = narrow;
+  // sentence chains run their level kernels side by side: each aims at its share of the co-resident clusters
+  const int slots = lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) * geom.nc / chain_count(c);
+  widen_if_crowded(c, cells, N, slots, geom);
+  G = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    G = lvl::level_cells_per_tile(cells, N, L, R, geom,
+                                  lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) / chain_count(c),
+                                  max_sent);
+    if (G >= 1 || geom.nc == narrow.nc) break;
+    geom = narrow;                                   // the wide tile does not fit this level's staging: narrow again
+  }
+  return G >= 1;
+}
+static bool plan_level_bwd(const Ctx& c, int level, bool outside, lvl::LevelGeom& geom, int& G, int& max_sent) {
+  const int n = c.d.n, L = n - level, N = outside ? n - level - 1 : level;
+  if (N < 1 || !fused_bwd_ok(c) || !fused_level_ok(c, N, geom)) return false;
+  widen_if_crowded(c, c.d.B * L, N, 148 / chain_count(c), geom);
+  int ms = 0;
+  G = lvl::level_cells_per_tile(c.d.B * L, N, L, 0, geom, (148 / geom.nc) / chain_count(c), ms);
+  max_sent = G > 0 ? (G - 1) / L + 2 : 0;
+  return G >= 1;
+}
+
 static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::LevelGeom& geom_in, const cliora_weights* w,
                            const float* ih, const float* is_, const float* os_, float* chart_h, float* chart_s,
                            const float* obj, const uint8_t* keep, float* ws) {
@@ -508,17 +539,7 @@ static int fused_level_fwd(const Ctx& c, int level, bool outside, const lvl::Lev
   a.R = outside ? 0 : c.d.R;
   a.cells = B * a.L;
   lvl::LevelGeom geom = geom_in;
-  // sentence chains run their level kernels side by side: each aims at its share of the co-resident clusters
-  const int slots = lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) * geom.nc / chain_count(c);
-  widen_if_crowded(c, a.cells, a.N, slots, geom);
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, a.R, geom,
-                                    lvl::max_active_clusters(geom.nc, lvl::level_fwd_smem(geom.n_umma)) / chain_count(c),
-                                    a.max_sent);
-    if (a.G >= 1 || geom.nc == geom_in.nc) break;
-    geom = geom_in;                                  // the wide tile does not fit this level's staging: narrow again
-  }
-  if (a.G < 1) return CLIORA_ERR_UNSUPPORTED;
+  if (!plan_level_fwd(c, level, outside, geom, a.G, a.max_sent)) return CLIORA_ERR_UNSUPPORTED;
   a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
   a.mode = c.lvl_mode;
   a.store_lo = c.lvl_mode == 2 ? 1 : 0;      // modes 1 and 3 never read the lo parts
@@ -577,12 +598,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
   // the fused kernel's prologue does the cell part: text cells always, CLIORA cells when a tile's images fit the rings
   lvl::LevelGeom geom0;
   int G0 = 0, max_sent0 = 0;
-  if (fused) {
-    fused_level_ok(c, g.c.N, geom0);
-    widen_if_crowded(c, B * (n - level), g.c.N, 148 / chain_count(c), geom0);
-    G0 = lvl::level_cells_per_tile(B * (n - level), g.c.N, n - level, 0, geom0, (148 / geom0.nc) / chain_count(c), max_sent0);
-    max_sent0 = G0 > 0 ? (G0 - 1) / (n - level) + 2 : 0;
-  }
+  if (fused && !plan_level_bwd(c, level, OUTSIDE, geom0, G0, max_sent0)) return CLIORA_ERR_UNSUPPORTED;
   const bool vl_fits = VL && D <= 128 * kColT && c.d.R <= 64 && (D % 4) == 0 && G0 > 0 &&
                        (size_t)max_sent0 * c.d.R * D * sizeof(float) <= (size_t)lvl::ring_bytes(geom0.n_umma);
   const bool cells_inline = fused && (!VL || vl_fits) && g_debug[14] == 0;
@@ -602,8 +618,7 @@ static int level_bwd(const Ctx& c, int level, const cliora_weights* w, const flo
     a.nc = geom.nc; a.ncols = geom.ncols; a.n_umma = geom.n_umma;
     a.single_acc = (a.n_umma > lvl::kNarrowUmmaN) ? 1 : 0;
     a.store_lo = c.lvl_mode == 2 ? 1 : 0;
-    int max_sent = 0;
-    a.G = lvl::level_cells_per_tile(a.cells, a.N, a.L, 0, geom, (148 / geom.nc) / chain_count(c), max_sent);
+    a.G = G0;
     a.mode = c.lvl_mode;
     a.no_norm = (c.d.flags & CLIORA_FLAG_NO_NORMALIZE) ? 1 : 0;
     a.outside = OUTSIDE ? 1 : 0;
@@ -715,6 +730,32 @@ int cliora_profile_stop(cliora_profile_row* rows, int max_rows) {
   g_prof.entries.clear();
   cudaGetLastError();
   return nrows;
+}
+
+int cliora_level_plan_query(const cliora_dims* dims, int level, int outside, int backward, cliora_level_plan* plan) {
+  if (plan == nullptr) return CLIORA_ERR_NULL_POINTER;
+  Ctx c;
+  CL_TRY(make_ctx(dims, nullptr, c));
+  const int n = c.d.n;
+  if (level < (outside ? 0 : 1) || level > (outside ? n - 2 : n - 1)) return CLIORA_ERR_BAD_SHAPE;
+  memset(plan, 0, sizeof(*plan));
+  plan->splits = outside ? n - level - 1 : level;
+  plan->cells = c.d.B * (n - level);
+  lvl::LevelGeom geom{};
+  int G = 0, max_sent = 0;
+  const bool ok = backward ? plan_level_bwd(c, level, outside != 0, geom, G, max_sent)
+                           : plan_level_fwd(c, level, outside != 0, geom, G, max_sent);
+  if (!ok) return CLIORA_OK;          // plan->fused == 0: this level runs the unfused kernel chain
+  plan->fused = 1;
+  plan->column_slices = geom.nc;
+  plan->slice_cols = geom.ncols;
+  plan->umma_n = geom.n_umma;
+  plan->cells_per_tile = G;
+  plan->tiles = ceil_div(plan->cells, G);
+  plan->max_sentences_per_tile = max_sent;
+  plan->ring_bytes = lvl::ring_bytes(geom.n_umma);
+  plan->smem_bytes = (int64_t)(backward ? lvl::level_bwd_smem(geom.n_umma) : lvl::level_fwd_smem(geom.n_umma));
+  return CLIORA_OK;
 }
 
 int64_t cliora_num_cells(int n) { return num_cells(n); }

@@ -1545,7 +1545,10 @@ level_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LevelBwdArgs g) 
     }
   }
   // Column passes: a narrow slice (<= 112 columns) fits the rings in one pass, a wide one takes two of 112 + the rest.
-  const int pass_cols = ncols > kNarrowUmmaN ? kNarrowUmmaN : ncols;        // multiple of 16 when it is not everything
+  int pass_cols = ncols > kNarrowUmmaN ? kNarrowUmmaN : ncols;              // multiple of 16 when it is not everything
+  if (ncols > kNarrowUmmaN)                                                 // three [128][pitch] stages must fit the rings
+    while (pass_cols > 16 && 3 * kRows * (((pass_cols >> 2) & 1) ? pass_cols : pass_cols + 4) * 4 > ring_bytes(a.n_umma))
+      pass_cols -= 16;
   const int pch = pass_cols >> 2;
   const int pitch = (pch & 1) ? pass_cols : pass_cols + 4;    // pitch / 4 odd: conflict-free 16-byte row accesses
   float* s_gz = reinterpret_cast<float*>(smem);              // [128][pitch] masked GZ

@@ -349,6 +349,26 @@ int cliora_split_tf32(const float* x, int64_t n, float* out_pair, cliora_stream_
  * 102  1 = narrow tcgen05 tile allocates 256 TMEM columns       103  narrow tile pipeline depth (2, 3 [default], 4)
  * 104  CTA target of the small-GEMM split-K (default 4 x 148)   105  1 = allow the 128x48 tcgen05 tile */
 void cliora_debug_set(int key, int value);
+/* How one chart level is tiled by the fused level kernels (csrc/level_kernels.cuh) for the given problem -- pure host
+ * arithmetic (the occupancy query falls back to a constant without a device), exposed so that the tiling rules can be
+ * checked without a GPU (tests/test_level_plan_cpu.py) and inspected by callers.  `level`: inside 1..n-1, outside
+ * 0..n-2; `backward`: the plan of level_bwd_kernel instead of level_fwd_kernel.  fused == 0: the level runs the unfused
+ * kernel chain (split_build -> GEMM -> cell_aggregate) and the other fields are 0 except splits / cells. */
+typedef struct cliora_level_plan {
+  int32_t fused;
+  int32_t splits;                 /* N: splits per cell at this level */
+  int32_t cells;                  /* B * (n - level) */
+  int32_t column_slices;          /* CTAs that share a tile (forward: the cluster size) */
+  int32_t slice_cols;             /* output columns per CTA */
+  int32_t umma_n;                 /* slice_cols rounded up to 16: the UMMA N */
+  int32_t cells_per_tile;         /* G: whole cells per tile, G * N <= 128 split rows */
+  int32_t tiles;
+  int32_t max_sentences_per_tile;
+  int32_t ring_bytes;             /* operand rings (raw A stages + W2 slice stages), reused by the epilogue */
+  int64_t smem_bytes;             /* dynamic shared memory of the launch */
+} cliora_level_plan;
+int cliora_level_plan_query(const cliora_dims* dims, int level, int outside, int backward, cliora_level_plan* plan);
+
 /* Development only: hands a device buffer to an instrumented kernel (key 0: int64 [ctas][32] timeline of the fused
  * level kernel selected by debug keys 8 (level + 1) and 9 (outside)). */
 void cliora_debug_ptr(int key, void* p);

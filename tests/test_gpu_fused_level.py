@@ -96,7 +96,8 @@ def test_fused_level_forward_matches_unfused_chain(B, n, D, R, share, train):
 
 @pytest.mark.parametrize('B,n,D,R,share', [(4, 10, 400, 36, True), (3, 8, 400, 0, False), (2, 6, 132, 4, True),
                                            (2, 20, 400, 36, True), (2, 6, 512, 4, True), (2, 5, 768, 0, False), (2, 4, 800, 4, True),
-                                           (2, 4, 896, 0, True), (3, 5, 36, 0, True), (2, 4, 1024, 0, True)])
+                                           (2, 4, 896, 0, True), (3, 5, 36, 0, True), (2, 4, 1024, 0, True), (8, 10, 512, 0, True),
+                                           (6, 9, 768, 4, True)])
 def test_wide_level_tiles_stay_parity_green(B, n, D, R, share):
     """Levels that do not fit one wave run with wide column slices (two CTAs per tile at D=400, single tensor-memory
     accumulator, three raw stages, two-pass backward epilogue).  Forced on for every level here: forward and every
@@ -138,3 +139,46 @@ def test_fused_forward_is_stable_across_runs(R, wide):
                 assert rel_err(a, b) < 1e-5
     finally:
         _lib.lib().cliora_debug_set(15, 0)
+
+
+@pytest.mark.parametrize('B,n,D,R', [(8, 10, 512, 0), (8, 10, 512, 36), (16, 12, 400, 36), (6, 9, 768, 0)])
+def test_wide_and_narrow_tiles_agree_on_full_tiles(B, n, D, R):
+    """Full 128-row tiles (the small oracle cases leave most of a tile empty): forward tensors and every gradient of the
+    wide geometry against the narrow one on the same input -- exercises the column-pass staging of the backward
+    epilogue at its largest (a slice of 113..128 columns once overflowed the operand rings there)."""
+    from cliora_b200 import _lib
+    if R:
+        from cliora_b200.net.cliora import DioraMLP
+    else:
+        from cliora_b200.net.diora import DioraMLP
+    torch.manual_seed(11)
+    m = DioraMLP(D).cuda().eval()
+    m.chains = 1
+    x0 = torch.randn(B, n, D, device='cuda')
+    obj0 = 0.05 * torch.randn(B, max(R, 1), D, device='cuda')
+    C = n * (n + 1) // 2
+    ct = [torch.randn(B, C, D, device='cuda'), torch.randn(B, C, 1, device='cuda'),
+          torch.randn(B, C, D, device='cuda'), torch.randn(B, C, 1, device='cuda')]
+    res = {}
+    for name, knob in (('narrow', 1), ('wide', 2)):
+        _lib.lib().cliora_debug_set(15, knob)
+        try:
+            for p in m.parameters():
+                p.grad = None
+            x = x0.clone().requires_grad_()
+            obj = obj0.clone().requires_grad_()
+            m(x, x, obj, obj) if R else m(x, x)
+            outs = [m.inside_h, m.inside_s, m.outside_h, m.outside_s]
+            sum((o * c).sum() for o, c in zip(outs, ct)).backward()
+            res[name] = [o.detach().clone() for o in outs] + [x.grad.clone()] + ([obj.grad.clone()] if R else []) + \
+                        [p.grad.clone() for p in m.parameters() if p.grad is not None]
+        finally:
+            _lib.lib().cliora_debug_set(15, 0)
+    assert len(res['narrow']) == len(res['wide'])
+    # The two geometries differ in accumulation order (single vs. split tensor-memory accumulator, ~2e-6), which flips the
+    # ReLU mask of a few pre-activations that sit within rounding of zero: gradients then move by ~5e-4 of max (the same
+    # effect the oracle tests detect and re-draw for).  A staging overflow or a wrong column pass is an O(1) error.
+    for a, b in zip(res['narrow'][:4], res['wide'][:4]):
+        assert rel_err(b, a) < 1e-4
+    for a, b in zip(res['narrow'][4:], res['wide'][4:]):
+        assert rel_err(b, a) < 3e-3
